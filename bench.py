@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""bench.py — EM throughput of the pLSA hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2] [--impl reference]
+
+A *step* is one EM iteration (E-step + M-step, plus the periodic log-likelihood test of
+plsa_fit_inner, enstop/plsa.py:595-638) over the whole synthetic corpus of the named config
+(default C2: 100k docs x 50k terms, ~10M stored entries, k=20 — SURVEY.md §8d recipe).
+``value`` is nnz*k*K / device time of K steps with corpus and factors resident in HBM
+(CUDA events on the context's stream, max over ranks).  ``e2e`` is the same metric through
+the public API (``PLSA.fit`` at N=1, the ensemble member call at N>1) from HOST buffers:
+validation, seeded init, H2D of the CSR arrays and factors, term-major build, EM, D2H of
+both factors, all inside the timed region.
+
+N > 1 (launched by torch.distributed.run, one rank per GPU): the ensemble path — every rank
+fits one bootstrapped member (enstop_.py:84-114) of the same corpus, no data-path
+collective; the NCCL gather of the topic matrices (enstop_.py:231) is timed separately.
+torch is used for the launcher's rendezvous/barrier only.
+
+``--impl reference`` times the CPU restatement of the reference algorithm (oracle/, C +
+OpenMP mirroring numba's prange/serial structure) on the host cores for the same metric.
+"""
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "EM iters/sec (nnz*k/s) at k=%d"
+UNIT = "nnz*k/s"
+SPEC_HBM_GBS = 8000.0
+FALLBACK_HBM_GBS = 6650.0
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        exe = shutil.which("nvidia-smi")
+        if not exe:
+            return
+        try:
+            self.proc = subprocess.Popen(
+                [exe, "-i", str(self.device), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ts, line in self.lines:
+            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                  "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    return rank, world, local
+
+
+class Plumbing:
+    """Launcher rendezvous: barrier, max-reduce and a small broadcast.  torch.distributed
+    (gloo, CPU tensors) when launched by torchrun; trivial at world size 1."""
+
+    def __init__(self, rank, world):
+        self.rank, self.world = rank, world
+        self.dist = None
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            self.torch = torch
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group(backend="gloo", rank=rank, world_size=world)
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+
+    def max(self, x):
+        if not self.dist:
+            return float(x)
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def sum(self, x):
+        if not self.dist:
+            return float(x)
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t[0])
+
+    def bcast_bytes(self, payload):
+        if not self.dist:
+            return payload
+        box = [payload]
+        self.dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def close(self):
+        if self.dist:
+            self.dist.destroy_process_group()
+
+
+def algorithmic_bytes(n, m, nnz, k):
+    """per EM iteration 8*nnz + 4*(n+1) + 8*k*(n+m); E-step reads
+    8*nnz + 4*(n+1) + 4*k*(n+m)."""
+    return (8 * nnz + 4 * (n + 1) + 8 * k * (n + m), 8 * nnz + 4 * (n + 1) + 4 * k * (n + m))
+
+
+def cpu_port_run(X, k, n_iter, seed=42):
+    """The oracle's float32 restatement of plsa_fit_inner on the host cores.
+    Returns seconds for n_iter EM iterations (tolerance 0: all of them run)."""
+    from oracle import oracle
+    rng = np.random.RandomState(seed)
+    n, m = X.shape
+    pzd, pwz = oracle.plsa_init_random(n, m, k, rng)
+    pzd = np.ascontiguousarray(pzd, dtype=np.float32)
+    pwz = np.ascontiguousarray(pwz, dtype=np.float32)
+    A = X.tocoo()
+    rows = np.ascontiguousarray(A.row, dtype=np.int32)
+    cols = np.ascontiguousarray(A.col, dtype=np.int32)
+    vals = np.ascontiguousarray(A.data, dtype=np.float32)
+    sw = np.ones(n, dtype=np.float32)
+    t0 = time.perf_counter()
+    iters, _ = oracle.fit_inner(rows, cols, vals, pwz, pzd, sw, n_iter=n_iter,
+                                n_iter_per_test=10, tolerance=0.0)
+    dt = time.perf_counter() - t0
+    assert iters == n_iter
+    return dt
+
+
+def pick_cpu_threads(X, k):
+    """Credit the CPU path with its best thread count (the M-step scatter is serial, so more
+    threads mostly add OpenMP noise — BASELINE.md §2): probe {1, n/2, n} on a row slice."""
+    from oracle import oracle
+    ncpu = os.cpu_count() or 1
+    probe = X[: max(64, X.shape[0] // 25)]
+    best_t, best = 1, None
+    for t in sorted({1, max(1, ncpu // 2), ncpu}):
+        oracle.set_num_threads(t)
+        cpu_port_run(probe, k, 1)
+        dt = min(cpu_port_run(probe, k, 2) for _ in range(2))
+        if best is None or dt < best:
+            best_t, best = t, dt
+    return oracle.set_num_threads(best_t)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port) on the host cores."""
+    if rank != 0:
+        return
+    from enstop_b200 import synth
+    from oracle import oracle
+    oracle.build()
+    cfg = synth.CONFIGS[args.config]
+    X, info = synth.make_config(args.config, return_info=True)
+    n, m = X.shape
+    k = cfg["k"]
+    budget_s = 150.0
+    cores = pick_cpu_threads(X, k)
+    # bound the sample: probe one iteration on a 1/16 row slice, then size the slice
+    probe = X[: max(64, n // 16)]
+    cpu_port_run(probe, k, 1)  # warm (page faults, OpenMP pool)
+    per_iter_probe = cpu_port_run(probe, k, 2) / 2.0
+    per_iter_full = per_iter_probe * (X.nnz / max(1, probe.nnz))
+    total_iters = args.steps + args.warmup
+    frac = min(1.0, budget_s / max(1e-9, per_iter_full * total_iters))
+    rows = n if frac >= 1.0 else max(64, int(n * frac))
+    Xs = X[:rows]
+    if args.warmup > 0:
+        cpu_port_run(Xs, k, min(args.warmup, 2))
+    dt = cpu_port_run(Xs, k, args.steps)
+    value = Xs.nnz * k * args.steps / dt
+    sample = ("%d EM iterations of plsa_fit_inner (oracle C port: OpenMP E-step/log-likelihood, "
+              "serial M-step scatter as enstop/plsa.py:182) on the first %d of %d documents "
+              "(%d of %d stored entries) of %s" % (args.steps, rows, n, Xs.nnz, X.nnz, args.config))
+    line = {
+        "impl": "reference", "metric": METRIC % k, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, cfg, info), "n_docs": n, "n_terms": m,
+                   "nnz": int(X.nnz), "k": k, "sample_nnz": int(Xs.nnz)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_name(name, cfg, info):
+    return ("%s: PLSA(n_components=%d) EM on synthetic Zipf(s=1) token-sampled CSR %dx%d, "
+            "%d stored entries (seed %d, %d tokens)"
+            % (name, cfg["k"], cfg["n"], cfg["m"], info["nnz"], info["seed"], info["tokens"]))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C5"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-iters", type=int, default=10)
+    ap.add_argument("--profile-iters", type=int, default=20)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank, world, local = dist_env()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    from enstop_b200 import _lib, plsa, synth
+    if _lib.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    plumb = Plumbing(rank, world)
+    device = local % _lib.device_count()
+    cfg = synth.CONFIGS[args.config]
+    k = cfg["k"]
+    X, info = synth.make_config(args.config, return_info=True)
+    n, m = X.shape
+    peak, peak_src = load_peaks()
+
+    # N > 1: this rank's ensemble member = bootstrap resample of the corpus (enstop_.py:86-88)
+    member_seed = 1000 + rank
+    ctx = _lib.Context(device)
+    ctx.upload_csr(X)
+    if world > 1:
+        idx = np.random.RandomState(member_seed).randint(0, n, size=n)
+        ctx.bootstrap(idx)
+    n_fit, m_fit, nnz_fit = ctx.shape
+    rng = np.random.RandomState(42 + rank)
+    import types
+    pzd0, pwz0 = plsa.plsa_init(types.SimpleNamespace(shape=(n_fit, m_fit)), k, "random", rng)
+    pzd0 = pzd0.astype(np.float32)
+    pwz0 = pwz0.astype(np.float32)
+    ctx.set_factors(pzd0, pwz0)
+    ctx.set_sample_weight(None)
+
+    # ---- device-timed K steps (inputs resident in HBM) -----------------------------------
+    ctx.em(args.warmup, n_iter_per_test=10, tolerance=0.0)          # warm-up, untimed
+    sampler = ClockSampler(device)
+    sampler.start()
+    time.sleep(0.25)
+    plumb.barrier()
+    launches0 = ctx.launches
+    t0 = time.time()
+    iters, trace = ctx.em(args.steps, n_iter_per_test=10, tolerance=0.0)
+    em_ms_local = ctx.last_em_ms
+    t1 = time.time()
+    plumb.barrier()
+    launches = ctx.launches - launches0
+    clocks = sampler.stop(t0, t1)
+    assert iters == args.steps
+    em_ms = plumb.max(em_ms_local)
+    total_units = plumb.sum(float(nnz_fit) * k * args.steps)
+    value = total_units / (em_ms * 1e-3)
+
+    # ---- per-kernel durations, live CUDA events (profiling mode adds event overhead, so it
+    # is a separate short run; the kernels and their inputs are the same) ------------------
+    ctx.set_profiling(True)
+    ctx.em(args.profile_iters, n_iter_per_test=10, tolerance=0.0)
+    prof = ctx.profile()
+    ctx.set_profiling(False)
+    b_iter, b_e = algorithmic_bytes(n_fit, m_fit, nnz_fit, k)
+    doc_ms = prof["doc_pass"]["ms"] / max(1, prof["doc_pass"]["launches"])
+    word_ms = prof["word_pass"]["ms"] / max(1, prof["word_pass"]["launches"])
+    achieved = b_e / (doc_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "row_pass_kernel<doc> (E-step + P(z|d) M-step)",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "peak_source": peak_src, "traffic": None,
+        "algorithmic_bytes_per_launch": b_e, "avg_launch_ms": doc_ms,
+        "frac_of_spec_8TBs": achieved / SPEC_HBM_GBS,
+        "word_pass": {"avg_launch_ms": word_ms,
+                      "achieved": b_e / (word_ms * 1e-3) / 1e9 if word_ms > 0 else None},
+        "iteration": {"algorithmic_bytes": b_iter, "ms": em_ms_local / args.steps,
+                      "achieved": b_iter / (em_ms_local / args.steps * 1e-3) / 1e9,
+                      "frac": b_iter / (em_ms_local / args.steps * 1e-3) / 1e9 / peak},
+        "kernel_ms_per_iter": {s: prof[s]["ms"] / args.profile_iters for s in prof},
+    }
+
+    # ---- end to end through the public API, HOST buffers ---------------------------------
+    sw = np.ones(n_fit, dtype=np.float32)
+    if world == 1:
+        def e2e_call(n_iter):
+            model = plsa.PLSA(n_components=k, n_iter=n_iter, tolerance=0.0, random_state=42,
+                              device=device)
+            model.fit(X)
+            return model
+        Xe = X
+    else:
+        Xe = X[np.random.RandomState(member_seed).randint(0, n, size=n)]
+
+        def e2e_call(n_iter):
+            return plsa.plsa_fit(Xe, k, sw, n_iter=n_iter, tolerance=0.0,
+                                 random_state=42 + rank, device=device)
+    e2e_call(3)                                                       # warm-up
+    plumb.barrier()
+    w0 = time.perf_counter()
+    e2e_call(args.steps)
+    e2e_s_local = time.perf_counter() - w0
+    plumb.barrier()
+    e2e_s = plumb.max(e2e_s_local)
+    e2e_value = plumb.sum(float(Xe.nnz) * k * args.steps) / e2e_s
+    h2d = (4 * (n_fit + 1) + 8 * Xe.nnz + 4 * k * (n_fit + m_fit) + 4 * n_fit) / args.steps
+    d2h = (4 * k * (n_fit + m_fit)) / args.steps
+
+    # ---- ensemble gather over NCCL (N > 1), outside the EM timing -------------------------
+    gather_ms = None
+    if world > 1:
+        uid = plumb.bcast_bytes(_lib.Comm.unique_id() if rank == 0 else None)
+        comm = _lib.Comm(device, world, rank, uid)
+        ctx.stash_topics(0, 1)
+        plumb.barrier()
+        g0 = time.perf_counter()
+        stacked = comm.gather_topics(ctx, [1] * world, root=0)
+        plumb.barrier()
+        gather_ms = (time.perf_counter() - g0) * 1e3
+        if rank == 0:
+            assert stacked.shape == (world * k, m_fit)
+            assert np.allclose(stacked.sum(axis=1), 1.0, atol=1e-4)
+        comm.close()
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ----------------------------------------
+    cpu = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        from oracle import oracle
+        oracle.build()
+        cores = pick_cpu_threads(X, k)
+        dt = cpu_port_run(X, k, args.cpu_iters)
+        cpu = {"value": X.nnz * k * args.cpu_iters / dt, "unit": UNIT,
+               "cores": cores, "host_cores": os.cpu_count() or 1, "kind": "port",
+               "ms_per_iter": 1e3 * dt / args.cpu_iters,
+               "sample": "%d EM iterations of plsa_fit_inner on the full %s corpus (oracle C "
+                         "port: OpenMP E-step/log-likelihood, serial M-step scatter as "
+                         "enstop/plsa.py:182)" % (args.cpu_iters, args.config)}
+
+    ctx.close()
+    if rank == 0:
+        line = {
+            "metric": METRIC % k, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": em_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args.config, cfg, info),
+                       "n_docs": n, "n_terms": m, "nnz": int(X.nnz), "k": k,
+                       "parallelism": "single fit" if world == 1 else
+                       "ensemble members sharded one per GPU (bootstrap resample per rank)",
+                       "l2": "working set (doc-major + term-major CSR + factors, %.0f MB) exceeds "
+                             "the 126 MB L2; no flush" % ((16 * nnz_fit + 16 * k * (n_fit + m_fit)) / 1e6),
+                       "em_iters_per_s": args.steps / (em_ms * 1e-3),
+                       "ll_first_last": [float(trace[0]), float(trace[-1])]},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "seconds": e2e_s,
+                    "call": "PLSA(n_components=%d, n_iter=%d, tolerance=0).fit(X)" % (k, args.steps)
+                    if world == 1 else "plsa_fit(bootstrap member) per rank"},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if gather_ms is not None:
+            line["ensemble_gather_ms"] = gather_ms
+        print(json.dumps(line))
+    plumb.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,347 @@
+"""ctypes binding of ``libplsa_b200.so`` (C ABI: ``include/plsa_b200.h``).
+
+The shared library is built in-tree by :func:`build` (nvcc, sm_100a only) and loaded with
+``ctypes.CDLL``, which releases the GIL for the duration of every call — the same property
+the reference relies on when it runs ``nogil`` numba kernels from ensemble worker threads
+(enstop/enstop_.py:209-217).
+
+There is no CPU fallback: if the library cannot be loaded or no CUDA device is present,
+every entry point raises.
+"""
+import ctypes
+import os
+import shutil
+import subprocess
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+SO_PATH = os.path.join(_HERE, "libplsa_b200.so")
+SOURCES = [os.path.join(_HERE, "csrc", "plsa_b200.cu")]
+HEADERS = [os.path.join(_HERE, "csrc", "plsa_kernels.cuh"),
+           os.path.join(ROOT, "include", "plsa_b200.h")]
+
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-diag-suppress", "550"]
+
+PLSA_OK, PLSA_EINVAL, PLSA_ECUDA, PLSA_ENOMEM, PLSA_ENCCL = 0, 1, 2, 3, 4
+PROF_SLOTS = ("doc_pass", "word_pass", "fixup", "normalize", "loglik")
+
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+_f32p = ctypes.POINTER(ctypes.c_float)
+_f64p = ctypes.POINTER(ctypes.c_double)
+_ctx = ctypes.c_void_p
+_i32, _i64, _f32, _f64 = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double
+
+# name -> (restype, argtypes); every symbol include/plsa_b200.h declares
+SIGNATURES = {
+    "plsa_version": (ctypes.c_int, []),
+    "plsa_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "plsa_last_error": (ctypes.c_char_p, [_ctx]),
+    "plsa_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_ctx)]),
+    "plsa_ctx_destroy": (ctypes.c_int, [_ctx]),
+    "plsa_upload_csr": (ctypes.c_int, [_ctx, _i32p, _i32p, _f32p, _i64, _i64, _i64]),
+    "plsa_upload_coo": (ctypes.c_int, [_ctx, _i32p, _i32p, _f32p, _i64, _i64, _i64]),
+    "plsa_bootstrap": (ctypes.c_int, [_ctx, _i32p, _i64]),
+    "plsa_corpus_shape": (ctypes.c_int, [_ctx, _i64p, _i64p, _i64p]),
+    "plsa_set_factors": (ctypes.c_int, [_ctx, _f32p, _f32p, _i32]),
+    "plsa_set_sample_weight": (ctypes.c_int, [_ctx, _f32p]),
+    "plsa_get_factors": (ctypes.c_int, [_ctx, _f32p, _f32p]),
+    "plsa_stash_topics": (ctypes.c_int, [_ctx, _i32, _i32]),
+    "plsa_topics_device": (ctypes.c_int, [_ctx, ctypes.POINTER(ctypes.c_void_p), _i64p]),
+    "plsa_em": (ctypes.c_int, [_ctx, _i32, _i32, _f64, _f32, _i32, _i32, _i32p, _f64p, _i32,
+                               _i32p]),
+    "plsa_log_likelihood": (ctypes.c_int, [_ctx, _f64p]),
+    "plsa_last_em_ms": (ctypes.c_int, [_ctx, _f32p]),
+    "plsa_set_profiling": (ctypes.c_int, [_ctx, _i32]),
+    "plsa_get_profile": (ctypes.c_int, [_ctx, _f64p, _i64p]),
+    "plsa_launch_count": (ctypes.c_int, [_ctx, _i64p]),
+    "plsa_set_option": (ctypes.c_int, [_ctx, ctypes.c_char_p, _i64]),
+    "plsa_b200_fit_inner": (ctypes.c_int, [_i32p, _i32p, _f32p, _i64, _f32p, _f32p, _f32p, _i64,
+                                           _i64, _i32, _i32, _i32, _f64, _f32, _i32, _i32, _i32p]),
+    "plsa_b200_refit_inner": (ctypes.c_int, [_i32p, _i32p, _f32p, _i64, _f32p, _f32p, _f32p,
+                                             _i64, _i64, _i32, _i32, _i32, _f64, _f32, _i32,
+                                             _i32p]),
+    "plsa_gather_topics": (ctypes.c_int, [ctypes.POINTER(_ctx), _i32, _i32p, _f32p]),
+    "plsa_nccl_unique_id": (ctypes.c_int, [ctypes.c_char_p]),
+    "plsa_comm_create": (ctypes.c_int, [ctypes.c_int, _i32, _i32, ctypes.c_char_p,
+                                        ctypes.POINTER(ctypes.c_void_p)]),
+    "plsa_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "plsa_comm_gather_topics": (ctypes.c_int, [ctypes.c_void_p, _ctx, _i32p, _i32, _f32p]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class PlsaError(RuntimeError):
+    """A call into libplsa_b200.so failed (message from plsa_last_error)."""
+
+
+def nvcc_path():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise PlsaError("nvcc not found; cannot build libplsa_b200.so")
+
+
+def needs_build():
+    if not os.path.exists(SO_PATH):
+        return True
+    t = os.path.getmtime(SO_PATH)
+    return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA extension in-tree for sm_100a.  Returns the path of the .so."""
+    if not force and not needs_build():
+        return SO_PATH
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", SO_PATH] + SOURCES + ["-ldl"]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+    if res.returncode != 0:
+        raise PlsaError("nvcc failed:\n" + res.stdout)
+    if verbose:
+        print(res.stdout)
+    return SO_PATH
+
+
+def lib():
+    """The loaded library.  Raises PlsaError if it is missing — never falls back to CPU."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(SO_PATH):
+            raise PlsaError(
+                "libplsa_b200.so is not built (run `python -c 'import __graft_entry__ as g; "
+                "g.build()'` or enstop_b200._lib.build()); there is no CPU fallback")
+        try:
+            L = ctypes.CDLL(SO_PATH)
+        except OSError as exc:
+            raise PlsaError("cannot load %s: %s" % (SO_PATH, exc)) from exc
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc, ctx=None):
+    if rc != PLSA_OK:
+        msg = lib().plsa_last_error(ctx)
+        msg = msg.decode("utf-8", "replace") if msg else "unknown error"
+        kind = {PLSA_EINVAL: "invalid argument", PLSA_ECUDA: "CUDA error",
+                PLSA_ENOMEM: "out of memory", PLSA_ENCCL: "NCCL error"}.get(rc, "error %d" % rc)
+        raise PlsaError("libplsa_b200: %s: %s" % (kind, msg))
+
+
+def device_count():
+    n = ctypes.c_int(0)
+    rc = lib().plsa_device_count(ctypes.byref(n))
+    return n.value if rc == PLSA_OK else 0
+
+
+def _ptr(a, ct):
+    return a.ctypes.data_as(ct) if a is not None else None
+
+
+def _as(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Context:
+    """One corpus resident on one GPU (opaque ``plsa_ctx``).  Not thread-safe; use one per
+    worker thread, as the reference's ensemble does with its numba kernels."""
+
+    def __init__(self, device=0):
+        self._h = _ctx()
+        self._L = lib()
+        check(self._L.plsa_ctx_create(int(device), ctypes.byref(self._h)))
+        self.device = int(device)
+        self.k = 0
+
+    def close(self):
+        if self._h:
+            self._L.plsa_ctx_destroy(self._h)
+            self._h = _ctx()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- corpus -----------------------------------------------------------------------
+    def upload_csr(self, X):
+        """X: scipy CSR matrix (any value dtype; converted to float32 as plsa.py:714)."""
+        indptr = _as(X.indptr, np.int32)
+        indices = _as(X.indices, np.int32)
+        data = _as(X.data, np.float32)
+        n, m = X.shape
+        check(self._L.plsa_upload_csr(self._h, _ptr(indptr, _i32p), _ptr(indices, _i32p),
+                                      _ptr(data, _f32p), n, m, data.shape[0]), self._h)
+
+    def upload_coo(self, rows, cols, vals, n, m):
+        rows, cols, vals = _as(rows, np.int32), _as(cols, np.int32), _as(vals, np.float32)
+        check(self._L.plsa_upload_coo(self._h, _ptr(rows, _i32p), _ptr(cols, _i32p),
+                                      _ptr(vals, _f32p), n, m, vals.shape[0]), self._h)
+
+    def bootstrap(self, row_idx):
+        if row_idx is None:
+            check(self._L.plsa_bootstrap(self._h, None, 0), self._h)
+            return
+        idx = _as(row_idx, np.int32)
+        check(self._L.plsa_bootstrap(self._h, _ptr(idx, _i32p), idx.shape[0]), self._h)
+
+    @property
+    def shape(self):
+        n, m, z = _i64(0), _i64(0), _i64(0)
+        check(self._L.plsa_corpus_shape(self._h, ctypes.byref(n), ctypes.byref(m),
+                                        ctypes.byref(z)), self._h)
+        return n.value, m.value, z.value
+
+    # -- model ------------------------------------------------------------------------
+    def set_factors(self, p_z_given_d, p_w_given_z):
+        pzd, pwz = _as(p_z_given_d, np.float32), _as(p_w_given_z, np.float32)
+        n, m, _ = self.shape
+        k = pwz.shape[0]
+        if pzd.shape != (n, k) or pwz.shape != (k, m):
+            raise ValueError("factor shapes %s, %s do not match corpus %s with k=%d"
+                             % (pzd.shape, pwz.shape, (n, m), k))
+        check(self._L.plsa_set_factors(self._h, _ptr(pzd, _f32p), _ptr(pwz, _f32p), k), self._h)
+        self.k = k
+
+    def set_sample_weight(self, sample_weight):
+        if sample_weight is None:
+            check(self._L.plsa_set_sample_weight(self._h, None), self._h)
+            return
+        sw = _as(sample_weight, np.float32)
+        if sw.shape != (self.shape[0],):
+            raise ValueError("sample_weight.shape == {}, expected {}!".format(
+                sw.shape, (self.shape[0],)))
+        check(self._L.plsa_set_sample_weight(self._h, _ptr(sw, _f32p)), self._h)
+
+    def get_factors(self, want_pzd=True, want_pwz=True):
+        n, m, _ = self.shape
+        pzd = np.empty((n, self.k), dtype=np.float32) if want_pzd else None
+        pwz = np.empty((self.k, m), dtype=np.float32) if want_pwz else None
+        check(self._L.plsa_get_factors(self._h, _ptr(pzd, _f32p), _ptr(pwz, _f32p)), self._h)
+        return pzd, pwz
+
+    # -- EM ---------------------------------------------------------------------------
+    def em(self, n_iter, n_iter_per_test=10, tolerance=0.001, e_step_thresh=1e-32, refit=False,
+           use_sample_weights=False, trace=False):
+        """Run the loop of plsa_fit_inner / plsa_refit_inner.  Returns (iters_run, ll_trace)."""
+        iters, n_ll = _i32(0), _i32(0)
+        cap = int(n_iter) // max(1, int(n_iter_per_test)) + 3
+        buf = np.zeros(cap, dtype=np.float64) if (trace or not refit) else None
+        check(self._L.plsa_em(self._h, int(n_iter), int(n_iter_per_test), float(tolerance),
+                              float(e_step_thresh), int(bool(refit)),
+                              int(bool(use_sample_weights)), ctypes.byref(iters),
+                              _ptr(buf, _f64p), cap if buf is not None else 0,
+                              ctypes.byref(n_ll)), self._h)
+        ll = buf[: min(cap, n_ll.value)].copy() if buf is not None else np.zeros(0)
+        return iters.value, ll
+
+    def log_likelihood(self):
+        out = _f64(0.0)
+        check(self._L.plsa_log_likelihood(self._h, ctypes.byref(out)), self._h)
+        return out.value
+
+    # -- measurement --------------------------------------------------------------------
+    @property
+    def last_em_ms(self):
+        ms = _f32(0.0)
+        check(self._L.plsa_last_em_ms(self._h, ctypes.byref(ms)), self._h)
+        return ms.value
+
+    def set_profiling(self, on=True):
+        check(self._L.plsa_set_profiling(self._h, int(bool(on))), self._h)
+
+    def profile(self):
+        ms = np.zeros(len(PROF_SLOTS), dtype=np.float64)
+        cnt = np.zeros(len(PROF_SLOTS), dtype=np.int64)
+        check(self._L.plsa_get_profile(self._h, _ptr(ms, _f64p), _ptr(cnt, _i64p)), self._h)
+        return {name: {"ms": float(ms[i]), "launches": int(cnt[i])}
+                for i, name in enumerate(PROF_SLOTS)}
+
+    @property
+    def launches(self):
+        out = _i64(0)
+        check(self._L.plsa_launch_count(self._h, ctypes.byref(out)), self._h)
+        return out.value
+
+    def set_option(self, name, value):
+        check(self._L.plsa_set_option(self._h, name.encode(), int(value)), self._h)
+
+    def stash_topics(self, slot, n_slots):
+        check(self._L.plsa_stash_topics(self._h, int(slot), int(n_slots)), self._h)
+
+
+def gather_topics(contexts, n_slots):
+    """np.vstack of the stashed P(w|z) of every context (enstop_.py:231): slots
+    [0, n_slots[i]) of contexts[i], context order then slot order, moved to contexts[0]'s
+    device over NCCL send/recv and copied to the host once."""
+    L = lib()
+    k = contexts[0].k
+    m = contexts[0].shape[1]
+    counts = np.ascontiguousarray(n_slots, dtype=np.int32)
+    out = np.empty((int(counts.sum()) * k, m), dtype=np.float32)
+    arr = (_ctx * len(contexts))(*[c._h for c in contexts])
+    check(L.plsa_gather_topics(arr, len(contexts), _ptr(counts, _i32p), _ptr(out, _f32p)))
+    return out
+
+
+class Comm:
+    """One rank of a one-process-per-GPU job (NCCL communicator behind ``plsa_comm``)."""
+
+    def __init__(self, device, n_ranks, rank, unique_id):
+        self._L = lib()
+        self._h = ctypes.c_void_p()
+        self.n_ranks, self.rank = int(n_ranks), int(rank)
+        check(self._L.plsa_comm_create(int(device), self.n_ranks, self.rank, unique_id,
+                                       ctypes.byref(self._h)))
+
+    @staticmethod
+    def unique_id():
+        buf = ctypes.create_string_buffer(128)
+        check(lib().plsa_nccl_unique_id(buf))
+        return buf.raw
+
+    def gather_topics(self, ctx, n_per_rank, root=0):
+        counts = np.ascontiguousarray(n_per_rank, dtype=np.int32)
+        out = None
+        if self.rank == root:
+            out = np.empty((int(counts.sum()) * ctx.k, ctx.shape[1]), dtype=np.float32)
+        check(self._L.plsa_comm_gather_topics(self._h, ctx._h, _ptr(counts, _i32p), int(root),
+                                              _ptr(out, _f32p)), ctx._h)
+        return out
+
+    def close(self):
+        if self._h:
+            self._L.plsa_comm_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

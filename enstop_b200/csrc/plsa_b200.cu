@@ -1,0 +1,1330 @@
+/*
+ * plsa_b200.cu — host side of libplsa_b200.so: the C ABI declared in include/plsa_b200.h.
+ *
+ * Replaces the raw-array seam of the reference (enstop/plsa.py:516-640 plsa_fit_inner,
+ * :819-920 plsa_refit_inner) and keeps a corpus resident on one B200 for repeated fits
+ * (ensemble members, transform).  Device code is in plsa_kernels.cuh.
+ *
+ * Data layout in HBM (per context):
+ *   doc-major CSR   indptr[n+1] i32, cols[nnz] i32, vals[nnz] f32      (working corpus)
+ *   term-major CSR  rows[nnz] i32, vals[nnz] f32 (+ vals*sample_weight) (built on device)
+ *   P(z|d)          A[2][n, strideA] f32, ping-pong
+ *   P(w|z)^T        B[2][m, strideB] f32, ping-pong, RAW column-unnormalised sums;
+ *                   scale[kp] = 1 / column sum is folded in by the next pass
+ *   work items      one per row, rows longer than `chunk` entries are split
+ */
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/plsa_b200.h"
+#include "plsa_kernels.cuh"
+
+using namespace plsa;
+
+#define API extern "C" __attribute__((visibility("default")))
+
+static thread_local std::string g_err;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Corpus {
+    int64_t n = 0, m = 0, nnz = 0;
+    DevBuf indptr, cols, vals;
+    std::vector<int32_t> h_indptr;
+};
+
+struct ItemSet {
+    DevBuf items, split_rows, slot_begin;
+    int64_t n_items = 0;
+    int32_t n_split = 0, n_slots = 0;
+    bool ready = false;
+};
+
+} // namespace
+
+struct plsa_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+
+    Corpus base, boot;
+    bool use_boot = false;
+    Corpus &cur() { return use_boot ? boot : base; }
+    const Corpus &cur() const { return use_boot ? boot : base; }
+
+    /* term-major copy of the working corpus */
+    DevBuf t_rows, t_vals, t_valsw, t_scratch;
+    std::vector<int32_t> h_tindptr;
+    bool t_ready = false, t_weighted_ready = false;
+
+    ItemSet doc_items, term_items;
+    int64_t chunk = 2048;
+
+    /* model */
+    int32_t k = 0, kp = 0, strideA = 0, strideB = 0;
+    DevBuf A[2], B[2], scale, ones, colnorm, colpart, partialA, partialB;
+    DevBuf sw, ll_part, ll_out, stage, topics_dev;
+    int32_t stash_slots = 0;
+    size_t stash_per = 0;
+    int curA = 0, curB = 0;
+    bool have_factors = false, have_sw = false;
+
+    /* measurement */
+    float last_em_ms = 0.f;
+    int64_t launches = 0;
+    bool profiling = false;
+    double prof_ms[PLSA_PROF_SLOTS] = {0, 0, 0, 0, 0};
+    int64_t prof_n[PLSA_PROF_SLOTS] = {0, 0, 0, 0, 0};
+    struct ProfRec { int slot; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_pending;
+    std::vector<cudaEvent_t> ev_pool;
+
+    int fail(int code, const std::string &msg)
+    {
+        err = msg;
+        g_err = msg;
+        return code;
+    }
+};
+
+#define CK(expr)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return ctx->fail(e_ == cudaErrorMemoryAllocation ? PLSA_ENOMEM : PLSA_ECUDA,      \
+                             std::string(#expr) + ": " + cudaGetErrorString(e_));            \
+    } while (0)
+
+#define CHECK_CTX(ctx)                                                                        \
+    do {                                                                                      \
+        if (!(ctx)) {                                                                         \
+            g_err = "null context";                                                           \
+            return PLSA_EINVAL;                                                               \
+        }                                                                                     \
+        cudaError_t e_ = cudaSetDevice((ctx)->device);                                        \
+        if (e_ != cudaSuccess)                                                                \
+            return (ctx)->fail(PLSA_ECUDA, std::string("cudaSetDevice: ") +                   \
+                                               cudaGetErrorString(e_));                       \
+    } while (0)
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+/* ---- profiling helpers ------------------------------------------------------------------- */
+static cudaEvent_t get_event(plsa_ctx *ctx)
+{
+    if (!ctx->ev_pool.empty()) {
+        cudaEvent_t e = ctx->ev_pool.back();
+        ctx->ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct ProfScope {
+    plsa_ctx *ctx;
+    int slot;
+    cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(plsa_ctx *c, int s) : ctx(c), slot(s)
+    {
+        if (ctx->profiling) {
+            a = get_event(ctx);
+            b = get_event(ctx);
+            cudaEventRecord(a, ctx->stream);
+        }
+    }
+    ~ProfScope()
+    {
+        if (ctx->profiling) {
+            cudaEventRecord(b, ctx->stream);
+            ctx->prof_pending.push_back({slot, a, b});
+        }
+    }
+};
+
+static void prof_collect(plsa_ctx *ctx)
+{
+    for (auto &r : ctx->prof_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            ctx->prof_ms[r.slot] += ms;
+            ctx->prof_n[r.slot] += 1;
+        }
+        ctx->ev_pool.push_back(r.a);
+        ctx->ev_pool.push_back(r.b);
+    }
+    ctx->prof_pending.clear();
+}
+
+/* ---- kernel dispatch ------------------------------------------------------------------------ */
+typedef void (*pass_fn)(const PassArgs);
+
+template <int G, int KV> static pass_fn pick_mode(int mode)
+{
+    switch (mode) {
+    case MODE_DOC: return row_pass_kernel<G, KV, MODE_DOC>;
+    case MODE_TERM: return row_pass_kernel<G, KV, MODE_TERM>;
+    default: return row_pass_kernel<G, KV, MODE_LOGLIK>;
+    }
+}
+
+static pass_fn pick_kernel(int kp, int mode)
+{
+    const int nv = kp / 4; /* float4 vectors per factor row */
+    switch (nv) {
+    case 1: return pick_mode<1, 1>(mode);
+    case 2: return pick_mode<2, 1>(mode);
+    case 3: return pick_mode<3, 1>(mode);
+    case 4: return pick_mode<4, 1>(mode);
+    case 5: return pick_mode<5, 1>(mode);
+    case 6: return pick_mode<6, 1>(mode);
+    case 7: return pick_mode<7, 1>(mode);
+    case 8: return pick_mode<8, 1>(mode);
+    default: break;
+    }
+    if (nv <= 16) return pick_mode<16, 1>(mode);
+    if (nv <= 32) return pick_mode<32, 1>(mode);
+    if (nv <= 64) return pick_mode<32, 2>(mode);
+    if (nv <= 128) return pick_mode<32, 4>(mode);
+    return pick_mode<32, 8>(mode);
+}
+
+static int launch_pass(plsa_ctx *ctx, int mode, const PassArgs &a)
+{
+    if (a.n_items == 0) return PLSA_OK;
+    pass_fn fn = pick_kernel(a.kp, mode);
+    const int warps = 8;
+    const int64_t grid = cdiv(a.n_items, warps);
+    fn<<<(unsigned)grid, warps * 32, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return PLSA_OK;
+}
+
+/* ---- work items --------------------------------------------------------------------------- */
+/* One item per row; rows longer than `chunk` stored entries are cut into chunks whose
+ * partial sums are added in order by fixup_kernel.  Items are ordered longest first
+ * (counting sort) so that the 8 warps of a CTA carry rows of similar length and the
+ * hardware CTA scheduler sees the heavy work first. */
+static int build_items(plsa_ctx *ctx, const std::vector<int32_t> &indptr, int64_t rows,
+                       ItemSet &out)
+{
+    const int64_t chunk = ctx->chunk;
+    std::vector<Item> items;
+    items.reserve((size_t)rows + 1024);
+    std::vector<int32_t> split_rows, slot_begin;
+    slot_begin.push_back(0);
+    int32_t slots = 0;
+    for (int64_t r = 0; r < rows; ++r) {
+        const int64_t s = indptr[r], len = indptr[r + 1] - s;
+        if (len <= chunk) {
+            items.push_back(Item{s, (int32_t)r, (int32_t)len, -1, 0});
+        } else {
+            const int64_t nc = cdiv(len, chunk);
+            for (int64_t c = 0; c < nc; ++c) {
+                const int64_t b = c * chunk;
+                items.push_back(
+                    Item{s + b, (int32_t)r, (int32_t)std::min(chunk, len - b), slots++, 0});
+            }
+            split_rows.push_back((int32_t)r);
+            slot_begin.push_back(slots);
+        }
+    }
+    /* counting sort by length, descending, stable */
+    std::vector<int64_t> cnt((size_t)chunk + 2, 0);
+    for (const Item &it : items) cnt[(size_t)(chunk - it.len)]++;
+    int64_t run = 0;
+    for (auto &c : cnt) {
+        const int64_t t = c;
+        c = run;
+        run += t;
+    }
+    std::vector<Item> sorted(items.size());
+    for (const Item &it : items) sorted[(size_t)cnt[(size_t)(chunk - it.len)]++] = it;
+
+    out.n_items = (int64_t)sorted.size();
+    out.n_split = (int32_t)split_rows.size();
+    out.n_slots = slots;
+    CK(out.items.ensure(sorted.size() * sizeof(Item)));
+    CK(cudaMemcpyAsync(out.items.p, sorted.data(), sorted.size() * sizeof(Item),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    CK(out.split_rows.ensure(split_rows.size() * sizeof(int32_t)));
+    CK(out.slot_begin.ensure(slot_begin.size() * sizeof(int32_t)));
+    if (!split_rows.empty())
+        CK(cudaMemcpyAsync(out.split_rows.p, split_rows.data(),
+                           split_rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
+                           ctx->stream));
+    CK(cudaMemcpyAsync(out.slot_begin.p, slot_begin.data(), slot_begin.size() * sizeof(int32_t),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream)); /* host vectors die here */
+    out.ready = true;
+    return PLSA_OK;
+}
+
+/* ---- term-major copy ---------------------------------------------------------------------- */
+/* Stable radix sort of the entry numbers by column: within a term the documents stay in
+ * ascending order, so the summation order — and the result — is reproducible. */
+static int build_term_major(plsa_ctx *ctx)
+{
+    Corpus &c = ctx->cur();
+    const int64_t nnz = c.nnz, n = c.n, m = c.m;
+    cudaStream_t s = ctx->stream;
+    DevBuf rows_exp, perm_in, perm_out, keys_out, counts, tmp;
+    int rc = PLSA_OK;
+    auto cleanup = [&]() {
+        rows_exp.release(); perm_in.release(); perm_out.release();
+        keys_out.release(); counts.release(); tmp.release();
+    };
+#define CKT(expr)                                                                             \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            cleanup();                                                                        \
+            return ctx->fail(e_ == cudaErrorMemoryAllocation ? PLSA_ENOMEM : PLSA_ECUDA,      \
+                             std::string(#expr) + ": " + cudaGetErrorString(e_));            \
+        }                                                                                     \
+    } while (0)
+    const size_t nz = (size_t)std::max<int64_t>(nnz, 1);
+    CKT(ctx->t_rows.ensure(nz * 4));
+    CKT(ctx->t_vals.ensure(nz * 4));
+    CKT(rows_exp.ensure(nz * 4));
+    CKT(perm_in.ensure(nz * 4));
+    CKT(perm_out.ensure(nz * 4));
+    CKT(keys_out.ensure(nz * 4));
+    CKT(counts.ensure((size_t)(m + 1) * 4));
+    ctx->h_tindptr.assign((size_t)m + 1, 0);
+    if (nnz > 0) {
+        const int T = 256;
+        expand_rows_kernel<<<(unsigned)cdiv(n * 32, T), T, 0, s>>>(c.indptr.as<int32_t>(), n,
+                                                                  rows_exp.as<int32_t>());
+        iota_kernel<<<(unsigned)cdiv(nnz, T), T, 0, s>>>(perm_in.as<int32_t>(), nnz);
+        ctx->launches += 2;
+        int end_bit = 1;
+        while (((int64_t)1 << end_bit) < m) ++end_bit;
+        size_t tmp_bytes = 0;
+        CKT(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c.cols.as<int32_t>(),
+                                            keys_out.as<int32_t>(), perm_in.as<int32_t>(),
+                                            perm_out.as<int32_t>(), (int)nnz, 0, end_bit, s));
+        CKT(tmp.ensure(tmp_bytes));
+        CKT(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, c.cols.as<int32_t>(),
+                                            keys_out.as<int32_t>(), perm_in.as<int32_t>(),
+                                            perm_out.as<int32_t>(), (int)nnz, 0, end_bit, s));
+        permute_kernel<<<(unsigned)cdiv(nnz, T), T, 0, s>>>(
+            perm_out.as<int32_t>(), nnz, rows_exp.as<int32_t>(), c.vals.as<float>(),
+            ctx->t_rows.as<int32_t>(), ctx->t_vals.as<float>());
+        CKT(cudaMemsetAsync(counts.p, 0, (size_t)(m + 1) * 4, s));
+        histogram_kernel<<<(unsigned)cdiv(nnz, T), T, 0, s>>>(c.cols.as<int32_t>(), nnz,
+                                                             counts.as<int32_t>() + 1);
+        ctx->launches += 2;
+        CKT(cudaGetLastError());
+        CKT(cudaMemcpyAsync(ctx->h_tindptr.data(), counts.p, (size_t)(m + 1) * 4,
+                            cudaMemcpyDeviceToHost, s));
+        CKT(cudaStreamSynchronize(s));
+        for (int64_t w = 0; w < m; ++w) ctx->h_tindptr[(size_t)w + 1] += ctx->h_tindptr[(size_t)w];
+    }
+    cleanup();
+#undef CKT
+    rc = build_items(ctx, ctx->h_tindptr, m, ctx->term_items);
+    if (rc) return rc;
+    ctx->t_ready = true;
+    ctx->t_weighted_ready = false;
+    return PLSA_OK;
+}
+
+static int ensure_weighted_vals(plsa_ctx *ctx)
+{
+    if (ctx->t_weighted_ready) return PLSA_OK;
+    const int64_t nnz = ctx->cur().nnz;
+    CK(ctx->t_valsw.ensure((size_t)std::max<int64_t>(nnz, 1) * 4));
+    if (nnz > 0) {
+        weight_vals_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, ctx->stream>>>(
+            ctx->t_vals.as<float>(), ctx->t_rows.as<int32_t>(), ctx->sw.as<float>(),
+            ctx->t_valsw.as<float>(), nnz);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    ctx->t_weighted_ready = true;
+    return PLSA_OK;
+}
+
+static void corpus_changed(plsa_ctx *ctx)
+{
+    ctx->t_ready = false;
+    ctx->t_weighted_ready = false;
+    ctx->doc_items.ready = false;
+    ctx->term_items.ready = false;
+    ctx->have_factors = false;
+    ctx->have_sw = false;
+}
+
+/* ============================================================================================
+ * C ABI
+ * ============================================================================================ */
+API int plsa_version(void) { return 100; }
+
+API int plsa_device_count(int *count)
+{
+    if (!count) return PLSA_EINVAL;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        g_err = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e);
+        return PLSA_ECUDA;
+    }
+    return PLSA_OK;
+}
+
+API const char *plsa_last_error(const plsa_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+API int plsa_ctx_create(int device, plsa_ctx **out)
+{
+    if (!out) return PLSA_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_err = std::string("no CUDA device: ") + cudaGetErrorString(e);
+        return PLSA_ECUDA;
+    }
+    if (device < 0 || device >= count) {
+        g_err = "device index out of range";
+        return PLSA_EINVAL;
+    }
+    plsa_ctx *ctx = new (std::nothrow) plsa_ctx();
+    if (!ctx) return PLSA_ENOMEM;
+    ctx->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) {
+        g_err = std::string("context setup: ") + cudaGetErrorString(e);
+        delete ctx;
+        return PLSA_ECUDA;
+    }
+    *out = ctx;
+    return PLSA_OK;
+}
+
+API int plsa_ctx_destroy(plsa_ctx *ctx)
+{
+    if (!ctx) return PLSA_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    prof_collect(ctx);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    for (Corpus *c : {&ctx->base, &ctx->boot}) {
+        c->indptr.release(); c->cols.release(); c->vals.release();
+    }
+    for (DevBuf *b : {&ctx->t_rows, &ctx->t_vals, &ctx->t_valsw, &ctx->t_scratch,
+                      &ctx->doc_items.items, &ctx->doc_items.split_rows, &ctx->doc_items.slot_begin,
+                      &ctx->term_items.items, &ctx->term_items.split_rows,
+                      &ctx->term_items.slot_begin, &ctx->A[0], &ctx->A[1], &ctx->B[0], &ctx->B[1],
+                      &ctx->scale, &ctx->ones, &ctx->colnorm, &ctx->colpart, &ctx->partialA,
+                      &ctx->partialB, &ctx->sw, &ctx->ll_part, &ctx->ll_out, &ctx->stage,
+                      &ctx->topics_dev})
+        b->release();
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return PLSA_OK;
+}
+
+/* ---- corpus ----------------------------------------------------------------------------------- */
+static int upload_csr_impl(plsa_ctx *ctx, const int32_t *indptr, const int32_t *indices,
+                           const float *data, int64_t n, int64_t m, int64_t nnz)
+{
+    if (n < 0 || m < 0 || nnz < 0 || (nnz > 0 && (!indices || !data)) || !indptr)
+        return ctx->fail(PLSA_EINVAL, "upload: null pointer or negative size");
+    if (nnz >= ((int64_t)1 << 31) || n >= ((int64_t)1 << 31) - 1 || m >= ((int64_t)1 << 31) - 1)
+        return ctx->fail(PLSA_EINVAL, "upload: sizes must fit int32 indices");
+    if (indptr[0] != 0 || indptr[n] != nnz)
+        return ctx->fail(PLSA_EINVAL, "upload: indptr[0] != 0 or indptr[n] != nnz");
+    for (int64_t r = 0; r < n; ++r)
+        if (indptr[r + 1] < indptr[r]) return ctx->fail(PLSA_EINVAL, "upload: indptr decreases");
+    for (int64_t i = 0; i < nnz; ++i)
+        if ((uint32_t)indices[i] >= (uint32_t)m)
+            return ctx->fail(PLSA_EINVAL, "upload: column index out of range");
+    Corpus &c = ctx->base;
+    c.n = n; c.m = m; c.nnz = nnz;
+    c.h_indptr.assign(indptr, indptr + n + 1);
+    CK(c.indptr.ensure((size_t)(n + 1) * 4));
+    CK(c.cols.ensure((size_t)std::max<int64_t>(nnz, 1) * 4));
+    CK(c.vals.ensure((size_t)std::max<int64_t>(nnz, 1) * 4));
+    CK(cudaMemcpyAsync(c.indptr.p, indptr, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (nnz > 0) {
+        CK(cudaMemcpyAsync(c.cols.p, indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(c.vals.p, data, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->use_boot = false;
+    corpus_changed(ctx);
+    return PLSA_OK;
+}
+
+API int plsa_upload_csr(plsa_ctx *ctx, const int32_t *indptr, const int32_t *indices,
+                        const float *data, int64_t n_docs, int64_t n_terms, int64_t nnz)
+{
+    CHECK_CTX(ctx);
+    return upload_csr_impl(ctx, indptr, indices, data, n_docs, n_terms, nnz);
+}
+
+API int plsa_upload_coo(plsa_ctx *ctx, const int32_t *rows, const int32_t *cols,
+                        const float *vals, int64_t n_docs, int64_t n_terms, int64_t nnz)
+{
+    CHECK_CTX(ctx);
+    if (n_docs < 0 || nnz < 0 || (nnz > 0 && !rows))
+        return ctx->fail(PLSA_EINVAL, "upload_coo: null pointer or negative size");
+    std::vector<int32_t> indptr((size_t)n_docs + 1, 0);
+    for (int64_t i = 0; i < nnz; ++i) {
+        if ((uint32_t)rows[i] >= (uint32_t)n_docs)
+            return ctx->fail(PLSA_EINVAL, "upload_coo: row index out of range");
+        if (i > 0 && rows[i] < rows[i - 1])
+            return ctx->fail(PLSA_EINVAL,
+                             "upload_coo: triplets must be sorted by row (X.tocoo() of a CSR matrix)");
+        indptr[(size_t)rows[i] + 1]++;
+    }
+    for (int64_t r = 0; r < n_docs; ++r) indptr[(size_t)r + 1] += indptr[(size_t)r];
+    return upload_csr_impl(ctx, indptr.data(), cols, vals, n_docs, n_terms, nnz);
+}
+
+API int plsa_bootstrap(plsa_ctx *ctx, const int32_t *row_idx, int64_t n_rows)
+{
+    CHECK_CTX(ctx);
+    if (ctx->base.h_indptr.empty()) return ctx->fail(PLSA_EINVAL, "bootstrap: no corpus uploaded");
+    if (!row_idx) {
+        ctx->use_boot = false;
+        corpus_changed(ctx);
+        return PLSA_OK;
+    }
+    if (n_rows < 0) return ctx->fail(PLSA_EINVAL, "bootstrap: negative row count");
+    const Corpus &b = ctx->base;
+    Corpus &c = ctx->boot;
+    c.h_indptr.assign((size_t)n_rows + 1, 0);
+    int64_t run = 0;
+    for (int64_t i = 0; i < n_rows; ++i) {
+        if ((uint32_t)row_idx[i] >= (uint32_t)b.n)
+            return ctx->fail(PLSA_EINVAL, "bootstrap: row index out of range");
+        run += b.h_indptr[(size_t)row_idx[i] + 1] - b.h_indptr[(size_t)row_idx[i]];
+        if (run >= ((int64_t)1 << 31))
+            return ctx->fail(PLSA_EINVAL, "bootstrap: resampled corpus exceeds int32 entries");
+        c.h_indptr[(size_t)i + 1] = (int32_t)run;
+    }
+    c.n = n_rows; c.m = b.m; c.nnz = run;
+    CK(c.indptr.ensure((size_t)(n_rows + 1) * 4));
+    CK(c.cols.ensure((size_t)std::max<int64_t>(run, 1) * 4));
+    CK(c.vals.ensure((size_t)std::max<int64_t>(run, 1) * 4));
+    CK(ctx->stage.ensure((size_t)std::max<int64_t>(n_rows, 1) * 4));
+    CK(cudaMemcpyAsync(c.indptr.p, c.h_indptr.data(), (size_t)(n_rows + 1) * 4,
+                       cudaMemcpyHostToDevice, ctx->stream));
+    if (n_rows > 0) {
+        CK(cudaMemcpyAsync(ctx->stage.p, row_idx, (size_t)n_rows * 4, cudaMemcpyHostToDevice,
+                           ctx->stream));
+        gather_rows_kernel<<<(unsigned)cdiv(n_rows * 32, 256), 256, 0, ctx->stream>>>(
+            ctx->stage.as<int32_t>(), n_rows, b.indptr.as<int32_t>(), b.cols.as<int32_t>(),
+            b.vals.as<float>(), c.indptr.as<int32_t>(), c.cols.as<int32_t>(), c.vals.as<float>());
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->use_boot = true;
+    corpus_changed(ctx);
+    return PLSA_OK;
+}
+
+API int plsa_corpus_shape(const plsa_ctx *ctx, int64_t *n_docs, int64_t *n_terms, int64_t *nnz)
+{
+    if (!ctx) return PLSA_EINVAL;
+    const Corpus &c = ctx->cur();
+    if (n_docs) *n_docs = c.n;
+    if (n_terms) *n_terms = c.m;
+    if (nnz) *nnz = c.nnz;
+    return PLSA_OK;
+}
+
+/* ---- model state -------------------------------------------------------------------------------- */
+static int32_t row_stride(int32_t kp)
+{
+    if (kp * 4 <= 128) { /* rows never straddle a 128-byte line */
+        int32_t s = 4;
+        while (s < kp) s <<= 1;
+        return s;
+    }
+    return (kp + 31) / 32 * 32;
+}
+
+static int fill(plsa_ctx *ctx, float *p, int64_t n, float v)
+{
+    if (n > 0) {
+        fill_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(p, n, v);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    return PLSA_OK;
+}
+
+API int plsa_set_factors(plsa_ctx *ctx, const float *p_z_given_d, const float *p_w_given_z,
+                         int32_t k)
+{
+    CHECK_CTX(ctx);
+    const Corpus &c = ctx->cur();
+    if (c.h_indptr.empty()) return ctx->fail(PLSA_EINVAL, "set_factors: no corpus uploaded");
+    if (k < 1 || k > PLSA_MAX_K) return ctx->fail(PLSA_EINVAL, "set_factors: k out of range");
+    if (!p_z_given_d || !p_w_given_z) return ctx->fail(PLSA_EINVAL, "set_factors: null factor");
+    const int32_t kp = (k + 3) / 4 * 4;
+    ctx->k = k;
+    ctx->kp = kp;
+    ctx->strideA = ctx->strideB = row_stride(kp);
+    const int64_t n = c.n, m = c.m;
+    const size_t bytesA = (size_t)std::max<int64_t>(n, 1) * ctx->strideA * 4;
+    const size_t bytesB = (size_t)std::max<int64_t>(m, 1) * ctx->strideB * 4;
+    for (int i = 0; i < 2; ++i) {
+        CK(ctx->A[i].ensure(bytesA));
+        CK(ctx->B[i].ensure(bytesB));
+        CK(cudaMemsetAsync(ctx->A[i].p, 0, bytesA, ctx->stream));
+        CK(cudaMemsetAsync(ctx->B[i].p, 0, bytesB, ctx->stream));
+    }
+    CK(ctx->scale.ensure((size_t)kp * 4));
+    CK(ctx->ones.ensure((size_t)kp * 4));
+    CK(ctx->colnorm.ensure((size_t)kp * 8));
+    CK(ctx->colpart.ensure((size_t)COLSUM_CTAS * kp * 8));
+    CK(ctx->ll_out.ensure(8));
+    int rc;
+    if ((rc = fill(ctx, ctx->scale.as<float>(), kp, 1.f))) return rc;
+    if ((rc = fill(ctx, ctx->ones.as<float>(), kp, 1.f))) return rc;
+
+    const size_t stage_bytes = (size_t)std::max<int64_t>(std::max(n, m), 1) * k * 4;
+    CK(ctx->stage.ensure(stage_bytes));
+    if (n > 0) {
+        CK(cudaMemcpyAsync(ctx->stage.p, p_z_given_d, (size_t)n * k * 4, cudaMemcpyHostToDevice,
+                           ctx->stream));
+        pack_rows_kernel<<<(unsigned)cdiv(n * kp, 256), 256, 0, ctx->stream>>>(
+            ctx->stage.as<float>(), ctx->A[0].as<float>(), n, k, kp, ctx->strideA, 0);
+        ctx->launches++;
+    }
+    if (m > 0) {
+        CK(cudaMemcpyAsync(ctx->stage.p, p_w_given_z, (size_t)m * k * 4, cudaMemcpyHostToDevice,
+                           ctx->stream));
+        pack_rows_kernel<<<(unsigned)cdiv(m * kp, 256), 256, 0, ctx->stream>>>(
+            ctx->stage.as<float>(), ctx->B[0].as<float>(), m, k, kp, ctx->strideB, 1);
+        ctx->launches++;
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->curA = ctx->curB = 0;
+    ctx->have_factors = true;
+    return PLSA_OK;
+}
+
+API int plsa_set_sample_weight(plsa_ctx *ctx, const float *sample_weight)
+{
+    CHECK_CTX(ctx);
+    const Corpus &c = ctx->cur();
+    if (c.h_indptr.empty()) return ctx->fail(PLSA_EINVAL, "set_sample_weight: no corpus uploaded");
+    CK(ctx->sw.ensure((size_t)std::max<int64_t>(c.n, 1) * 4));
+    if (sample_weight) {
+        if (c.n > 0)
+            CK(cudaMemcpyAsync(ctx->sw.p, sample_weight, (size_t)c.n * 4, cudaMemcpyHostToDevice,
+                               ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else {
+        int rc = fill(ctx, ctx->sw.as<float>(), c.n, 1.f);
+        if (rc) return rc;
+    }
+    ctx->have_sw = true;
+    ctx->t_weighted_ready = false;
+    return PLSA_OK;
+}
+
+API int plsa_get_factors(plsa_ctx *ctx, float *p_z_given_d, float *p_w_given_z)
+{
+    CHECK_CTX(ctx);
+    if (!ctx->have_factors) return ctx->fail(PLSA_EINVAL, "get_factors: no factors set");
+    const Corpus &c = ctx->cur();
+    const int64_t n = c.n, m = c.m;
+    const int k = ctx->k;
+    CK(ctx->stage.ensure((size_t)std::max<int64_t>(std::max(n, m), 1) * k * 4));
+    if (p_z_given_d && n > 0) {
+        unpack_rows_kernel<<<(unsigned)cdiv(n * k, 256), 256, 0, ctx->stream>>>(
+            ctx->A[ctx->curA].as<float>(), nullptr, ctx->stage.as<float>(), n, k, ctx->strideA, 0);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(p_z_given_d, ctx->stage.p, (size_t)n * k * 4, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (p_w_given_z && m > 0) {
+        unpack_rows_kernel<<<(unsigned)cdiv(m * k, 256), 256, 0, ctx->stream>>>(
+            ctx->B[ctx->curB].as<float>(), ctx->scale.as<float>(), ctx->stage.as<float>(), m, k,
+            ctx->strideB, 1);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(p_w_given_z, ctx->stage.p, (size_t)m * k * 4, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return PLSA_OK;
+}
+
+/* ---- EM ------------------------------------------------------------------------------------------ */
+static int ensure_doc_items(plsa_ctx *ctx)
+{
+    if (ctx->doc_items.ready) return PLSA_OK;
+    return build_items(ctx, ctx->cur().h_indptr, ctx->cur().n, ctx->doc_items);
+}
+
+static int run_loglik(plsa_ctx *ctx, double *out)
+{
+    const Corpus &c = ctx->cur();
+    int rc = ensure_doc_items(ctx);
+    if (rc) return rc;
+    if (!ctx->have_sw && (rc = plsa_set_sample_weight(ctx, nullptr))) return rc;
+    const int64_t grid = cdiv(ctx->doc_items.n_items, 8);
+    if (grid == 0) {
+        *out = 0.0;
+        return PLSA_OK;
+    }
+    CK(ctx->ll_part.ensure((size_t)grid * 8));
+    {
+        ProfScope ps(ctx, PLSA_PROF_LOGLIK);
+        PassArgs a{};
+        a.items = ctx->doc_items.items.as<Item>();
+        a.n_items = ctx->doc_items.n_items;
+        a.idx = c.cols.as<int32_t>();
+        a.val = c.vals.as<float>();
+        a.own_old = ctx->A[ctx->curA].as<float>();
+        a.gat_old = ctx->B[ctx->curB].as<float>();
+        a.own_scale = ctx->scale.as<float>();
+        a.row_weight = ctx->sw.as<float>();
+        a.ll_partial = ctx->ll_part.as<double>();
+        a.stride_own = ctx->strideA;
+        a.stride_gat = ctx->strideB;
+        a.kp = ctx->kp;
+        if ((rc = launch_pass(ctx, MODE_LOGLIK, a))) return rc;
+        sum_doubles_kernel<<<1, 256, 0, ctx->stream>>>(ctx->ll_part.as<double>(), grid,
+                                                       ctx->ll_out.as<double>());
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(out, ctx->ll_out.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PLSA_OK;
+}
+
+API int plsa_log_likelihood(plsa_ctx *ctx, double *ll)
+{
+    CHECK_CTX(ctx);
+    if (!ll) return ctx->fail(PLSA_EINVAL, "log_likelihood: null output");
+    if (!ctx->have_factors) return ctx->fail(PLSA_EINVAL, "log_likelihood: no factors set");
+    return run_loglik(ctx, ll);
+}
+
+static int run_fixup(plsa_ctx *ctx, const ItemSet &is, const float *partial, float *own_new,
+                     int stride, int normalise)
+{
+    if (is.n_split == 0) return PLSA_OK;
+    ProfScope ps(ctx, PLSA_PROF_FIXUP);
+    FixArgs f{};
+    f.rows = is.split_rows.as<int32_t>();
+    f.slot_begin = is.slot_begin.as<int32_t>();
+    f.partial = partial;
+    f.own_new = own_new;
+    f.n_split = is.n_split;
+    f.kp = ctx->kp;
+    f.stride_own = stride;
+    f.normalise = normalise;
+    fixup_kernel<<<(unsigned)is.n_split, 256, 0, ctx->stream>>>(f);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return PLSA_OK;
+}
+
+API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double tolerance,
+                float e_step_thresh, int32_t refit, int32_t use_sample_weights,
+                int32_t *iters_run, double *ll_trace, int32_t ll_cap, int32_t *n_ll)
+{
+    CHECK_CTX(ctx);
+    if (iters_run) *iters_run = 0;
+    if (n_ll) *n_ll = 0;
+    if (!ctx->have_factors) return ctx->fail(PLSA_EINVAL, "em: no factors set");
+    if (n_iter < 0 || n_iter_per_test < 1)
+        return ctx->fail(PLSA_EINVAL, "em: n_iter < 0 or n_iter_per_test < 1");
+    Corpus &c = ctx->cur();
+    int rc;
+    if ((rc = ensure_doc_items(ctx))) return rc;
+    if (!ctx->have_sw && (rc = plsa_set_sample_weight(ctx, nullptr))) return rc;
+    if (!refit) {
+        if (!ctx->t_ready && (rc = build_term_major(ctx))) return rc;
+        if (use_sample_weights && (rc = ensure_weighted_vals(ctx))) return rc;
+    }
+    const int kp = ctx->kp;
+    CK(ctx->partialA.ensure((size_t)std::max(ctx->doc_items.n_slots, 1) * kp * 4));
+    if (!refit) CK(ctx->partialB.ensure((size_t)std::max(ctx->term_items.n_slots, 1) * kp * 4));
+
+    /* plsa.py:913 — the refit loop's early stop is guarded by LL > 0, which a
+     * log-likelihood never satisfies: LL is evaluated there only when a trace is asked for */
+    const bool want_ll = !refit || ll_trace != nullptr;
+    int32_t nl = 0;
+    double prev = 0.0;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (want_ll) {
+        if ((rc = run_loglik(ctx, &prev))) return rc; /* plsa.py:591 */
+        if (ll_trace && nl < ll_cap) ll_trace[nl] = prev;
+        nl++;
+    }
+    int32_t done = 0;
+    for (int32_t i = 0; i < n_iter; ++i) {
+        const int nA = ctx->curA ^ 1, nB = ctx->curB ^ 1;
+        {   /* E-step + M-step of P(z|d): plsa.py:91-105, :189-194 (P(z|d) part), :199-202 */
+            ProfScope ps(ctx, PLSA_PROF_DOC_PASS);
+            PassArgs a{};
+            a.items = ctx->doc_items.items.as<Item>();
+            a.n_items = ctx->doc_items.n_items;
+            a.idx = c.cols.as<int32_t>();
+            a.val = c.vals.as<float>();
+            a.own_old = ctx->A[ctx->curA].as<float>();
+            a.gat_old = ctx->B[ctx->curB].as<float>();
+            a.own_scale = ctx->scale.as<float>();
+            a.own_new = ctx->A[nA].as<float>();
+            a.partial = ctx->partialA.as<float>();
+            a.stride_own = ctx->strideA;
+            a.stride_gat = ctx->strideB;
+            a.kp = kp;
+            a.thresh = e_step_thresh;
+            if ((rc = launch_pass(ctx, MODE_DOC, a))) return rc;
+        }
+        if ((rc = run_fixup(ctx, ctx->doc_items, ctx->partialA.as<float>(),
+                            ctx->A[nA].as<float>(), ctx->strideA, 1)))
+            return rc;
+        if (!refit) {
+            {   /* E-step + M-step of P(w|z): plsa.py:91-105, :189-193 (P(w|z) part) */
+                ProfScope ps(ctx, PLSA_PROF_WORD_PASS);
+                PassArgs a{};
+                a.items = ctx->term_items.items.as<Item>();
+                a.n_items = ctx->term_items.n_items;
+                a.idx = ctx->t_rows.as<int32_t>();
+                a.val = use_sample_weights ? ctx->t_valsw.as<float>() : ctx->t_vals.as<float>();
+                a.own_old = ctx->B[ctx->curB].as<float>();
+                a.gat_old = ctx->A[ctx->curA].as<float>();
+                a.own_scale = ctx->scale.as<float>();
+                a.own_new = ctx->B[nB].as<float>();
+                a.partial = ctx->partialB.as<float>();
+                a.stride_own = ctx->strideB;
+                a.stride_gat = ctx->strideA;
+                a.kp = kp;
+                a.thresh = e_step_thresh;
+                if ((rc = launch_pass(ctx, MODE_TERM, a))) return rc;
+            }
+            if ((rc = run_fixup(ctx, ctx->term_items, ctx->partialB.as<float>(),
+                                ctx->B[nB].as<float>(), ctx->strideB, 0)))
+                return rc;
+            {   /* plsa.py:196-198: per-topic normaliser of P(w|z), applied lazily */
+                ProfScope ps(ctx, PLSA_PROF_NORMALIZE);
+                colsum_partial_kernel<<<COLSUM_CTAS, 256, 0, ctx->stream>>>(
+                    ctx->B[nB].as<float>(), c.m, ctx->strideB, kp, ctx->colpart.as<double>());
+                colsum_final_kernel<<<1, 256, 0, ctx->stream>>>(ctx->colpart.as<double>(),
+                                                                COLSUM_CTAS, kp,
+                                                                ctx->scale.as<float>(),
+                                                                ctx->colnorm.as<double>());
+                ctx->launches += 2;
+                CK(cudaGetLastError());
+            }
+            ctx->curB = nB;
+        }
+        ctx->curA = nA;
+        done = i + 1;
+        if (want_ll && i % n_iter_per_test == 0) { /* plsa.py:630-638 / :909-918 */
+            double cur = 0.0;
+            if ((rc = run_loglik(ctx, &cur))) return rc;
+            if (ll_trace && nl < ll_cap) ll_trace[nl] = cur;
+            nl++;
+            if (!refit) {
+                /* the reference holds the log-likelihood in float32 (plsa.py:322) */
+                const float curf = (float)cur, prevf = (float)prev;
+                const float change = fabsf(curf - prevf);
+                if (change == 0.f || (double)(change / fabsf(curf)) < tolerance) break;
+                prev = cur;
+            } else if (cur > 0.0) {
+                const float change = fabsf((float)cur - (float)prev);
+                if ((double)(change / fabsf((float)cur)) < tolerance) break;
+                prev = cur;
+            }
+        }
+    }
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(&ctx->last_em_ms, ctx->ev0, ctx->ev1));
+    prof_collect(ctx);
+    if (iters_run) *iters_run = done;
+    if (n_ll) *n_ll = nl;
+    return PLSA_OK;
+}
+
+/* ---- measurement ------------------------------------------------------------------------------------ */
+API int plsa_last_em_ms(const plsa_ctx *ctx, float *ms)
+{
+    if (!ctx || !ms) return PLSA_EINVAL;
+    *ms = ctx->last_em_ms;
+    return PLSA_OK;
+}
+
+API int plsa_set_profiling(plsa_ctx *ctx, int32_t on)
+{
+    if (!ctx) return PLSA_EINVAL;
+    ctx->profiling = on != 0;
+    for (int i = 0; i < PLSA_PROF_SLOTS; ++i) {
+        ctx->prof_ms[i] = 0.0;
+        ctx->prof_n[i] = 0;
+    }
+    return PLSA_OK;
+}
+
+API int plsa_get_profile(plsa_ctx *ctx, double *ms, int64_t *launches)
+{
+    if (!ctx) return PLSA_EINVAL;
+    for (int i = 0; i < PLSA_PROF_SLOTS; ++i) {
+        if (ms) ms[i] = ctx->prof_ms[i];
+        if (launches) launches[i] = ctx->prof_n[i];
+    }
+    return PLSA_OK;
+}
+
+API int plsa_launch_count(const plsa_ctx *ctx, int64_t *launches)
+{
+    if (!ctx || !launches) return PLSA_EINVAL;
+    *launches = ctx->launches;
+    return PLSA_OK;
+}
+
+API int plsa_set_option(plsa_ctx *ctx, const char *name, int64_t value)
+{
+    if (!ctx || !name) return PLSA_EINVAL;
+    if (!strcmp(name, "chunk")) {
+        if (value < 32 || value > (1 << 20)) return ctx->fail(PLSA_EINVAL, "chunk out of range");
+        ctx->chunk = value;
+        ctx->doc_items.ready = false;
+        ctx->term_items.ready = false;
+        ctx->t_ready = false; /* term items are rebuilt with the term-major copy */
+        return PLSA_OK;
+    }
+    return ctx->fail(PLSA_EINVAL, std::string("unknown option: ") + name);
+}
+
+/* ---- one-shot drop-ins ---------------------------------------------------------------------------------- */
+static int one_shot(const int32_t *rows, const int32_t *cols, const float *vals, int64_t nnz,
+                    float *pwz_inout, const float *topics, float *pzd, const float *sw, int64_t n,
+                    int64_t m, int32_t k, int32_t n_iter, int32_t per_test, double tol,
+                    float thresh, int32_t use_sw, int32_t refit, int32_t device, int32_t *iters)
+{
+    plsa_ctx *ctx = nullptr;
+    int rc = plsa_ctx_create(device, &ctx);
+    if (rc) return rc;
+    auto bail = [&](int code) {
+        g_err = ctx->err;
+        plsa_ctx_destroy(ctx);
+        return code;
+    };
+    if ((rc = plsa_upload_coo(ctx, rows, cols, vals, n, m, nnz))) return bail(rc);
+    if ((rc = plsa_set_factors(ctx, pzd, refit ? topics : pwz_inout, k))) return bail(rc);
+    if ((rc = plsa_set_sample_weight(ctx, sw))) return bail(rc);
+    if ((rc = plsa_em(ctx, n_iter, per_test, tol, thresh, refit, use_sw, iters, nullptr, 0, nullptr)))
+        return bail(rc);
+    if ((rc = plsa_get_factors(ctx, pzd, refit ? nullptr : pwz_inout))) return bail(rc);
+    plsa_ctx_destroy(ctx);
+    return PLSA_OK;
+}
+
+API int plsa_b200_fit_inner(const int32_t *X_rows, const int32_t *X_cols, const float *X_vals,
+                            int64_t nnz, float *p_w_given_z, float *p_z_given_d,
+                            const float *sample_weight, int64_t n_docs, int64_t n_terms,
+                            int32_t k, int32_t n_iter, int32_t n_iter_per_test, double tolerance,
+                            float e_step_thresh, int32_t use_sample_weights, int32_t device,
+                            int32_t *iters_run)
+{
+    return one_shot(X_rows, X_cols, X_vals, nnz, p_w_given_z, nullptr, p_z_given_d, sample_weight,
+                    n_docs, n_terms, k, n_iter, n_iter_per_test, tolerance, e_step_thresh,
+                    use_sample_weights, 0, device, iters_run);
+}
+
+API int plsa_b200_refit_inner(const int32_t *X_rows, const int32_t *X_cols, const float *X_vals,
+                              int64_t nnz, const float *topics, float *p_z_given_d,
+                              const float *sample_weight, int64_t n_docs, int64_t n_terms,
+                              int32_t k, int32_t n_iter, int32_t n_iter_per_test,
+                              double tolerance, float e_step_thresh, int32_t device,
+                              int32_t *iters_run)
+{
+    return one_shot(X_rows, X_cols, X_vals, nnz, nullptr, topics, p_z_given_d, sample_weight,
+                    n_docs, n_terms, k, n_iter, n_iter_per_test, tolerance, e_step_thresh, 0, 1,
+                    device, iters_run);
+}
+
+/* ---- ensemble topic stash + gather over NCCL ------------------------------------------------------ */
+/* Each finished ensemble member leaves its P(w|z) [k, m] (reference layout) in a slot of the
+ * context's device-side stash; one gather at the end moves every slot to the root
+ * (enstop_.py:231 np.vstack(topics)).  NCCL is resolved at run time (dlopen) so the library
+ * loads on hosts without it; a single rank / single context never touches NCCL. */
+API int plsa_stash_topics(plsa_ctx *ctx, int32_t slot, int32_t n_slots)
+{
+    CHECK_CTX(ctx);
+    if (!ctx->have_factors) return ctx->fail(PLSA_EINVAL, "stash_topics: no factors set");
+    if (n_slots < 1 || slot < 0 || slot >= n_slots)
+        return ctx->fail(PLSA_EINVAL, "stash_topics: slot out of range");
+    const int64_t m = ctx->cur().m;
+    const size_t per = (size_t)std::max<int64_t>(m, 1) * ctx->k;
+    if (ctx->stash_slots != n_slots || ctx->stash_per != per) {
+        ctx->topics_dev.release();
+        CK(ctx->topics_dev.ensure(per * (size_t)n_slots * 4));
+        ctx->stash_slots = n_slots;
+        ctx->stash_per = per;
+    }
+    if (m > 0) {
+        unpack_rows_kernel<<<(unsigned)cdiv(m * ctx->k, 256), 256, 0, ctx->stream>>>(
+            ctx->B[ctx->curB].as<float>(), ctx->scale.as<float>(),
+            ctx->topics_dev.as<float>() + per * (size_t)slot, m, ctx->k, ctx->strideB, 1);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PLSA_OK;
+}
+
+API int plsa_topics_device(plsa_ctx *ctx, void **device_ptr, int64_t *floats_per_slot)
+{
+    if (!ctx || !device_ptr) return PLSA_EINVAL;
+    if (!ctx->topics_dev.p) return ctx->fail(PLSA_EINVAL, "topics_device: nothing stashed");
+    *device_ptr = ctx->topics_dev.p;
+    if (floats_per_slot) *floats_per_slot = (int64_t)ctx->stash_per;
+    return PLSA_OK;
+}
+
+namespace {
+typedef struct ncclComm *ncclComm_t;
+struct NcclId { char bytes[PLSA_NCCL_ID_BYTES]; };
+typedef int (*fn_GetUniqueId)(NcclId *);
+typedef int (*fn_CommInitRank)(ncclComm_t *, int, NcclId, int);
+typedef int (*fn_CommInitAll)(ncclComm_t *, int, const int *);
+typedef int (*fn_CommDestroy)(ncclComm_t);
+typedef int (*fn_GroupStart)(void);
+typedef int (*fn_GroupEnd)(void);
+typedef int (*fn_Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t);
+typedef int (*fn_Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t);
+typedef const char *(*fn_GetErrorString)(int);
+struct Nccl {
+    void *h = nullptr;
+    fn_GetUniqueId GetUniqueId;
+    fn_CommInitRank CommInitRank;
+    fn_CommInitAll CommInitAll;
+    fn_CommDestroy CommDestroy;
+    fn_GroupStart GroupStart;
+    fn_GroupEnd GroupEnd;
+    fn_Send Send;
+    fn_Recv Recv;
+    fn_GetErrorString GetErrorString;
+};
+const int kNcclFloat = 7; /* ncclFloat32 */
+
+static Nccl *load_nccl()
+{
+    static Nccl n;
+    static bool tried = false;
+    if (tried) return n.h ? &n : nullptr;
+    tried = true;
+    for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+        n.h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+        if (n.h) break;
+    }
+    if (!n.h) return nullptr;
+    n.GetUniqueId = (fn_GetUniqueId)dlsym(n.h, "ncclGetUniqueId");
+    n.CommInitRank = (fn_CommInitRank)dlsym(n.h, "ncclCommInitRank");
+    n.CommInitAll = (fn_CommInitAll)dlsym(n.h, "ncclCommInitAll");
+    n.CommDestroy = (fn_CommDestroy)dlsym(n.h, "ncclCommDestroy");
+    n.GroupStart = (fn_GroupStart)dlsym(n.h, "ncclGroupStart");
+    n.GroupEnd = (fn_GroupEnd)dlsym(n.h, "ncclGroupEnd");
+    n.Send = (fn_Send)dlsym(n.h, "ncclSend");
+    n.Recv = (fn_Recv)dlsym(n.h, "ncclRecv");
+    n.GetErrorString = (fn_GetErrorString)dlsym(n.h, "ncclGetErrorString");
+    if (!n.GetUniqueId || !n.CommInitRank || !n.CommInitAll || !n.CommDestroy ||
+        !n.GroupStart || !n.GroupEnd || !n.Send || !n.Recv) {
+        dlclose(n.h);
+        n.h = nullptr;
+        return nullptr;
+    }
+    return &n;
+}
+
+static int nccl_fail(Nccl *nc, const char *what, int r)
+{
+    g_err = std::string(what) + ": NCCL error: " +
+            ((nc && nc->GetErrorString) ? nc->GetErrorString(r) : "?");
+    return PLSA_ENCCL;
+}
+} // namespace
+
+/* Single process, one context per device (one host thread per GPU during the fits). */
+API int plsa_gather_topics(plsa_ctx **ctxs, int32_t n_ctx, const int32_t *n_slots, float *out)
+{
+    if (!ctxs || n_ctx < 1 || !n_slots || !out) {
+        g_err = "gather_topics: bad arguments";
+        return PLSA_EINVAL;
+    }
+    plsa_ctx *root = ctxs[0];
+    size_t per = 0, total = 0;
+    for (int i = 0; i < n_ctx; ++i) {
+        plsa_ctx *c = ctxs[i];
+        if (!c || n_slots[i] < 0 || (n_slots[i] > 0 && (!c->topics_dev.p || n_slots[i] > c->stash_slots))) {
+            g_err = "gather_topics: a context has fewer stashed topic matrices than requested";
+            return PLSA_EINVAL;
+        }
+        if (n_slots[i] > 0) {
+            if (per == 0) per = c->stash_per;
+            if (c->stash_per != per) {
+                g_err = "gather_topics: contexts must share k and n_terms";
+                return PLSA_EINVAL;
+            }
+        }
+        for (int j = 0; j < i; ++j)
+            if (ctxs[j]->device == c->device) {
+                g_err = "gather_topics: one context per device";
+                return PLSA_EINVAL;
+            }
+        total += (size_t)n_slots[i];
+    }
+    if (total == 0) return PLSA_OK;
+    cudaSetDevice(root->device);
+    DevBuf stack;
+    if (stack.ensure(per * total * 4) != cudaSuccess) {
+        g_err = "gather_topics: staging allocation failed";
+        return PLSA_ENOMEM;
+    }
+    int rc = PLSA_OK;
+    cudaError_t ce = cudaSuccess;
+    if (n_slots[0] > 0)
+        ce = cudaMemcpyAsync(stack.p, root->topics_dev.p, per * (size_t)n_slots[0] * 4,
+                             cudaMemcpyDeviceToDevice, root->stream);
+    bool any_remote = false;
+    for (int i = 1; i < n_ctx; ++i) any_remote |= n_slots[i] > 0;
+    if (ce == cudaSuccess && any_remote) {
+        Nccl *nc = load_nccl();
+        if (!nc) {
+            stack.release();
+            g_err = "gather_topics: libnccl.so.2 could not be loaded";
+            return PLSA_ENCCL;
+        }
+        std::vector<int> devs((size_t)n_ctx);
+        for (int i = 0; i < n_ctx; ++i) devs[(size_t)i] = ctxs[i]->device;
+        std::vector<ncclComm_t> comms((size_t)n_ctx);
+        int r = nc->CommInitAll(comms.data(), n_ctx, devs.data());
+        if (r != 0) {
+            stack.release();
+            return nccl_fail(nc, "gather_topics: ncclCommInitAll", r);
+        }
+        nc->GroupStart();
+        size_t off = (size_t)n_slots[0] * per;
+        for (int i = 1; i < n_ctx && r == 0; ++i) {
+            const size_t cnt = (size_t)n_slots[i] * per;
+            if (cnt == 0) continue;
+            cudaSetDevice(ctxs[i]->device);
+            r = nc->Send(ctxs[i]->topics_dev.p, cnt, kNcclFloat, 0, comms[(size_t)i],
+                         ctxs[i]->stream);
+            if (r) break;
+            cudaSetDevice(root->device);
+            r = nc->Recv(stack.as<float>() + off, cnt, kNcclFloat, i, comms[0], root->stream);
+            off += cnt;
+        }
+        const int r2 = nc->GroupEnd();
+        if (r == 0) r = r2;
+        for (int i = 0; i < n_ctx; ++i) {
+            cudaSetDevice(ctxs[i]->device);
+            cudaStreamSynchronize(ctxs[i]->stream);
+        }
+        for (int i = 0; i < n_ctx; ++i) nc->CommDestroy(comms[(size_t)i]);
+        if (r != 0) rc = nccl_fail(nc, "gather_topics", r);
+    }
+    cudaSetDevice(root->device);
+    if (rc == PLSA_OK && ce == cudaSuccess)
+        ce = cudaMemcpyAsync(out, stack.p, per * total * 4, cudaMemcpyDeviceToHost, root->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(root->stream);
+    stack.release();
+    if (rc == PLSA_OK && ce != cudaSuccess) {
+        g_err = std::string("gather_topics: ") + cudaGetErrorString(ce);
+        rc = PLSA_ECUDA;
+    }
+    if (rc) root->err = g_err;
+    return rc;
+}
+
+/* One process per GPU (torchrun-style launch): rank 0 makes the id, the launcher's own
+ * rendezvous distributes the 128 bytes, every rank creates its communicator. */
+struct plsa_comm {
+    ncclComm_t comm = nullptr;
+    int device = 0, n_ranks = 1, rank = 0;
+    cudaStream_t stream = nullptr;
+};
+
+API int plsa_nccl_unique_id(char *id)
+{
+    if (!id) return PLSA_EINVAL;
+    Nccl *nc = load_nccl();
+    if (!nc) {
+        g_err = "nccl_unique_id: libnccl.so.2 could not be loaded";
+        return PLSA_ENCCL;
+    }
+    NcclId u;
+    memset(&u, 0, sizeof(u));
+    const int r = nc->GetUniqueId(&u);
+    if (r != 0) return nccl_fail(nc, "nccl_unique_id", r);
+    memcpy(id, u.bytes, PLSA_NCCL_ID_BYTES);
+    return PLSA_OK;
+}
+
+API int plsa_comm_create(int device, int32_t n_ranks, int32_t rank, const char *id, plsa_comm **out)
+{
+    if (!out || n_ranks < 1 || rank < 0 || rank >= n_ranks || (n_ranks > 1 && !id)) {
+        g_err = "comm_create: bad arguments";
+        return PLSA_EINVAL;
+    }
+    *out = nullptr;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        g_err = std::string("comm_create: cudaSetDevice: ") + cudaGetErrorString(e);
+        return PLSA_ECUDA;
+    }
+    plsa_comm *c = new (std::nothrow) plsa_comm();
+    if (!c) return PLSA_ENOMEM;
+    c->device = device;
+    c->n_ranks = n_ranks;
+    c->rank = rank;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_err = std::string("comm_create: ") + cudaGetErrorString(e);
+        delete c;
+        return PLSA_ECUDA;
+    }
+    if (n_ranks > 1) {
+        Nccl *nc = load_nccl();
+        if (!nc) {
+            cudaStreamDestroy(c->stream);
+            delete c;
+            g_err = "comm_create: libnccl.so.2 could not be loaded";
+            return PLSA_ENCCL;
+        }
+        NcclId u;
+        memcpy(u.bytes, id, PLSA_NCCL_ID_BYTES);
+        const int r = nc->CommInitRank(&c->comm, n_ranks, u, rank);
+        if (r != 0) {
+            cudaStreamDestroy(c->stream);
+            delete c;
+            return nccl_fail(nc, "comm_create: ncclCommInitRank", r);
+        }
+    }
+    *out = c;
+    return PLSA_OK;
+}
+
+API int plsa_comm_destroy(plsa_comm *c)
+{
+    if (!c) return PLSA_OK;
+    cudaSetDevice(c->device);
+    if (c->comm) {
+        Nccl *nc = load_nccl();
+        if (nc) nc->CommDestroy(c->comm);
+    }
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return PLSA_OK;
+}
+
+/* Every rank sends the first n_local slots of ctx's stash; `root` receives them in rank
+ * order into `out` (host, [sum(n_per_rank) * k, m]); n_per_rank is read on every rank. */
+API int plsa_comm_gather_topics(plsa_comm *c, plsa_ctx *ctx, const int32_t *n_per_rank,
+                                int32_t root, float *out)
+{
+    if (!c || !n_per_rank || root < 0 || root >= c->n_ranks) {
+        g_err = "comm_gather_topics: bad arguments";
+        return PLSA_EINVAL;
+    }
+    CHECK_CTX(ctx);
+    if (ctx->device != c->device)
+        return ctx->fail(PLSA_EINVAL, "comm_gather_topics: context and communicator devices differ");
+    const int32_t mine = n_per_rank[c->rank];
+    if (mine < 0 || (mine > 0 && (!ctx->topics_dev.p || mine > ctx->stash_slots)))
+        return ctx->fail(PLSA_EINVAL, "comm_gather_topics: fewer stashed topic matrices than announced");
+    if (!ctx->have_factors) return ctx->fail(PLSA_EINVAL, "comm_gather_topics: no model");
+    const size_t per = (size_t)std::max<int64_t>(ctx->cur().m, 1) * ctx->k;
+    size_t total = 0;
+    for (int r = 0; r < c->n_ranks; ++r) total += (size_t)n_per_rank[r];
+    const bool is_root = c->rank == root;
+    if (is_root && !out && total > 0) return ctx->fail(PLSA_EINVAL, "comm_gather_topics: null output");
+    DevBuf stack;
+    if (is_root && total > 0) CK(stack.ensure(per * total * 4));
+    Nccl *nc = c->n_ranks > 1 ? load_nccl() : nullptr;
+    int r = 0;
+    if (c->n_ranks > 1) {
+        nc->GroupStart();
+        if (is_root) {
+            size_t off = 0;
+            for (int p = 0; p < c->n_ranks && r == 0; ++p) {
+                const size_t cnt = (size_t)n_per_rank[p] * per;
+                if (p != root && cnt > 0)
+                    r = nc->Recv(stack.as<float>() + off, cnt, kNcclFloat, p, c->comm, c->stream);
+                off += cnt;
+            }
+        } else if (mine > 0) {
+            r = nc->Send(ctx->topics_dev.p, (size_t)mine * per, kNcclFloat, root, c->comm, c->stream);
+        }
+        const int r2 = nc->GroupEnd();
+        if (r == 0) r = r2;
+    }
+    cudaError_t ce = cudaSuccess;
+    if (is_root && total > 0) {
+        size_t off = 0;
+        for (int p = 0; p < root; ++p) off += (size_t)n_per_rank[p] * per;
+        if (mine > 0)
+            ce = cudaMemcpyAsync(stack.as<float>() + off, ctx->topics_dev.p, (size_t)mine * per * 4,
+                                 cudaMemcpyDeviceToDevice, c->stream);
+        if (ce == cudaSuccess && r == 0)
+            ce = cudaMemcpyAsync(out, stack.p, per * total * 4, cudaMemcpyDeviceToHost, c->stream);
+    }
+    cudaError_t ce2 = cudaStreamSynchronize(c->stream);
+    if (ce == cudaSuccess) ce = ce2;
+    stack.release();
+    if (r != 0) {
+        const int rc = nccl_fail(nc, "comm_gather_topics", r);
+        ctx->err = g_err;
+        return rc;
+    }
+    if (ce != cudaSuccess)
+        return ctx->fail(PLSA_ECUDA, std::string("comm_gather_topics: ") + cudaGetErrorString(ce));
+    return PLSA_OK;
+}

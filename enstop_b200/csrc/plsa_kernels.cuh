@@ -1,0 +1,478 @@
+/*
+ * plsa_kernels.cuh — sm_100a device code of the pLSA EM engine.
+ *
+ * One generic "row pass" kernel carries the whole EM iteration.  It walks a sparse matrix
+ * whose rows OWN one factor row (k floats) and whose entries GATHER a row of the other
+ * factor:
+ *
+ *   doc pass   rows = documents (CSR of X)   own = P(z|d)[d,:]   gather = P(w|z)^T[w,:]
+ *   term pass  rows = terms     (CSR of X^T) own = P(w|z)^T[w,:] gather = P(z|d)[d,:]
+ *
+ * For every stored entry x of the row it forms the thresholded products
+ * v_z = own_z * gather_z (enstop/plsa.py:95-102), the normaliser sum_z v_z (plsa.py:100),
+ * and adds x * v_z / norm to the row's k accumulators — that is the E-step posterior
+ * (plsa.py:104-105) consumed immediately by the M-step sums (plsa.py:182-194) without the
+ * nnz x k P(z|d,w) array ever existing in memory.  The doc pass row-normalises its result
+ * (plsa.py:199-202); the term pass leaves raw sums and a column-sum kernel produces the
+ * per-topic normalisers (plsa.py:196-198) that the NEXT pass folds into the owned row.
+ *
+ * Lane mapping: a row of k floats is KV*G float4 vectors; G lanes cooperate on one stored
+ * entry (lane j of the group holds topics 4j..4j+3), 32/G entries are in flight per warp
+ * step, the normaliser is a G-lane shuffle reduction.  k = 20 -> G = 5, six entries per
+ * step; k = 128 -> G = 32.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace plsa {
+
+struct Item {          /* one unit of warp work: a row, or a chunk of a long row        */
+    int64_t start;     /* first stored entry                                            */
+    int32_t row;       /* row whose factor this item owns                               */
+    int32_t len;       /* stored entries in this item                                   */
+    int32_t slot;      /* < 0: whole row, result goes to own_new; else partial-sum slot */
+    int32_t pad;
+};
+
+enum { MODE_DOC = 0, MODE_TERM = 1, MODE_LOGLIK = 2 };
+
+struct PassArgs {
+    const Item *items;
+    int64_t n_items;
+    const int32_t *idx;      /* gather-row index of every stored entry                  */
+    const float *val;        /* value of every stored entry                             */
+    const float *own_old;    /* [rows, stride_own]                                      */
+    const float *gat_old;    /* [cols, stride_gat]                                      */
+    const float *own_scale;  /* [kp] folded into the owned row (1/column-sum of P(w|z)) */
+    float *own_new;          /* [rows, stride_own]                                      */
+    float *partial;          /* [slots, kp] raw sums of split rows                      */
+    const float *row_weight; /* MODE_LOGLIK: sample_weight[d]                           */
+    double *ll_partial;      /* MODE_LOGLIK: one double per CTA                         */
+    int32_t stride_own, stride_gat, kp;
+    float thresh;
+};
+
+__device__ __forceinline__ float4 ldg_f4(const float *p)
+{
+    return __ldg(reinterpret_cast<const float4 *>(p));
+}
+
+/* streaming loads of the CSR arrays: read once, keep them out of L1 so the gathered
+ * factor rows stay cached */
+__device__ __forceinline__ int32_t ld_stream_i32(const int32_t *p)
+{
+    int32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ld_stream_f32(const float *p)
+{
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+
+/* Sum over the G lanes of a group; every lane of the group receives the total.
+ * Power-of-two G: xor butterfly.  Other G: cyclic windows W_s(j) = v_j + .. + v_{j+s-1}
+ * (indices mod G) built by doubling, then one window per set bit of G is combined. */
+template <int G>
+__device__ __forceinline__ float group_sum(float v, int gbase, int j)
+{
+    if constexpr (G == 1) {
+        return v;
+    } else if constexpr ((G & (G - 1)) == 0) {
+#pragma unroll
+        for (int off = G / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        return v;
+    } else {
+        float w = v, total = 0.f;
+#pragma unroll
+        for (int b = 0; (1 << b) <= G; ++b) {
+            const int s = 1 << b;
+            if (G & s) {
+                const int off = G & ~((s << 1) - 1); /* set bits above b */
+                if (off == 0)
+                    total += w;
+                else
+                    total += __shfl_sync(0xffffffffu, w, gbase + (j + off) % G);
+            }
+            if ((s << 1) <= G) w += __shfl_sync(0xffffffffu, w, gbase + (j + s) % G);
+        }
+        return total;
+    }
+}
+
+template <int G, int KV, int MODE>
+__global__ void __launch_bounds__(256) row_pass_kernel(const PassArgs a)
+{
+    constexpr int NG = 32 / G;                               /* entries per warp step  */
+    constexpr int UMAX = (KV >= 8) ? 1 : (8 / KV);
+    constexpr int U = (32 / NG) < UMAX ? (32 / NG) : UMAX;   /* steps per index chunk  */
+    constexpr int CH = NG * U;                               /* entries per chunk      */
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int64_t item_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+
+    const int grp = lane / G;
+    const int j = lane - grp * G;
+    const int gbase = grp * G;
+    const bool lane_on = grp < NG; /* 32 % G lanes idle when G does not divide 32 */
+
+    double ll_acc = 0.0;
+    if (item_id < a.n_items) {
+        const Item it = a.items[item_id];
+
+        /* the owned row, with the lazily applied P(w|z) normaliser folded in */
+        float4 own[KV];
+#pragma unroll
+        for (int q = 0; q < KV; ++q) {
+            const int c = 4 * (j + G * q);
+            if (lane_on && c < a.kp) {
+                float4 o = ldg_f4(a.own_old + (int64_t)it.row * a.stride_own + c);
+                const float4 s = ldg_f4(a.own_scale + c);
+                own[q] = make_float4(o.x * s.x, o.y * s.y, o.z * s.z, o.w * s.w);
+            } else {
+                own[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        float4 acc[KV];
+#pragma unroll
+        for (int q = 0; q < KV; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float rw = 1.f;
+        if constexpr (MODE == MODE_LOGLIK) rw = a.row_weight[it.row];
+
+        const int32_t *idx = a.idx + it.start;
+        const float *val = a.val + it.start;
+        const int len = it.len;
+
+        int32_t my_idx = 0;
+        float my_val = 0.f;
+        if (lane < CH && lane < len) {
+            my_idx = ld_stream_i32(idx + lane);
+            my_val = ld_stream_f32(val + lane);
+        }
+        for (int base = 0; base < len; base += CH) {
+            const int cnt = min(CH, len - base);
+            const int32_t cur_idx = my_idx;
+            const float cur_val = my_val;
+            const int nb = base + CH + lane; /* prefetch the next chunk of the row */
+            if (lane < CH && nb < len) {
+                my_idx = ld_stream_i32(idx + nb);
+                my_val = ld_stream_f32(val + nb);
+            }
+
+            float4 g[U][KV];
+            float x[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int src = u * NG + grp;
+                const int32_t w = __shfl_sync(0xffffffffu, cur_idx, src & 31);
+                x[u] = __shfl_sync(0xffffffffu, cur_val, src & 31);
+                const bool ok = lane_on && src < cnt;
+                const float *grow = a.gat_old + (int64_t)w * a.stride_gat;
+#pragma unroll
+                for (int q = 0; q < KV; ++q) {
+                    const int c = 4 * (j + G * q);
+                    g[u][q] = (ok && c < a.kp) ? ldg_f4(grow + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                float part = 0.f;
+#pragma unroll
+                for (int q = 0; q < KV; ++q) {
+                    float4 v;
+                    v.x = g[u][q].x * own[q].x;
+                    v.y = g[u][q].y * own[q].y;
+                    v.z = g[u][q].z * own[q].z;
+                    v.w = g[u][q].w * own[q].w;
+                    if constexpr (MODE != MODE_LOGLIK) { /* plsa.py:98-102 */
+                        v.x = v.x > a.thresh ? v.x : 0.f;
+                        v.y = v.y > a.thresh ? v.y : 0.f;
+                        v.z = v.z > a.thresh ? v.z : 0.f;
+                        v.w = v.w > a.thresh ? v.w : 0.f;
+                    }
+                    g[u][q] = v;
+                    part += (v.x + v.y) + (v.z + v.w);
+                }
+                const float norm = group_sum<G>(part, gbase, j);
+                if constexpr (MODE == MODE_LOGLIK) {
+                    /* plsa.py:383-384; one lane per entry contributes */
+                    if (lane_on && j == 0 && (u * NG + grp) < cnt)
+                        ll_acc += (double)(x[u] * __logf(norm) * rw);
+                } else {
+                    const float c = norm > 0.f ? __fdividef(x[u], norm) : 0.f; /* plsa.py:104 */
+#pragma unroll
+                    for (int q = 0; q < KV; ++q) {
+                        acc[q].x = fmaf(c, g[u][q].x, acc[q].x);
+                        acc[q].y = fmaf(c, g[u][q].y, acc[q].y);
+                        acc[q].z = fmaf(c, g[u][q].z, acc[q].z);
+                        acc[q].w = fmaf(c, g[u][q].w, acc[q].w);
+                    }
+                }
+            }
+        }
+
+        if constexpr (MODE != MODE_LOGLIK) {
+            /* fold the NG groups: group 0 ends up with the row's sums */
+#pragma unroll
+            for (int off = G; off < 32; off <<= 1) {
+#pragma unroll
+                for (int q = 0; q < KV; ++q) {
+                    const float tx = __shfl_down_sync(0xffffffffu, acc[q].x, off & 31);
+                    const float ty = __shfl_down_sync(0xffffffffu, acc[q].y, off & 31);
+                    const float tz = __shfl_down_sync(0xffffffffu, acc[q].z, off & 31);
+                    const float tw = __shfl_down_sync(0xffffffffu, acc[q].w, off & 31);
+                    if (lane + off < NG * G) {
+                        acc[q].x += tx; acc[q].y += ty; acc[q].z += tz; acc[q].w += tw;
+                    }
+                }
+            }
+            float inv = 1.f;
+            if constexpr (MODE == MODE_DOC) {
+                if (it.slot < 0) { /* plsa.py:199-202: divide by the row's total if > 0 */
+                    float part = 0.f;
+#pragma unroll
+                    for (int q = 0; q < KV; ++q)
+                        part += (acc[q].x + acc[q].y) + (acc[q].z + acc[q].w);
+                    float tot = (grp == 0) ? part : 0.f;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1)
+                        tot += __shfl_xor_sync(0xffffffffu, tot, off);
+                    inv = tot > 0.f ? 1.f / tot : 1.f;
+                }
+            }
+            if (grp == 0) {
+                float *dst = (it.slot < 0)
+                                 ? a.own_new + (int64_t)it.row * a.stride_own
+                                 : a.partial + (int64_t)it.slot * a.kp;
+#pragma unroll
+                for (int q = 0; q < KV; ++q) {
+                    const int c = 4 * (j + G * q);
+                    if (c < a.kp)
+                        *reinterpret_cast<float4 *>(dst + c) = make_float4(
+                            acc[q].x * inv, acc[q].y * inv, acc[q].z * inv, acc[q].w * inv);
+                }
+            }
+        }
+    }
+
+    if constexpr (MODE == MODE_LOGLIK) {
+        /* deterministic per-CTA sum: lanes, then warps in order */
+        __shared__ double wsum[8];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+            ll_acc += __shfl_xor_sync(0xffffffffu, ll_acc, off);
+        if (lane == 0) wsum[warp] = ll_acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += wsum[i];
+            a.ll_partial[blockIdx.x] = t;
+        }
+    }
+}
+
+/* Split rows: add the partial sums of each split row in slot order (float64), write the
+ * row; document rows are normalised here (plsa.py:199-202). */
+struct FixArgs {
+    const int32_t *rows;       /* [n_split]   */
+    const int32_t *slot_begin; /* [n_split+1] */
+    const float *partial;      /* [slots, kp] */
+    float *own_new;
+    int32_t n_split, kp, stride_own, normalise;
+};
+
+__global__ void fixup_kernel(const FixArgs a)
+{
+    const int r = blockIdx.x;
+    if (r >= a.n_split) return;
+    const int s0 = a.slot_begin[r], s1 = a.slot_begin[r + 1];
+    __shared__ double red[32];
+    __shared__ double total;
+    double tsum = 0.0;
+    /* each thread owns columns z = tid, tid + blockDim, ...; at most 4 with kp <= 1024 */
+    double colsum[4];
+    int nc = 0;
+    for (int z = threadIdx.x; z < a.kp; z += blockDim.x) {
+        double s = 0.0;
+        for (int sl = s0; sl < s1; ++sl) s += (double)a.partial[(int64_t)sl * a.kp + z];
+        colsum[nc++] = s;
+        tsum += s;
+    }
+    double inv = 1.0;
+    if (a.normalise) {
+        for (int off = 16; off > 0; off >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, off);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tsum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int i = 0; i < (int)((blockDim.x + 31) >> 5); ++i) t += red[i];
+            total = t;
+        }
+        __syncthreads();
+        inv = total > 0.0 ? 1.0 / total : 1.0;
+    }
+    nc = 0;
+    for (int z = threadIdx.x; z < a.kp; z += blockDim.x)
+        a.own_new[(int64_t)a.rows[r] * a.stride_own + z] = (float)(colsum[nc++] * inv);
+}
+
+/* Column sums of the raw P(w|z)^T accumulators -> per-topic scale 1/sum (plsa.py:196-198).
+ * Two deterministic stages: per-CTA float64 partials over a slab of rows, then one CTA. */
+constexpr int COLSUM_CTAS = 296;
+
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float *__restrict__ B,
+                                                            int64_t n_rows, int stride, int kp,
+                                                            double *__restrict__ partial)
+{
+    __shared__ double sm[256];
+    const int64_t per = (n_rows + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = per * blockIdx.x;
+    const int64_t r1 = min(n_rows, r0 + per);
+    for (int zb = 0; zb < kp; zb += 256) {
+        const int width = min(256, kp - zb);       /* columns handled in this sweep    */
+        const int rl = 256 / width;                /* row lanes                        */
+        const int z = threadIdx.x % width, rr = threadIdx.x / width;
+        double s = 0.0;
+        if (rr < rl)
+            for (int64_t r = r0 + rr; r < r1; r += rl) s += (double)B[r * stride + zb + z];
+        sm[threadIdx.x] = s;
+        __syncthreads();
+        if (threadIdx.x < width) {
+            double t = 0.0;
+            for (int i = 0; i < rl; ++i) t += sm[i * width + threadIdx.x];
+            partial[(int64_t)blockIdx.x * kp + zb + threadIdx.x] = t;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void colsum_final_kernel(const double *__restrict__ partial, int n_part, int kp,
+                                    float *__restrict__ scale, double *__restrict__ colnorm)
+{
+    for (int z = threadIdx.x; z < kp; z += blockDim.x) {
+        double t = 0.0;
+        for (int i = 0; i < n_part; ++i) t += partial[(int64_t)i * kp + z];
+        colnorm[z] = t;
+        scale[z] = t > 0.0 ? (float)(1.0 / t) : 1.f;
+    }
+}
+
+__global__ void sum_doubles_kernel(const double *__restrict__ in, int64_t n, double *out)
+{
+    /* single CTA, fixed order */
+    __shared__ double sm[256];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += in[i];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) sm[threadIdx.x] += sm[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sm[0];
+}
+
+/* ---- layout conversion between the reference's arrays and the device layout ---------- */
+/* dense [rows, k] -> padded [rows, stride] (P(z|d); also P(w|z)^T when src is [k, rows]) */
+__global__ void pack_rows_kernel(const float *__restrict__ src, float *__restrict__ dst,
+                                 int64_t rows, int k, int kp, int stride, int transposed)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * kp) return;
+    const int64_t r = i / kp;
+    const int z = (int)(i - r * kp);
+    float v = 0.f;
+    if (z < k) v = transposed ? src[(int64_t)z * rows + r] : src[r * k + z];
+    dst[r * stride + z] = v;
+}
+
+/* padded [rows, stride] (* scale[z]) -> dense [rows, k] or its transpose [k, rows] */
+__global__ void unpack_rows_kernel(const float *__restrict__ src, const float *__restrict__ scale,
+                                   float *__restrict__ dst, int64_t rows, int k, int stride,
+                                   int transposed)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * k) return;
+    if (transposed) { /* consecutive threads -> consecutive rows of one topic: coalesced writes */
+        const int z = (int)(i / rows);
+        const int64_t r = i - (int64_t)z * rows;
+        dst[i] = src[r * stride + z] * (scale ? scale[z] : 1.f);
+    } else {
+        const int64_t r = i / k;
+        const int z = (int)(i - r * k);
+        dst[i] = src[r * stride + z] * (scale ? scale[z] : 1.f);
+    }
+}
+
+/* ---- corpus preparation ------------------------------------------------------------------ */
+__global__ void expand_rows_kernel(const int32_t *__restrict__ indptr, int64_t n_rows,
+                                   int32_t *__restrict__ rows_out)
+{
+    /* one warp per row */
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    for (int32_t p = indptr[r] + lane; p < indptr[r + 1]; p += 32) rows_out[p] = (int32_t)r;
+}
+
+__global__ void histogram_kernel(const int32_t *__restrict__ keys, int64_t n, int32_t *counts)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(counts + keys[i], 1);
+}
+
+__global__ void permute_kernel(const int32_t *__restrict__ perm, int64_t n,
+                               const int32_t *__restrict__ rows_in, const float *__restrict__ vals_in,
+                               int32_t *__restrict__ rows_out, float *__restrict__ vals_out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t p = perm[i];
+    rows_out[i] = rows_in[p];
+    vals_out[i] = vals_in[p];
+}
+
+__global__ void iota_kernel(int32_t *p, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (int32_t)i;
+}
+
+__global__ void weight_vals_kernel(const float *__restrict__ vals, const int32_t *__restrict__ rows,
+                                   const float *__restrict__ w, float *__restrict__ out, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = vals[i] * w[rows[i]];
+}
+
+/* bootstrap: new row i <- base row src[i]; one warp per new row */
+__global__ void gather_rows_kernel(const int32_t *__restrict__ src, int64_t n_new,
+                                   const int32_t *__restrict__ base_indptr,
+                                   const int32_t *__restrict__ base_cols,
+                                   const float *__restrict__ base_vals,
+                                   const int32_t *__restrict__ new_indptr,
+                                   int32_t *__restrict__ cols, float *__restrict__ vals)
+{
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_new) return;
+    const int lane = threadIdx.x & 31;
+    const int32_t b0 = base_indptr[src[r]];
+    const int32_t len = base_indptr[src[r] + 1] - b0;
+    const int32_t o0 = new_indptr[r];
+    for (int32_t p = lane; p < len; p += 32) {
+        cols[o0 + p] = base_cols[b0 + p];
+        vals[o0 + p] = base_vals[b0 + p];
+    }
+}
+
+__global__ void fill_kernel(float *p, int64_t n, float v)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+} // namespace plsa

@@ -1,0 +1,258 @@
+"""pLSA on a B200: the host-side mirror of enstop/plsa.py.
+
+Same names, arguments, defaults and error behaviour as the reference —
+``plsa_init`` (plsa.py:412-513), ``plsa_fit`` (plsa.py:643-730), ``plsa_refit``
+(plsa.py:923-997) and the sklearn-style ``PLSA`` estimator (plsa.py:1000-1285) — with the EM
+loop (``plsa_fit_inner`` / ``plsa_refit_inner``, plsa.py:516-640 / :819-920) carried out by
+hand-written sm_100a kernels behind the C ABI in ``include/plsa_b200.h``.  Host code is
+plain numpy/scipy + ctypes; initialisation stays on the host so that a seed produces the
+reference's exact ``RandomState`` stream (plsa.py:455-456).
+
+Extra keyword-only arguments (``device``, ``context``) and fitted attributes (``n_iter_``,
+``log_likelihood_trace_``) are additive; positional use is unchanged.
+"""
+import os
+
+import numpy as np
+from scipy.sparse import csr_matrix, issparse
+from sklearn.base import BaseEstimator, TransformerMixin
+from sklearn.decomposition import non_negative_factorization
+from sklearn.utils import check_array, check_random_state
+from sklearn.utils.extmath import randomized_svd
+
+from . import _lib
+from .utils import (_check_sample_weight, coherence, log_lift, mean_coherence, mean_log_lift,
+                    normalize, standardize_input)
+
+
+def default_device():
+    return int(os.environ.get("ENSTOP_B200_DEVICE", "0"))
+
+
+def _l2(x):
+    return np.sqrt(np.sum(np.square(x)))
+
+
+def plsa_init(X, k, init="random", rng=np.random):
+    """Initial P(z|d) [n, k] and P(w|z) [k, m], float64, L1 row-normalised.
+
+    ``"random"`` draws P(w|z) first and P(z|d) second from ``rng.rand`` (plsa.py:454-456);
+    ``"nndsvd"`` is the non-negative double SVD start of sklearn's NMF built on
+    ``randomized_svd`` (plsa.py:458-493); ``"nmf"`` runs sklearn's coordinate-descent NMF
+    (plsa.py:495-504); a tuple/list is taken as given (plsa.py:505-506)."""
+    n, m = X.shape
+    if isinstance(init, str) and init == "random":
+        p_w_given_z = rng.rand(k, m)
+        p_z_given_d = rng.rand(n, k)
+    elif isinstance(init, str) and init == "nndsvd":
+        U, S, V = randomized_svd(X, k)
+        p_z_given_d, p_w_given_z = np.zeros(U.shape), np.zeros(V.shape)
+        p_z_given_d[:, 0] = np.sqrt(S[0]) * np.abs(U[:, 0])
+        p_w_given_z[0, :] = np.sqrt(S[0]) * np.abs(V[0, :])
+        for j in range(1, k):
+            x, y = U[:, j], V[j, :]
+            x_pos, y_pos = np.maximum(x, 0), np.maximum(y, 0)
+            x_neg, y_neg = np.abs(np.minimum(x, 0)), np.abs(np.minimum(y, 0))
+            pos = (_l2(x_pos), _l2(y_pos))
+            neg = (_l2(x_neg), _l2(y_neg))
+            if pos[0] * pos[1] > neg[0] * neg[1]:
+                u, v, sigma = x_pos / pos[0], y_pos / pos[1], pos[0] * pos[1]
+            else:
+                u, v, sigma = x_neg / neg[0], y_neg / neg[1], neg[0] * neg[1]
+            scale = np.sqrt(S[j] * sigma)
+            p_z_given_d[:, j] = scale * u
+            p_w_given_z[j, :] = scale * v
+    elif isinstance(init, str) and init == "nmf":
+        p_z_given_d, p_w_given_z, _ = non_negative_factorization(
+            X, n_components=k, init="nndsvd", solver="cd", beta_loss=2, tol=1e-2, max_iter=100)
+    elif isinstance(init, (tuple, list)):
+        p_z_given_d, p_w_given_z = init
+        p_z_given_d = np.array(p_z_given_d, dtype=np.float64)
+        p_w_given_z = np.array(p_w_given_z, dtype=np.float64)
+        if p_z_given_d.shape != (n, k) or p_w_given_z.shape != (k, m):
+            raise ValueError("init arrays must have shapes ({}, {}) and ({}, {})".format(
+                n, k, k, m))
+    else:
+        raise ValueError("Unrecognized init {}".format(init))
+    normalize(p_w_given_z, axis=1)
+    normalize(p_z_given_d, axis=1)
+    return p_z_given_d, p_w_given_z
+
+
+def _as_csr(X):
+    if not issparse(X):
+        X = csr_matrix(X)
+    elif X.format != "csr":
+        X = X.tocsr()
+    return X
+
+
+def _open_context(X, device, context):
+    """(context, owned).  A caller-supplied context already holds the corpus."""
+    if context is not None:
+        return context, False
+    ctx = _lib.Context(default_device() if device is None else device)
+    try:
+        ctx.upload_csr(_as_csr(X))
+    except Exception:
+        ctx.close()
+        raise
+    return ctx, True
+
+
+def plsa_fit(X, k, sample_weight, init="random", n_iter=100, n_iter_per_test=10,
+             tolerance=0.001, e_step_thresh=1e-32, random_state=None, *, device=None,
+             context=None, return_info=False):
+    """Fit pLSA with ``k`` topics; returns ``(p_z_given_d [n,k], p_w_given_z [k,m])`` float32.
+
+    Drop-in for enstop.plsa.plsa_fit (plsa.py:643-730).  ``context`` (an
+    ``enstop_b200._lib.Context`` whose resident corpus is X) skips the upload — used by the
+    ensemble for its bootstrapped members."""
+    rng = check_random_state(random_state)
+    p_z_given_d, p_w_given_z = plsa_init(X, k, init=init, rng=rng)
+    p_z_given_d = p_z_given_d.astype(np.float32, order="C")
+    p_w_given_z = p_w_given_z.astype(np.float32, order="C")
+    sample_weight = np.asarray(sample_weight, dtype=np.float32)
+    use_sample_weights = bool(np.any(sample_weight != 1.0))  # plsa.py:712
+
+    ctx, owned = _open_context(X, device, context)
+    try:
+        ctx.set_factors(p_z_given_d, p_w_given_z)
+        ctx.set_sample_weight(sample_weight)
+        iters, trace = ctx.em(n_iter, n_iter_per_test, tolerance, e_step_thresh, refit=False,
+                              use_sample_weights=use_sample_weights)
+        p_z_given_d, p_w_given_z = ctx.get_factors()
+        info = {"n_iter": iters, "ll_trace": trace, "em_ms": ctx.last_em_ms,
+                "launches": ctx.launches}
+    finally:
+        if owned:
+            ctx.close()
+    if return_info:
+        return p_z_given_d, p_w_given_z, info
+    return p_z_given_d, p_w_given_z
+
+
+def plsa_refit(X, topics, sample_weight, n_iter=50, n_iter_per_test=10, tolerance=0.005,
+               e_step_thresh=1e-32, random_state=None, *, device=None, context=None,
+               return_info=False):
+    """Estimate P(z|d) for documents X against frozen ``topics`` [k, m].
+
+    Drop-in for enstop.plsa.plsa_refit (plsa.py:923-997): fresh ``rng.rand(n, k)`` start,
+    E-step + P(z|d)-only M-step; as in the reference the loop always runs ``n_iter``
+    iterations (its early stop is guarded by ``LL > 0``, plsa.py:913)."""
+    topics = np.ascontiguousarray(topics, dtype=np.float32)
+    k = topics.shape[0]
+    rng = check_random_state(random_state)
+    p_z_given_d = rng.rand(X.shape[0], k)
+    normalize(p_z_given_d, axis=1)
+    p_z_given_d = p_z_given_d.astype(np.float32)
+    sample_weight = np.asarray(sample_weight, dtype=np.float32)
+
+    ctx, owned = _open_context(X, device, context)
+    try:
+        ctx.set_factors(p_z_given_d, topics)
+        ctx.set_sample_weight(sample_weight)
+        iters, _ = ctx.em(n_iter, n_iter_per_test, tolerance, e_step_thresh, refit=True)
+        p_z_given_d, _ = ctx.get_factors(want_pwz=False)
+        info = {"n_iter": iters, "em_ms": ctx.last_em_ms, "launches": ctx.launches}
+    finally:
+        if owned:
+            ctx.close()
+    if return_info:
+        return p_z_given_d, info
+    return p_z_given_d
+
+
+class PLSA(BaseEstimator, TransformerMixin):
+    """Probabilistic Latent Semantic Analysis, sklearn-style (mirrors plsa.py:1000-1285).
+
+    Parameters are the reference's (plsa.py:1074-1084): ``n_components=10``,
+    ``init="random"`` (``"random"``, ``"nndsvd"``, ``"nmf"`` or a tuple of arrays),
+    ``n_iter=100``, ``n_iter_per_test=10``, ``tolerance=0.001``, ``e_step_thresh=1e-32``,
+    ``transform_random_seed=42``, ``random_state=None``; plus ``device`` (CUDA ordinal,
+    default ``$ENSTOP_B200_DEVICE`` or 0).
+
+    Attributes: ``components_`` (P(w|z), [n_topics, n_words] float32), ``embedding_``
+    (P(z|d), [n_docs, n_topics]), ``training_data_``; additionally ``n_iter_`` and
+    ``log_likelihood_trace_`` (the values the early-stop test saw).
+    """
+
+    def __init__(self, n_components=10, init="random", n_iter=100, n_iter_per_test=10,
+                 tolerance=0.001, e_step_thresh=1e-32, transform_random_seed=42,
+                 random_state=None, device=None):
+        self.n_components = n_components
+        self.init = init
+        self.n_iter = n_iter
+        self.n_iter_per_test = n_iter_per_test
+        self.tolerance = tolerance
+        self.e_step_thresh = e_step_thresh
+        self.transform_random_seed = transform_random_seed
+        self.random_state = random_state
+        self.device = device
+
+    def fit(self, X, y=None, sample_weight=None):
+        self.fit_transform(X, sample_weight=sample_weight)
+        return self
+
+    def fit_transform(self, X, y=None, sample_weight=None):
+        X = check_array(X, accept_sparse="csr")
+        X = standardize_input(X)
+        if not issparse(X):
+            X = csr_matrix(X)
+        sample_weight = _check_sample_weight(sample_weight, X, dtype=np.float32)
+        if np.any(X.data < 0):
+            raise ValueError("PLSA is only valid for matrices with non-negative entries")
+
+        row_sums = np.array(X.sum(axis=1).T)[0]
+        good_rows = row_sums != 0
+        if not np.all(good_rows):
+            zero_rows_found = True
+            data_for_fitting = X[good_rows]
+            # plsa.py:1144 vs :1156-1164 leaves the weights unaligned with the stripped
+            # matrix; the weights of the kept rows are what is meant
+            sample_weight = sample_weight[good_rows]
+        else:
+            zero_rows_found = False
+            data_for_fitting = X
+
+        U, V, info = plsa_fit(data_for_fitting, self.n_components, sample_weight, self.init,
+                              self.n_iter, self.n_iter_per_test, self.tolerance,
+                              self.e_step_thresh, self.random_state, device=self.device,
+                              return_info=True)
+        if zero_rows_found:
+            self.embedding_ = np.zeros((X.shape[0], self.n_components))
+            self.embedding_[good_rows] = U
+        else:
+            self.embedding_ = U
+        self.components_ = V
+        self.training_data_ = X
+        self.n_iter_ = info["n_iter"]
+        self.log_likelihood_trace_ = info["ll_trace"]
+        return self.embedding_
+
+    def transform(self, X, y=None):
+        X = check_array(X, accept_sparse="csr")
+        random_state = check_random_state(self.transform_random_seed)
+        sample_weight = _check_sample_weight(None, X, dtype=np.float32)
+        if not issparse(X):
+            X = csr_matrix(X)
+        return plsa_refit(X, self.components_, sample_weight, n_iter=50, n_iter_per_test=5,
+                          tolerance=0.001, random_state=random_state, device=self.device)
+
+    def coherence(self, topic_num=None, n_words=20):
+        if not isinstance(topic_num, int) and topic_num is not None:
+            raise ValueError("Topic number must be an integer or None.")
+        if topic_num is None:
+            return mean_coherence(self.components_, self.training_data_, n_words)
+        if 0 <= topic_num < self.n_components:
+            return coherence(self.components_, topic_num, self.training_data_, n_words)
+        raise ValueError("Topic number must be in range 0 to {}".format(self.n_components))
+
+    def log_lift(self, topic_num=None, n_words=20):
+        if not isinstance(topic_num, int) and topic_num is not None:
+            raise ValueError("Topic number must be an integer or None.")
+        if topic_num is None:
+            return mean_log_lift(self.components_, self.training_data_, n_words)
+        if 0 <= topic_num < self.n_components:
+            return log_lift(self.components_, topic_num, self.training_data_, n_words)
+        raise ValueError("Topic number must be in range 0 to {}".format(self.n_components))

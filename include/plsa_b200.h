@@ -1,0 +1,158 @@
+/*
+ * plsa_b200 — C ABI of the B200-native pLSA EM engine (libplsa_b200.so).
+ *
+ * This is the drop-in boundary for the EM hot path of lmcinnes/enstop.  The reference has
+ * no FFI of its own; its raw-array seam is the pair of numba entry points
+ *     enstop/plsa.py:516-640   plsa_fit_inner(X_rows, X_cols, X_vals, p_w_given_z,
+ *                              p_z_given_d, sample_weight, n_iter, n_iter_per_test,
+ *                              tolerance, e_step_thresh, use_sample_weights)
+ *     enstop/plsa.py:819-920   plsa_refit_inner(X_rows, X_cols, X_vals, topics,
+ *                              p_z_given_d, sample_weight, n_iter, n_iter_per_test,
+ *                              tolerance, e_step_thresh)
+ * (contiguous int32 / float32 buffers, factors mutated in place, scalars by value), and
+ * the precedent for swapping the backend is enstop/enstop_.py:52-53,92-114 where
+ * `enstop.cuda_plsa.plsa_fit` replaces `enstop.plsa.plsa_fit`.  The one-shot entry points
+ * below (plsa_b200_fit_inner / plsa_b200_refit_inner) bind exactly that seam; the context
+ * API underneath is what the Python host layer (enstop_b200/plsa.py) uses to keep the
+ * corpus resident across calls (ensemble members, transform after fit).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a PLSA_E* code otherwise; no C++ exception or
+ *     abort crosses this boundary; plsa_last_error() gives the message.
+ *   - all pointers are HOST pointers unless the name says `_device`; the caller owns
+ *     every host buffer; the library owns all device memory behind the opaque context.
+ *   - layouts are the reference's: P(z|d) is [n, k] row-major float32, P(w|z) is [k, m]
+ *     row-major float32 (the device keeps P(w|z) transposed and padded; that is private).
+ *   - a context is bound to one device and one stream and must not be used from two
+ *     threads at once; different contexts are independent (one per ensemble worker).
+ */
+#ifndef PLSA_B200_H
+#define PLSA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLSA_OK 0
+#define PLSA_EINVAL 1   /* bad argument / state                                     */
+#define PLSA_ECUDA 2    /* a CUDA runtime call or kernel failed                      */
+#define PLSA_ENOMEM 3   /* host or device allocation failed                          */
+#define PLSA_ENCCL 4    /* NCCL could not be loaded or a collective failed           */
+
+#define PLSA_MAX_K 1024 /* same ceiling as the incumbent GPU path (cuda_plsa.py:135) */
+
+typedef struct plsa_ctx plsa_ctx;
+
+/* ---- library / device ------------------------------------------------------------ */
+int plsa_version(void);                      /* 100 * major + minor                   */
+int plsa_device_count(int *count);
+const char *plsa_last_error(const plsa_ctx *ctx); /* ctx == NULL: last error of a call
+                                                     that had no context (thread local) */
+
+int plsa_ctx_create(int device, plsa_ctx **ctx);
+int plsa_ctx_destroy(plsa_ctx *ctx);
+
+/* ---- corpus ------------------------------------------------------------------------ */
+/* Upload a CSR doc-term matrix (what enstop/plsa.py:714 turns into COO triplets).  The
+ * transposed (term-major) copy used by the P(w|z) pass is built on the device. */
+int plsa_upload_csr(plsa_ctx *ctx, const int32_t *indptr, const int32_t *indices,
+                    const float *data, int64_t n_docs, int64_t n_terms, int64_t nnz);
+/* Same from row-sorted COO triplets — the argument form of plsa_fit_inner. */
+int plsa_upload_coo(plsa_ctx *ctx, const int32_t *rows, const int32_t *cols,
+                    const float *vals, int64_t n_docs, int64_t n_terms, int64_t nnz);
+/* Bootstrap resample (enstop/enstop_.py:86-88, B = A[bootstrap_sample_indices]): the
+ * working corpus becomes rows `row_idx[0..n_rows)` of the uploaded one, gathered on the
+ * device.  row_idx == NULL restores the uploaded corpus. */
+int plsa_bootstrap(plsa_ctx *ctx, const int32_t *row_idx, int64_t n_rows);
+int plsa_corpus_shape(const plsa_ctx *ctx, int64_t *n_docs, int64_t *n_terms, int64_t *nnz);
+
+/* ---- model state -------------------------------------------------------------------- */
+/* p_z_given_d [n_docs, k], p_w_given_z [k, n_terms] (plsa.py:709-710 float32 C-order). */
+int plsa_set_factors(plsa_ctx *ctx, const float *p_z_given_d, const float *p_w_given_z,
+                     int32_t k);
+/* sample_weight [n_docs] or NULL for all ones (plsa.py:1144). */
+int plsa_set_sample_weight(plsa_ctx *ctx, const float *sample_weight);
+/* Either output may be NULL. */
+int plsa_get_factors(plsa_ctx *ctx, float *p_z_given_d, float *p_w_given_z);
+/* ---- EM ------------------------------------------------------------------------------- */
+/* The loop of plsa_fit_inner (refit == 0; plsa.py:583-640) or plsa_refit_inner
+ * (refit != 0; plsa.py:884-920) on the resident corpus and factors.
+ *   use_sample_weights  plsa.py:606 — P(w|z) accumulates s*sample_weight[d]
+ *   iters_run           EM iterations actually carried out (early stop, plsa.py:635)
+ *   ll_trace/ll_cap     optional: log-likelihood before the loop, then every tested value
+ *   n_ll                number of entries the trace would hold */
+int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double tolerance,
+            float e_step_thresh, int32_t refit, int32_t use_sample_weights,
+            int32_t *iters_run, double *ll_trace, int32_t ll_cap, int32_t *n_ll);
+/* log_likelihood (plsa.py:329-386) of the resident model, float64 reduction. */
+int plsa_log_likelihood(plsa_ctx *ctx, double *ll);
+
+/* ---- measurement ------------------------------------------------------------------------ */
+/* Device time of the last plsa_em loop (CUDA events on the context's stream). */
+int plsa_last_em_ms(const plsa_ctx *ctx, float *ms);
+/* With profiling on, every kernel launch inside plsa_em is bracketed by CUDA events on
+ * the context's stream.  Slots: see PLSA_PROF_* . */
+#define PLSA_PROF_DOC_PASS 0   /* E-step + P(z|d) M-step over the doc-major copy        */
+#define PLSA_PROF_WORD_PASS 1  /* E-step + P(w|z) M-step over the term-major copy      */
+#define PLSA_PROF_FIXUP 2      /* ordered sums of split rows                           */
+#define PLSA_PROF_NORMALIZE 3  /* column sums + P(w|z) renormalisation                 */
+#define PLSA_PROF_LOGLIK 4     /* log-likelihood pass                                  */
+#define PLSA_PROF_SLOTS 5
+int plsa_set_profiling(plsa_ctx *ctx, int32_t on);
+int plsa_get_profile(plsa_ctx *ctx, double *ms /*[PLSA_PROF_SLOTS]*/,
+                     int64_t *launches /*[PLSA_PROF_SLOTS]*/);
+/* Kernel launches issued by this context since creation (bench "gpu_launches"). */
+int plsa_launch_count(const plsa_ctx *ctx, int64_t *launches);
+/* Tunables: "chunk" (max stored entries per work item; longer rows are split). */
+int plsa_set_option(plsa_ctx *ctx, const char *name, int64_t value);
+
+/* ---- one-shot drop-ins for the reference's raw-array seam --------------------------------- */
+/* plsa.py:516-640.  p_w_given_z [k, m] and p_z_given_d [n, k] are updated in place. */
+int plsa_b200_fit_inner(const int32_t *X_rows, const int32_t *X_cols, const float *X_vals,
+                        int64_t nnz, float *p_w_given_z, float *p_z_given_d,
+                        const float *sample_weight, int64_t n_docs, int64_t n_terms,
+                        int32_t k, int32_t n_iter, int32_t n_iter_per_test,
+                        double tolerance, float e_step_thresh, int32_t use_sample_weights,
+                        int32_t device, int32_t *iters_run);
+/* plsa.py:819-920.  topics [k, m] is read only; p_z_given_d [n, k] is updated in place. */
+int plsa_b200_refit_inner(const int32_t *X_rows, const int32_t *X_cols, const float *X_vals,
+                          int64_t nnz, const float *topics, float *p_z_given_d,
+                          const float *sample_weight, int64_t n_docs, int64_t n_terms,
+                          int32_t k, int32_t n_iter, int32_t n_iter_per_test,
+                          double tolerance, float e_step_thresh, int32_t device,
+                          int32_t *iters_run);
+
+/* ---- ensemble: topic stash + gather (enstop_.py:209-231) ------------------------------------ */
+/* plsa_topics (enstop_.py:56-115) returns only P(w|z); ensemble_of_topics stacks the
+ * members' results with np.vstack (enstop_.py:231).  Here every finished member leaves its
+ * P(w|z) [k, n_terms] (reference layout, float32) in slot `slot` of an n_slots-deep
+ * device-side stash owned by the context, and one gather moves all of them to the host. */
+int plsa_stash_topics(plsa_ctx *ctx, int32_t slot, int32_t n_slots);
+/* The stash as a DEVICE pointer (valid until the next stash/destroy on this context). */
+int plsa_topics_device(plsa_ctx *ctx, void **device_ptr, int64_t *floats_per_slot);
+
+/* Single process, one context per device: slots [0, n_slots[i]) of ctxs[i] are sent to
+ * ctxs[0]'s device with NCCL send/recv over NVLink (ncclCommInitAll) and copied to `out`
+ * (host, [sum(n_slots) * k, n_terms], context order then slot order).  One context, or no
+ * remote slots, never touches NCCL. */
+int plsa_gather_topics(plsa_ctx **ctxs, int32_t n_ctx, const int32_t *n_slots, float *out);
+
+/* One process per GPU (torchrun-style launch).  Rank 0 obtains a unique id, the caller's
+ * own rendezvous hands its PLSA_NCCL_ID_BYTES bytes to every rank, each rank creates a
+ * communicator; plsa_comm_gather_topics sends slots [0, n_per_rank[rank]) of ctx's stash to
+ * `root`, which receives them in rank order into `out` (host; ignored on other ranks). */
+#define PLSA_NCCL_ID_BYTES 128
+typedef struct plsa_comm plsa_comm;
+int plsa_nccl_unique_id(char *id /*[PLSA_NCCL_ID_BYTES]*/);
+int plsa_comm_create(int device, int32_t n_ranks, int32_t rank,
+                     const char *id /*[PLSA_NCCL_ID_BYTES]*/, plsa_comm **comm);
+int plsa_comm_destroy(plsa_comm *comm);
+int plsa_comm_gather_topics(plsa_comm *comm, plsa_ctx *ctx, const int32_t *n_per_rank,
+                            int32_t root, float *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLSA_B200_H */

@@ -89,12 +89,19 @@ def lib():
     L.oracle_refit_inner_f64.restype = _i64
     L.oracle_normalize_rows_f64.argtypes = [_f64p, _i64, _i64]
     L.oracle_normalize_rows_f64.restype = None
+    L.oracle_set_num_threads.argtypes = [ctypes.c_int]
+    L.oracle_set_num_threads.restype = ctypes.c_int
     _lib = L
     return L
 
 
 def _p(a, ct):
     return a.ctypes.data_as(ct)
+
+
+def set_num_threads(n=0):
+    """Threads used by the parallel (prange) loops; 0 = all cores.  Returns the count."""
+    return int(lib().oracle_set_num_threads(int(n)))
 
 
 def _coo(X, dtype):

@@ -8,6 +8,7 @@
  * the .npz files under tests/golden; checked by tests/test_oracle_golden.py).
  */
 #include <math.h>
+#include <omp.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -112,4 +113,12 @@ API void oracle_normalize_rows_f64(double *a, int64_t n_rows, int64_t n_cols)
         if (marginal > 0.0)
             for (int64_t j = 0; j < n_cols; ++j) a[i * n_cols + j] /= marginal;
     }
+}
+
+/* Thread count of the `prange` loops (numba: NUMBA_NUM_THREADS).  n <= 0 restores the
+ * OpenMP default.  Returns the count now in effect. */
+API int oracle_set_num_threads(int n)
+{
+    omp_set_num_threads(n > 0 ? n : omp_get_num_procs());
+    return omp_get_max_threads();
 }

@@ -1,0 +1,147 @@
+"""CPU: the C-ABI library loads and exports every declared symbol, the host-side mirror of
+the reference API behaves like the reference before any device work, and the product path
+fails loudly (no CPU fallback) when there is no GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+from conftest import ROOT
+
+from enstop_b200 import _lib, plsa, synth, utils
+from oracle import oracle
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "plsa_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(plsa_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    _lib.build()
+    L = _lib.lib()
+    names = header_functions()
+    assert len(names) >= 25
+    for name in names:
+        assert hasattr(L, name), name
+    # and the binding table covers exactly the header
+    assert sorted(_lib.SIGNATURES) == names
+    assert L.plsa_version() >= 100
+
+
+def test_binary_is_sm100a_only():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.SO_PATH], stdout=subprocess.PIPE, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_\d+a?", out.stdout))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_silent_cpu_fallback():
+    if _lib.device_count() > 0:
+        pytest.skip("a GPU is present")
+    X = synth.make_corpus(50, 60, 500, seed=0)
+    with pytest.raises(_lib.PlsaError):
+        plsa.plsa_fit(X, 3, np.ones(50, dtype=np.float32), n_iter=2)
+    with pytest.raises(_lib.PlsaError):
+        plsa.PLSA(n_components=3).fit(X)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "enstop_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(base, f)).read()
+                assert "oracle" not in text.lower().replace("oracle (", ""), os.path.join(base, f)
+
+
+def test_random_init_is_the_references_stream(golden_c1_zipf):
+    """plsa.py:455-456: P(w|z) drawn first, then P(z|d); float64 L1 normalisation; the
+    float32 cast equals the reference's own initial factors stored in the fixture."""
+    g, X = golden_c1_zipf
+    pzd, pwz = plsa.plsa_init(X, 10, "random", np.random.RandomState(42))
+    assert pzd.dtype == np.float64 and pwz.dtype == np.float64
+    assert np.array_equal(pzd.astype(np.float32), g["pzd0"])
+    assert np.array_equal(pwz.astype(np.float32), g["pwz0"])
+    opzd, opwz = oracle.plsa_init_random(X.shape[0], X.shape[1], 10, np.random.RandomState(42))
+    assert np.allclose(pzd, opzd, rtol=1e-15) and np.allclose(pwz, opwz, rtol=1e-15)
+
+
+def test_init_variants():
+    X = synth.make_corpus(200, 300, 6000, seed=2, planted=True, k_true=4).astype(np.float64)
+    for init in ("nndsvd", "nmf"):
+        pzd, pwz = plsa.plsa_init(X, 4, init, np.random.RandomState(0))
+        assert pzd.shape == (200, 4) and pwz.shape == (4, 300)
+        assert pzd.min() >= 0 and pwz.min() >= 0
+        assert np.allclose(pwz.sum(axis=1), 1.0)
+        rows = pzd.sum(axis=1)
+        assert np.all(np.isclose(rows, 1.0) | (rows == 0.0))
+    a, b = np.random.rand(200, 4), np.random.rand(4, 300)
+    pzd, pwz = plsa.plsa_init(X, 4, (a, b))
+    assert np.allclose(pzd, a / a.sum(1, keepdims=True))
+    with pytest.raises(ValueError, match="Unrecognized init"):
+        plsa.plsa_init(X, 4, "bogus")
+    with pytest.raises(ValueError):
+        plsa.plsa_init(X, 4, (a[:, :3], b))
+
+
+def test_normalize_semantics():
+    a = np.array([[1.0, 3.0], [0.0, 0.0], [2.0, 2.0]])
+    utils.normalize(a, axis=1)
+    assert np.allclose(a, [[0.25, 0.75], [0.0, 0.0], [0.5, 0.5]])
+    b = np.array([[1.0, 0.0], [3.0, 0.0]])
+    utils.normalize(b, axis=0)
+    assert np.allclose(b, [[0.25, 0.0], [0.75, 0.0]])
+    c = np.random.RandomState(0).rand(5, 7)
+    d = c.copy()
+    utils.normalize(c, axis=1)
+    oracle.normalize_rows(d)
+    assert np.allclose(c, d, rtol=1e-15)
+
+
+def test_standardize_input_and_validation():
+    Xi = sp.csr_matrix(np.array([[1, 2], [0, 3]], dtype=np.int64))
+    assert utils.standardize_input(Xi) is Xi
+    Xf = utils.standardize_input(Xi.astype(np.float64))
+    assert np.allclose(Xf.toarray(), [[1 / 3, 2 / 3], [0, 1]])
+    Xn = sp.csr_matrix(np.array([[1.0, -2.0], [0.0, 3.0]]))
+    with pytest.raises(ValueError, match="non-negative"):
+        plsa.PLSA(n_components=2).fit(Xn)   # raised before any device work
+    m = plsa.PLSA()
+    assert m.get_params()["n_components"] == 10 and m.get_params()["e_step_thresh"] == 1e-32
+    assert m.get_params()["transform_random_seed"] == 42 and m.get_params()["n_iter"] == 100
+
+
+def test_metrics_match_a_direct_computation():
+    X = synth.make_corpus(120, 80, 2500, seed=4, planted=True, k_true=3)
+    topics = np.random.RandomState(0).rand(3, 80)
+    topics /= topics.sum(axis=1, keepdims=True)
+    # log lift over the full vocabulary (utils.py:70-74)
+    p = np.asarray(X.sum(axis=0), dtype=np.float64).ravel()
+    p /= p.sum()
+    ok = p > 0
+    expect = np.log(np.sum(topics[1][ok] / p[ok]) / 80)
+    assert np.isclose(utils.log_lift(topics, 1, X), expect)
+    # coherence (utils.py:196-207)
+    top = np.argsort(topics[0])[-5:]
+    D = (X > 0).toarray()
+    ndw = D.sum(axis=0)
+    tot = 0.0
+    for i in range(4):
+        for j in range(i + 1, 5):
+            tot += np.log((np.sum(D[:, top[i]] & D[:, top[j]]) + 1.0) / ndw[top[i]])
+    assert np.isclose(utils.coherence(topics, 0, X, n_words=5), tot)
+    assert np.isfinite(utils.mean_coherence(topics, X, 5)) and np.isfinite(utils.mean_log_lift(topics, X))
+
+
+def test_synth_recipe():
+    X, info = synth.make_corpus(2000, 5000, 200_000, seed=1, return_info=True)
+    assert abs(X.nnz - 200_000) / 200_000 < 0.03
+    assert X.dtype == np.int32 and X.has_sorted_indices
+    assert info["sum_counts"] == info["tokens"]
+    Y = synth.make_corpus(2000, 5000, 200_000, seed=1)
+    assert (X != Y).nnz == 0
