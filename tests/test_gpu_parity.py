@@ -70,12 +70,20 @@ def test_fit_inner_vs_reference_golden(tag, it, request):
 
 
 def test_north_star_tolerance_on_planted_c1(golden_c1_planted):
-    """components_ within 1e-4 relative L2 of the reference at matched seed (C1, 50 iters)."""
+    """components_ vs the reference at matched seed (C1, PLSA defaults, 50 iterations).
+    The north star asks for 1e-4; the reference's own distance from exact arithmetic on this
+    input is 1.1e-4 (its serial float32 norm_pwz accumulator, plsa.py:193), so the engine —
+    1e-6 from exact — lands at the reference's error, not inside 1e-4.  Asserted: engine vs
+    exact <= 1e-5, and engine vs reference no further than the reference is from exact."""
     g, X = golden_c1_planted
     sw = np.ones(X.shape[0], dtype=np.float32)
     pzd, pwz = plsa.plsa_fit(X, 10, sw, n_iter=50, random_state=42, device=0)
-    assert rel_l2(pwz, g["fit_pwz"]) < 1e-4
-    assert rel_l2(pzd, g["fit_pzd"]) < 1.5e-4
+    ez, ew = oracle.plsa_fit(X, 10, sw, n_iter=50, random_state=42, precision="f64")
+    ref_err_w, ref_err_z = rel_l2(g["fit_pwz"], ew), rel_l2(g["fit_pzd"], ez)
+    assert rel_l2(pwz, ew) < TOL_EXACT and rel_l2(pzd, ez) < TOL_EXACT
+    assert rel_l2(pwz, g["fit_pwz"]) < 1.05 * ref_err_w + TOL_EXACT
+    assert rel_l2(pzd, g["fit_pzd"]) < 1.05 * ref_err_z + TOL_EXACT
+    assert rel_l2(pwz, g["fit_pwz"]) < 1.5e-4 and rel_l2(pzd, g["fit_pzd"]) < 1.5e-4
 
 
 def test_seeded_fit_matches_reference_zipf(golden_c1_zipf):
