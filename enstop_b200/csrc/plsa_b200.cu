@@ -6,8 +6,8 @@
  * (ensemble members, transform).  Device code is in plsa_kernels.cuh.
  *
  * Data layout in HBM (per context):
- *   doc-major CSR   indptr[n+1] i32, cols[nnz] i32, vals[nnz] f32      (working corpus)
- *   term-major CSR  rows[nnz] i32, vals[nnz] f32 (+ vals*sample_weight) (built on device)
+ *   doc-major CSR   indptr[n+1] i32, ent[nnz] {term i32, count f32}     (working corpus)
+ *   term-major CSR  ent[nnz] {doc i32, count f32} (+ a sample-weighted copy), built on device
  *   P(z|d)          A[2][n, strideA] f32, ping-pong
  *   P(w|z)^T        B[2][m, strideB] f32, ping-pong, RAW column-unnormalised sums;
  *                   scale[kp] = 1 / column sum is folded in by the next pass
@@ -59,9 +59,11 @@ struct DevBuf {
 
 struct Corpus {
     int64_t n = 0, m = 0, nnz = 0;
-    DevBuf indptr, cols, vals;
+    DevBuf indptr, ent; /* ent: int2 {column, value bits} [nnz + ENT_SLACK], slack zeroed */
     std::vector<int32_t> h_indptr;
 };
+
+static inline size_t ent_bytes(int64_t nnz) { return (size_t)(nnz + ENT_SLACK) * sizeof(int2); }
 
 struct ItemSet {
     DevBuf items, split_rows, slot_begin;
@@ -84,7 +86,7 @@ struct plsa_ctx {
     const Corpus &cur() const { return use_boot ? boot : base; }
 
     /* term-major copy of the working corpus */
-    DevBuf t_rows, t_vals, t_valsw, t_scratch;
+    DevBuf t_ent, t_entw, up_cols, up_vals;
     std::vector<int32_t> h_tindptr;
     bool t_ready = false, t_weighted_ready = false;
 
@@ -301,11 +303,10 @@ static int build_term_major(plsa_ctx *ctx)
     Corpus &c = ctx->cur();
     const int64_t nnz = c.nnz, n = c.n, m = c.m;
     cudaStream_t s = ctx->stream;
-    DevBuf rows_exp, perm_in, perm_out, keys_out, counts, tmp;
-    int rc = PLSA_OK;
+    DevBuf rows_exp, keys_in, perm_in, perm_out, keys_out, tindptr, tmp;
     auto cleanup = [&]() {
-        rows_exp.release(); perm_in.release(); perm_out.release();
-        keys_out.release(); counts.release(); tmp.release();
+        rows_exp.release(); keys_in.release(); perm_in.release(); perm_out.release();
+        keys_out.release(); tindptr.release(); tmp.release();
     };
 #define CKT(expr)                                                                             \
     do {                                                                                      \
@@ -317,46 +318,46 @@ static int build_term_major(plsa_ctx *ctx)
         }                                                                                     \
     } while (0)
     const size_t nz = (size_t)std::max<int64_t>(nnz, 1);
-    CKT(ctx->t_rows.ensure(nz * 4));
-    CKT(ctx->t_vals.ensure(nz * 4));
-    CKT(rows_exp.ensure(nz * 4));
-    CKT(perm_in.ensure(nz * 4));
-    CKT(perm_out.ensure(nz * 4));
-    CKT(keys_out.ensure(nz * 4));
-    CKT(counts.ensure((size_t)(m + 1) * 4));
+    CKT(ctx->t_ent.ensure(ent_bytes(nnz)));
+    CKT(cudaMemsetAsync(ctx->t_ent.as<int2>() + nnz, 0, ENT_SLACK * sizeof(int2), s));
     ctx->h_tindptr.assign((size_t)m + 1, 0);
     if (nnz > 0) {
+        CKT(rows_exp.ensure(nz * 4));
+        CKT(keys_in.ensure(nz * 4));
+        CKT(perm_in.ensure(nz * 4));
+        CKT(perm_out.ensure(nz * 4));
+        CKT(keys_out.ensure(nz * 4));
+        CKT(tindptr.ensure((size_t)(m + 1) * 4));
         const int T = 256;
-        expand_rows_kernel<<<(unsigned)cdiv(n * 32, T), T, 0, s>>>(c.indptr.as<int32_t>(), n,
-                                                                  rows_exp.as<int32_t>());
+        expand_rows_kernel<<<(unsigned)cdiv(n * 32, T), T, 0, s>>>(
+            c.indptr.as<int32_t>(), n, c.ent.as<int2>(), rows_exp.as<int32_t>(),
+            keys_in.as<int32_t>());
         iota_kernel<<<(unsigned)cdiv(nnz, T), T, 0, s>>>(perm_in.as<int32_t>(), nnz);
         ctx->launches += 2;
         int end_bit = 1;
         while (((int64_t)1 << end_bit) < m) ++end_bit;
         size_t tmp_bytes = 0;
-        CKT(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c.cols.as<int32_t>(),
+        CKT(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in.as<int32_t>(),
                                             keys_out.as<int32_t>(), perm_in.as<int32_t>(),
                                             perm_out.as<int32_t>(), (int)nnz, 0, end_bit, s));
         CKT(tmp.ensure(tmp_bytes));
-        CKT(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, c.cols.as<int32_t>(),
+        CKT(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_in.as<int32_t>(),
                                             keys_out.as<int32_t>(), perm_in.as<int32_t>(),
                                             perm_out.as<int32_t>(), (int)nnz, 0, end_bit, s));
-        permute_kernel<<<(unsigned)cdiv(nnz, T), T, 0, s>>>(
-            perm_out.as<int32_t>(), nnz, rows_exp.as<int32_t>(), c.vals.as<float>(),
-            ctx->t_rows.as<int32_t>(), ctx->t_vals.as<float>());
-        CKT(cudaMemsetAsync(counts.p, 0, (size_t)(m + 1) * 4, s));
-        histogram_kernel<<<(unsigned)cdiv(nnz, T), T, 0, s>>>(c.cols.as<int32_t>(), nnz,
-                                                             counts.as<int32_t>() + 1);
+        permute_kernel<<<(unsigned)cdiv(nnz, T), T, 0, s>>>(perm_out.as<int32_t>(), nnz,
+                                                           rows_exp.as<int32_t>(),
+                                                           c.ent.as<int2>(), ctx->t_ent.as<int2>());
+        lower_bound_kernel<<<(unsigned)cdiv(m + 1, T), T, 0, s>>>(keys_out.as<int32_t>(), nnz, m,
+                                                                 tindptr.as<int32_t>());
         ctx->launches += 2;
         CKT(cudaGetLastError());
-        CKT(cudaMemcpyAsync(ctx->h_tindptr.data(), counts.p, (size_t)(m + 1) * 4,
+        CKT(cudaMemcpyAsync(ctx->h_tindptr.data(), tindptr.p, (size_t)(m + 1) * 4,
                             cudaMemcpyDeviceToHost, s));
         CKT(cudaStreamSynchronize(s));
-        for (int64_t w = 0; w < m; ++w) ctx->h_tindptr[(size_t)w + 1] += ctx->h_tindptr[(size_t)w];
     }
     cleanup();
 #undef CKT
-    rc = build_items(ctx, ctx->h_tindptr, m, ctx->term_items);
+    int rc = build_items(ctx, ctx->h_tindptr, m, ctx->term_items);
     if (rc) return rc;
     ctx->t_ready = true;
     ctx->t_weighted_ready = false;
@@ -367,11 +368,11 @@ static int ensure_weighted_vals(plsa_ctx *ctx)
 {
     if (ctx->t_weighted_ready) return PLSA_OK;
     const int64_t nnz = ctx->cur().nnz;
-    CK(ctx->t_valsw.ensure((size_t)std::max<int64_t>(nnz, 1) * 4));
+    CK(ctx->t_entw.ensure(ent_bytes(nnz)));
+    CK(cudaMemsetAsync(ctx->t_entw.as<int2>() + nnz, 0, ENT_SLACK * sizeof(int2), ctx->stream));
     if (nnz > 0) {
         weight_vals_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, ctx->stream>>>(
-            ctx->t_vals.as<float>(), ctx->t_rows.as<int32_t>(), ctx->sw.as<float>(),
-            ctx->t_valsw.as<float>(), nnz);
+            ctx->t_ent.as<int2>(), ctx->sw.as<float>(), ctx->t_entw.as<int2>(), nnz);
         ctx->launches++;
         CK(cudaGetLastError());
     }
@@ -445,9 +446,9 @@ API int plsa_ctx_destroy(plsa_ctx *ctx)
     prof_collect(ctx);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     for (Corpus *c : {&ctx->base, &ctx->boot}) {
-        c->indptr.release(); c->cols.release(); c->vals.release();
+        c->indptr.release(); c->ent.release();
     }
-    for (DevBuf *b : {&ctx->t_rows, &ctx->t_vals, &ctx->t_valsw, &ctx->t_scratch,
+    for (DevBuf *b : {&ctx->t_ent, &ctx->t_entw, &ctx->up_cols, &ctx->up_vals,
                       &ctx->doc_items.items, &ctx->doc_items.split_rows, &ctx->doc_items.slot_begin,
                       &ctx->term_items.items, &ctx->term_items.split_rows,
                       &ctx->term_items.slot_begin, &ctx->A[0], &ctx->A[1], &ctx->B[0], &ctx->B[1],
@@ -481,14 +482,22 @@ static int upload_csr_impl(plsa_ctx *ctx, const int32_t *indptr, const int32_t *
     c.n = n; c.m = m; c.nnz = nnz;
     c.h_indptr.assign(indptr, indptr + n + 1);
     CK(c.indptr.ensure((size_t)(n + 1) * 4));
-    CK(c.cols.ensure((size_t)std::max<int64_t>(nnz, 1) * 4));
-    CK(c.vals.ensure((size_t)std::max<int64_t>(nnz, 1) * 4));
+    CK(c.ent.ensure(ent_bytes(nnz)));
+    CK(cudaMemsetAsync(c.ent.as<int2>() + nnz, 0, ENT_SLACK * sizeof(int2), ctx->stream));
     CK(cudaMemcpyAsync(c.indptr.p, indptr, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
     if (nnz > 0) {
-        CK(cudaMemcpyAsync(c.cols.p, indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(c.vals.p, data, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(ctx->up_cols.ensure((size_t)nnz * 4));
+        CK(ctx->up_vals.ensure((size_t)nnz * 4));
+        CK(cudaMemcpyAsync(ctx->up_cols.p, indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->up_vals.p, data, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+        interleave_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, ctx->stream>>>(
+            ctx->up_cols.as<int32_t>(), ctx->up_vals.as<float>(), nnz, c.ent.as<int2>());
+        ctx->launches++;
+        CK(cudaGetLastError());
     }
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->up_cols.release(); /* staging only */
+    ctx->up_vals.release();
     ctx->use_boot = false;
     corpus_changed(ctx);
     return PLSA_OK;
@@ -544,8 +553,8 @@ API int plsa_bootstrap(plsa_ctx *ctx, const int32_t *row_idx, int64_t n_rows)
     }
     c.n = n_rows; c.m = b.m; c.nnz = run;
     CK(c.indptr.ensure((size_t)(n_rows + 1) * 4));
-    CK(c.cols.ensure((size_t)std::max<int64_t>(run, 1) * 4));
-    CK(c.vals.ensure((size_t)std::max<int64_t>(run, 1) * 4));
+    CK(c.ent.ensure(ent_bytes(run)));
+    CK(cudaMemsetAsync(c.ent.as<int2>() + run, 0, ENT_SLACK * sizeof(int2), ctx->stream));
     CK(ctx->stage.ensure((size_t)std::max<int64_t>(n_rows, 1) * 4));
     CK(cudaMemcpyAsync(c.indptr.p, c.h_indptr.data(), (size_t)(n_rows + 1) * 4,
                        cudaMemcpyHostToDevice, ctx->stream));
@@ -553,8 +562,8 @@ API int plsa_bootstrap(plsa_ctx *ctx, const int32_t *row_idx, int64_t n_rows)
         CK(cudaMemcpyAsync(ctx->stage.p, row_idx, (size_t)n_rows * 4, cudaMemcpyHostToDevice,
                            ctx->stream));
         gather_rows_kernel<<<(unsigned)cdiv(n_rows * 32, 256), 256, 0, ctx->stream>>>(
-            ctx->stage.as<int32_t>(), n_rows, b.indptr.as<int32_t>(), b.cols.as<int32_t>(),
-            b.vals.as<float>(), c.indptr.as<int32_t>(), c.cols.as<int32_t>(), c.vals.as<float>());
+            ctx->stage.as<int32_t>(), n_rows, b.indptr.as<int32_t>(), b.ent.as<int2>(),
+            c.indptr.as<int32_t>(), c.ent.as<int2>());
         ctx->launches++;
         CK(cudaGetLastError());
     }
@@ -722,8 +731,7 @@ static int run_loglik(plsa_ctx *ctx, double *out)
         PassArgs a{};
         a.items = ctx->doc_items.items.as<Item>();
         a.n_items = ctx->doc_items.n_items;
-        a.idx = c.cols.as<int32_t>();
-        a.val = c.vals.as<float>();
+        a.ent = c.ent.as<int2>();
         a.own_old = ctx->A[ctx->curA].as<float>();
         a.gat_old = ctx->B[ctx->curB].as<float>();
         a.own_scale = ctx->scale.as<float>();
@@ -733,7 +741,7 @@ static int run_loglik(plsa_ctx *ctx, double *out)
         a.stride_gat = ctx->strideB;
         a.kp = ctx->kp;
         if ((rc = launch_pass(ctx, MODE_LOGLIK, a))) return rc;
-        sum_doubles_kernel<<<1, 256, 0, ctx->stream>>>(ctx->ll_part.as<double>(), grid,
+        sum_doubles_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->ll_part.as<double>(), grid,
                                                        ctx->ll_out.as<double>());
         ctx->launches++;
         CK(cudaGetLastError());
@@ -790,6 +798,9 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
         if (use_sample_weights && (rc = ensure_weighted_vals(ctx))) return rc;
     }
     const int kp = ctx->kp;
+    /* products at or below the threshold are dropped (plsa.py:98-102); subnormal products
+     * are dropped as well so that a surviving posterior normaliser is never subnormal */
+    e_step_thresh = std::max(e_step_thresh, 1.17549435e-38f);
     CK(ctx->partialA.ensure((size_t)std::max(ctx->doc_items.n_slots, 1) * kp * 4));
     if (!refit) CK(ctx->partialB.ensure((size_t)std::max(ctx->term_items.n_slots, 1) * kp * 4));
 
@@ -812,8 +823,7 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
             PassArgs a{};
             a.items = ctx->doc_items.items.as<Item>();
             a.n_items = ctx->doc_items.n_items;
-            a.idx = c.cols.as<int32_t>();
-            a.val = c.vals.as<float>();
+            a.ent = c.ent.as<int2>();
             a.own_old = ctx->A[ctx->curA].as<float>();
             a.gat_old = ctx->B[ctx->curB].as<float>();
             a.own_scale = ctx->scale.as<float>();
@@ -834,8 +844,7 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                 PassArgs a{};
                 a.items = ctx->term_items.items.as<Item>();
                 a.n_items = ctx->term_items.n_items;
-                a.idx = ctx->t_rows.as<int32_t>();
-                a.val = use_sample_weights ? ctx->t_valsw.as<float>() : ctx->t_vals.as<float>();
+                a.ent = use_sample_weights ? ctx->t_entw.as<int2>() : ctx->t_ent.as<int2>();
                 a.own_old = ctx->B[ctx->curB].as<float>();
                 a.gat_old = ctx->A[ctx->curA].as<float>();
                 a.own_scale = ctx->scale.as<float>();
@@ -854,7 +863,7 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                 ProfScope ps(ctx, PLSA_PROF_NORMALIZE);
                 colsum_partial_kernel<<<COLSUM_CTAS, 256, 0, ctx->stream>>>(
                     ctx->B[nB].as<float>(), c.m, ctx->strideB, kp, ctx->colpart.as<double>());
-                colsum_final_kernel<<<1, 256, 0, ctx->stream>>>(ctx->colpart.as<double>(),
+                colsum_final_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->colpart.as<double>(),
                                                                 COLSUM_CTAS, kp,
                                                                 ctx->scale.as<float>(),
                                                                 ctx->colnorm.as<double>());

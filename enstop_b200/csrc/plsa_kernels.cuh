@@ -40,8 +40,8 @@ enum { MODE_DOC = 0, MODE_TERM = 1, MODE_LOGLIK = 2 };
 struct PassArgs {
     const Item *items;
     int64_t n_items;
-    const int32_t *idx;      /* gather-row index of every stored entry                  */
-    const float *val;        /* value of every stored entry                             */
+    const int2 *ent;         /* stored entries {gather-row index, float bits of the value};
+                                the array carries ENT_SLACK readable entries past its end   */
     const float *own_old;    /* [rows, stride_own]                                      */
     const float *gat_old;    /* [cols, stride_gat]                                      */
     const float *own_scale;  /* [kp] folded into the owned row (1/column-sum of P(w|z)) */
@@ -53,23 +53,27 @@ struct PassArgs {
     float thresh;
 };
 
+constexpr int ENT_SLACK = 128;
+
 __device__ __forceinline__ float4 ldg_f4(const float *p)
 {
     return __ldg(reinterpret_cast<const float4 *>(p));
 }
-
-/* streaming loads of the CSR arrays: read once, keep them out of L1 so the gathered
- * factor rows stay cached */
-__device__ __forceinline__ int32_t ld_stream_i32(const int32_t *p)
+__device__ __forceinline__ float4 ldg_f4_bytes(const char *p)
 {
-    int32_t r;
-    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
-    return r;
+    return __ldg(reinterpret_cast<const float4 *>(p));
 }
-__device__ __forceinline__ float ld_stream_f32(const float *p)
+/* keep a per-lane 64-bit base in ordinary registers so that base + idx * stride is one
+ * IMAD.WIDE (ptxas otherwise splits it into a uniform base plus two carry adds per load) */
+__device__ __forceinline__ const char *opaque_ptr(const char *p)
+{
+    asm volatile("" : "+l"(p));
+    return p;
+}
+__device__ __forceinline__ float rcp_fast(float x)
 {
     float r;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 
@@ -103,22 +107,103 @@ __device__ __forceinline__ float group_sum(float v, int gbase, int j)
     }
 }
 
-template <int G, int KV, int MODE>
-__global__ void __launch_bounds__(256) row_pass_kernel(const PassArgs a)
+template <int G, int KV> struct PassShape {
+    static constexpr int NG = 32 / G;                       /* entries per warp step      */
+    static constexpr int U = (KV >= 4) ? 1 : (KV == 2) ? 2 : (NG >= 8) ? 2 : (NG >= 4) ? 3 : 4;
+    static constexpr int CH = NG * U;                       /* entries per loop iteration */
+};
+
+/* One loop iteration: U steps of NG entries.  TAIL: entries at or past `len` are read (the
+ * next row's, or the slack) but their value is forced to 0 so they add nothing. */
+template <int G, int KV>
+__device__ __forceinline__ void load_entries(const int2 *__restrict__ ent, int base, int grp,
+                                             int2 (&e)[PassShape<G, KV>::U])
 {
-    constexpr int NG = 32 / G;                               /* entries per warp step  */
-    constexpr int UMAX = (KV >= 8) ? 1 : (8 / KV);
-    constexpr int U = (32 / NG) < UMAX ? (32 / NG) : UMAX;   /* steps per index chunk  */
-    constexpr int CH = NG * U;                               /* entries per chunk      */
+#pragma unroll
+    for (int u = 0; u < PassShape<G, KV>::U; ++u)
+        e[u] = __ldg(ent + base + u * PassShape<G, KV>::NG + grp);
+}
+
+template <int G, int KV, int MODE, bool TAIL>
+__device__ __forceinline__ void pass_iteration(const PassArgs &a,
+                                               const int2 (&e)[PassShape<G, KV>::U],
+                                               int base, int len, const char *gat_base,
+                                               const uint32_t (&lane_off)[KV],
+                                               uint32_t stride_bytes, const float4 (&own)[KV],
+                                               float4 (&acc)[KV], double &ll_acc, float rw,
+                                               float thresh, int grp, int j, int gbase)
+{
+    constexpr int NG = PassShape<G, KV>::NG;
+    constexpr int U = PassShape<G, KV>::U;
+    float4 g[U][KV];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if constexpr (KV == 1) { /* lane offset is folded into gat_base */
+            g[u][0] = ldg_f4_bytes(gat_base + (uint64_t)(uint32_t)e[u].x * stride_bytes);
+        } else {
+            const char *row = gat_base + (uint64_t)(uint32_t)e[u].x * stride_bytes;
+#pragma unroll
+            for (int q = 0; q < KV; ++q) g[u][q] = ldg_f4_bytes(row + lane_off[q]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        float x = __int_as_float(e[u].y);
+        if constexpr (TAIL) x = (base + u * NG + grp < len) ? x : 0.f;
+        float part;
+#pragma unroll
+        for (int q = 0; q < KV; ++q) {
+            float4 v;
+            v.x = g[u][q].x * own[q].x;
+            v.y = g[u][q].y * own[q].y;
+            v.z = g[u][q].z * own[q].z;
+            v.w = g[u][q].w * own[q].w;
+            if constexpr (MODE != MODE_LOGLIK) { /* plsa.py:98-102 */
+                v.x = v.x > thresh ? v.x : 0.f;
+                v.y = v.y > thresh ? v.y : 0.f;
+                v.z = v.z > thresh ? v.z : 0.f;
+                v.w = v.w > thresh ? v.w : 0.f;
+            }
+            g[u][q] = v;
+            const float s4 = (v.x + v.y) + (v.z + v.w);
+            part = (q == 0) ? s4 : part + s4;
+        }
+        const float norm = group_sum<G>(part, gbase, j);
+        if constexpr (MODE == MODE_LOGLIK) {
+            /* plsa.py:383-384; one lane per entry contributes, x == 0 marks a non-entry */
+            if (j == 0 && grp < NG && x != 0.f) ll_acc += (double)(x * logf(norm) * rw);
+        } else {
+            /* plsa.py:104: posterior = v / norm if norm > 0.  Products that survive the
+             * threshold are normal floats (the host passes thresh >= FLT_MIN), so norm is
+             * 0 or normal; norm == 0 gives x * inf (or NaN), clamped to a finite c that
+             * multiplies v == 0. */
+            const float c = fminf(x * rcp_fast(norm), 3.0e38f);
+#pragma unroll
+            for (int q = 0; q < KV; ++q) {
+                acc[q].x = fmaf(c, g[u][q].x, acc[q].x);
+                acc[q].y = fmaf(c, g[u][q].y, acc[q].y);
+                acc[q].z = fmaf(c, g[u][q].z, acc[q].z);
+                acc[q].w = fmaf(c, g[u][q].w, acc[q].w);
+            }
+        }
+    }
+}
+
+template <int G, int KV, int MODE>
+__global__ void __launch_bounds__(256, (KV == 1) ? 4 : (KV == 2) ? 3 : 1)
+    row_pass_kernel(const PassArgs a)
+{
+    constexpr int NG = PassShape<G, KV>::NG;
+    constexpr int CH = PassShape<G, KV>::CH;
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int64_t item_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
 
-    const int grp = lane / G;
+    const int grp = lane / G;      /* == NG for the 32 % G idle lanes: they read valid memory,
+                                      own zeros, and are never folded in                    */
     const int j = lane - grp * G;
     const int gbase = grp * G;
-    const bool lane_on = grp < NG; /* 32 % G lanes idle when G does not divide 32 */
 
     double ll_acc = 0.0;
     if (item_id < a.n_items) {
@@ -129,8 +214,8 @@ __global__ void __launch_bounds__(256) row_pass_kernel(const PassArgs a)
 #pragma unroll
         for (int q = 0; q < KV; ++q) {
             const int c = 4 * (j + G * q);
-            if (lane_on && c < a.kp) {
-                float4 o = ldg_f4(a.own_old + (int64_t)it.row * a.stride_own + c);
+            if (grp < NG && c < a.kp) {
+                const float4 o = ldg_f4(a.own_old + (int64_t)it.row * a.stride_own + c);
                 const float4 s = ldg_f4(a.own_scale + c);
                 own[q] = make_float4(o.x * s.x, o.y * s.y, o.z * s.z, o.w * s.w);
             } else {
@@ -143,77 +228,38 @@ __global__ void __launch_bounds__(256) row_pass_kernel(const PassArgs a)
         float rw = 1.f;
         if constexpr (MODE == MODE_LOGLIK) rw = a.row_weight[it.row];
 
-        const int32_t *idx = a.idx + it.start;
-        const float *val = a.val + it.start;
+        const int2 *ent = a.ent + it.start;
         const int len = it.len;
-
-        int32_t my_idx = 0;
-        float my_val = 0.f;
-        if (lane < CH && lane < len) {
-            my_idx = ld_stream_i32(idx + lane);
-            my_val = ld_stream_f32(val + lane);
+        const float thresh = a.thresh;
+        const uint32_t stride_bytes = (uint32_t)a.stride_gat * 4u;
+        /* lanes whose 4 topics lie in the padding (c >= kp) re-read the row's first vector:
+         * always in bounds, and their `own` is zero */
+        uint32_t lane_off[KV];
+#pragma unroll
+        for (int q = 0; q < KV; ++q) {
+            const int c = 4 * (j + G * q);
+            lane_off[q] = (c < a.kp) ? (uint32_t)c * 4u : 0u;
         }
-        for (int base = 0; base < len; base += CH) {
-            const int cnt = min(CH, len - base);
-            const int32_t cur_idx = my_idx;
-            const float cur_val = my_val;
-            const int nb = base + CH + lane; /* prefetch the next chunk of the row */
-            if (lane < CH && nb < len) {
-                my_idx = ld_stream_i32(idx + nb);
-                my_val = ld_stream_f32(val + nb);
-            }
+        const char *gat_base = opaque_ptr(reinterpret_cast<const char *>(a.gat_old) +
+                                          (KV == 1 ? lane_off[0] : 0u));
 
-            float4 g[U][KV];
-            float x[U];
+        /* entries are fetched one iteration ahead (reads past the row end land in the next
+         * row or in the array's slack and are ignored) */
+        constexpr int U = PassShape<G, KV>::U;
+        int2 e[U];
+        load_entries<G, KV>(ent, 0, grp, e);
+        int base = 0;
+        for (; base + CH <= len; base += CH) {
+            int2 en[U];
+            load_entries<G, KV>(ent, base + CH, grp, en);
+            pass_iteration<G, KV, MODE, false>(a, e, base, len, gat_base, lane_off, stride_bytes,
+                                               own, acc, ll_acc, rw, thresh, grp, j, gbase);
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int src = u * NG + grp;
-                const int32_t w = __shfl_sync(0xffffffffu, cur_idx, src & 31);
-                x[u] = __shfl_sync(0xffffffffu, cur_val, src & 31);
-                const bool ok = lane_on && src < cnt;
-                const float *grow = a.gat_old + (int64_t)w * a.stride_gat;
-#pragma unroll
-                for (int q = 0; q < KV; ++q) {
-                    const int c = 4 * (j + G * q);
-                    g[u][q] = (ok && c < a.kp) ? ldg_f4(grow + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                float part = 0.f;
-#pragma unroll
-                for (int q = 0; q < KV; ++q) {
-                    float4 v;
-                    v.x = g[u][q].x * own[q].x;
-                    v.y = g[u][q].y * own[q].y;
-                    v.z = g[u][q].z * own[q].z;
-                    v.w = g[u][q].w * own[q].w;
-                    if constexpr (MODE != MODE_LOGLIK) { /* plsa.py:98-102 */
-                        v.x = v.x > a.thresh ? v.x : 0.f;
-                        v.y = v.y > a.thresh ? v.y : 0.f;
-                        v.z = v.z > a.thresh ? v.z : 0.f;
-                        v.w = v.w > a.thresh ? v.w : 0.f;
-                    }
-                    g[u][q] = v;
-                    part += (v.x + v.y) + (v.z + v.w);
-                }
-                const float norm = group_sum<G>(part, gbase, j);
-                if constexpr (MODE == MODE_LOGLIK) {
-                    /* plsa.py:383-384; one lane per entry contributes */
-                    if (lane_on && j == 0 && (u * NG + grp) < cnt)
-                        ll_acc += (double)(x[u] * __logf(norm) * rw);
-                } else {
-                    const float c = norm > 0.f ? __fdividef(x[u], norm) : 0.f; /* plsa.py:104 */
-#pragma unroll
-                    for (int q = 0; q < KV; ++q) {
-                        acc[q].x = fmaf(c, g[u][q].x, acc[q].x);
-                        acc[q].y = fmaf(c, g[u][q].y, acc[q].y);
-                        acc[q].z = fmaf(c, g[u][q].z, acc[q].z);
-                        acc[q].w = fmaf(c, g[u][q].w, acc[q].w);
-                    }
-                }
-            }
+            for (int u = 0; u < U; ++u) e[u] = en[u];
         }
+        if (base < len)
+            pass_iteration<G, KV, MODE, true>(a, e, base, len, gat_base, lane_off, stride_bytes,
+                                              own, acc, ll_acc, rw, thresh, grp, j, gbase);
 
         if constexpr (MODE != MODE_LOGLIK) {
             /* fold the NG groups: group 0 ends up with the row's sums */
@@ -350,26 +396,35 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float *__rest
     }
 }
 
-__global__ void colsum_final_kernel(const double *__restrict__ partial, int n_part, int kp,
-                                    float *__restrict__ scale, double *__restrict__ colnorm)
+/* one warp per topic: lanes stride over the per-CTA partials, fixed-order butterfly */
+__global__ void __launch_bounds__(1024) colsum_final_kernel(const double *__restrict__ partial,
+                                                            int n_part, int kp,
+                                                            float *__restrict__ scale,
+                                                            double *__restrict__ colnorm)
 {
-    for (int z = threadIdx.x; z < kp; z += blockDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int z = warp; z < kp; z += nw) {
         double t = 0.0;
-        for (int i = 0; i < n_part; ++i) t += partial[(int64_t)i * kp + z];
-        colnorm[z] = t;
-        scale[z] = t > 0.0 ? (float)(1.0 / t) : 1.f;
+        for (int i = lane; i < n_part; i += 32) t += partial[(int64_t)i * kp + z];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        if (lane == 0) {
+            colnorm[z] = t;
+            scale[z] = t > 0.0 ? (float)(1.0 / t) : 1.f;
+        }
     }
 }
 
-__global__ void sum_doubles_kernel(const double *__restrict__ in, int64_t n, double *out)
+__global__ void __launch_bounds__(1024) sum_doubles_kernel(const double *__restrict__ in, int64_t n,
+                                                           double *out)
 {
     /* single CTA, fixed order */
-    __shared__ double sm[256];
+    __shared__ double sm[1024];
     double s = 0.0;
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += in[i];
     sm[threadIdx.x] = s;
     __syncthreads();
-    for (int off = 128; off > 0; off >>= 1) {
+    for (int off = 512; off > 0; off >>= 1) {
         if ((int)threadIdx.x < off) sm[threadIdx.x] += sm[threadIdx.x + off];
         __syncthreads();
     }
@@ -409,31 +464,51 @@ __global__ void unpack_rows_kernel(const float *__restrict__ src, const float *_
 }
 
 /* ---- corpus preparation ------------------------------------------------------------------ */
-__global__ void expand_rows_kernel(const int32_t *__restrict__ indptr, int64_t n_rows,
-                                   int32_t *__restrict__ rows_out)
+/* separate index / value arrays (the caller's CSR) -> interleaved entries */
+__global__ void interleave_kernel(const int32_t *__restrict__ cols, const float *__restrict__ vals,
+                                  int64_t n, int2 *__restrict__ ent)
 {
-    /* one warp per row */
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ent[i] = make_int2(cols[i], __float_as_int(vals[i]));
+}
+
+/* per entry: its row (expanded indptr) and its column as a sort key; one warp per row */
+__global__ void expand_rows_kernel(const int32_t *__restrict__ indptr, int64_t n_rows,
+                                   const int2 *__restrict__ ent, int32_t *__restrict__ rows_out,
+                                   int32_t *__restrict__ keys_out)
+{
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= n_rows) return;
     const int lane = threadIdx.x & 31;
-    for (int32_t p = indptr[r] + lane; p < indptr[r + 1]; p += 32) rows_out[p] = (int32_t)r;
+    for (int32_t p = indptr[r] + lane; p < indptr[r + 1]; p += 32) {
+        rows_out[p] = (int32_t)r;
+        keys_out[p] = ent[p].x;
+    }
 }
 
-__global__ void histogram_kernel(const int32_t *__restrict__ keys, int64_t n, int32_t *counts)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) atomicAdd(counts + keys[i], 1);
-}
-
+/* term-major entries from the stable sort permutation: {document, value} */
 __global__ void permute_kernel(const int32_t *__restrict__ perm, int64_t n,
-                               const int32_t *__restrict__ rows_in, const float *__restrict__ vals_in,
-                               int32_t *__restrict__ rows_out, float *__restrict__ vals_out)
+                               const int32_t *__restrict__ rows_in, const int2 *__restrict__ ent_in,
+                               int2 *__restrict__ ent_out)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int32_t p = perm[i];
-    rows_out[i] = rows_in[p];
-    vals_out[i] = vals_in[p];
+    ent_out[i] = make_int2(rows_in[p], ent_in[p].y);
+}
+
+/* column pointers of the sorted keys: indptr[w] = first position with key >= w */
+__global__ void lower_bound_kernel(const int32_t *__restrict__ sorted_keys, int64_t n,
+                                   int64_t n_cols, int32_t *__restrict__ indptr)
+{
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w > n_cols) return;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (sorted_keys[mid] < (int32_t)w) lo = mid + 1; else hi = mid;
+    }
+    indptr[w] = (int32_t)lo;
 }
 
 __global__ void iota_kernel(int32_t *p, int64_t n)
@@ -442,20 +517,22 @@ __global__ void iota_kernel(int32_t *p, int64_t n)
     if (i < n) p[i] = (int32_t)i;
 }
 
-__global__ void weight_vals_kernel(const float *__restrict__ vals, const int32_t *__restrict__ rows,
-                                   const float *__restrict__ w, float *__restrict__ out, int64_t n)
+/* P(w|z) receives s * sample_weight[d] (plsa.py:293-297): pre-weighted term-major values */
+__global__ void weight_vals_kernel(const int2 *__restrict__ ent, const float *__restrict__ w,
+                                   int2 *__restrict__ out, int64_t n)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = vals[i] * w[rows[i]];
+    if (i < n) {
+        const int2 e = ent[i];
+        out[i] = make_int2(e.x, __float_as_int(__int_as_float(e.y) * w[e.x]));
+    }
 }
 
 /* bootstrap: new row i <- base row src[i]; one warp per new row */
 __global__ void gather_rows_kernel(const int32_t *__restrict__ src, int64_t n_new,
                                    const int32_t *__restrict__ base_indptr,
-                                   const int32_t *__restrict__ base_cols,
-                                   const float *__restrict__ base_vals,
-                                   const int32_t *__restrict__ new_indptr,
-                                   int32_t *__restrict__ cols, float *__restrict__ vals)
+                                   const int2 *__restrict__ base_ent,
+                                   const int32_t *__restrict__ new_indptr, int2 *__restrict__ ent)
 {
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= n_new) return;
@@ -463,10 +540,7 @@ __global__ void gather_rows_kernel(const int32_t *__restrict__ src, int64_t n_ne
     const int32_t b0 = base_indptr[src[r]];
     const int32_t len = base_indptr[src[r] + 1] - b0;
     const int32_t o0 = new_indptr[r];
-    for (int32_t p = lane; p < len; p += 32) {
-        cols[o0 + p] = base_cols[b0 + p];
-        vals[o0 + p] = base_vals[b0 + p];
-    }
+    for (int32_t p = lane; p < len; p += 32) ent[o0 + p] = base_ent[b0 + p];
 }
 
 __global__ void fill_kernel(float *p, int64_t n, float v)
