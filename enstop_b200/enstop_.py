@@ -102,6 +102,23 @@ class _Shape:
         self.shape = shape
 
 
+def shard_members(n_runs, n_shards):
+    """Member r runs on shard r mod n_shards (a shard = one GPU / one rank)."""
+    return [[r for r in range(n_runs) if r % n_shards == i] for i in range(n_shards)]
+
+
+def stack_in_member_order(stacked, shards, k):
+    """Rows of a shard-major gather ([shard 0's members..., shard 1's members..., ...], k
+    rows each) re-ordered to member order — the np.vstack order of enstop_.py:231."""
+    order = [r for members in shards for r in members]
+    m = stacked.shape[1]
+    blocks = stacked.reshape(len(order), k, m)
+    out = np.empty_like(stacked)
+    for pos, r in enumerate(order):
+        out[r * k:(r + 1) * k] = blocks[pos]
+    return out
+
+
 def resolve_devices(devices=None, n_jobs=None):
     count = _lib.device_count()
     if count < 1:
@@ -129,8 +146,7 @@ def ensemble_of_topics(X, k, model="plsa", n_jobs=4, n_runs=16, parallelism="thr
     if parallelism == "none":
         devices = devices[:1]
     seeds = member_seeds(kwargs.get("random_state", None), n_runs)
-    assign = {d: [r for r in range(n_runs) if r % len(devices) == i]
-              for i, d in enumerate(devices)}
+    assign = dict(zip(devices, shard_members(n_runs, len(devices))))
     contexts, errors = {}, []
 
     def worker(dev):
@@ -162,13 +178,7 @@ def ensemble_of_topics(X, k, model="plsa", n_jobs=4, n_runs=16, parallelism="thr
     finally:
         for ctx in contexts.values():
             ctx.close()
-    # device-major -> member order (np.vstack order of enstop_.py:231)
-    order = [r for d in used for r in assign[d]]
-    m = X.shape[1]
-    out = np.empty((n_runs * k, m), dtype=np.float32)
-    blocks = stacked.reshape(len(order), k, m)
-    for pos, r in enumerate(order):
-        out[r * k:(r + 1) * k] = blocks[pos]
+    out = stack_in_member_order(stacked, [assign[d] for d in used], k)
     if return_seeds:
         return out, seeds
     return out
