@@ -18,7 +18,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
-SO_PATH = os.path.join(_HERE, "libplsa_b200.so")
+SO_PATH = os.environ.get("ENSTOP_B200_LIB") or os.path.join(_HERE, "libplsa_b200.so")
 SOURCES = [os.path.join(_HERE, "csrc", "plsa_b200.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", "plsa_kernels.cuh"),
            os.path.join(ROOT, "include", "plsa_b200.h")]
@@ -171,6 +171,10 @@ class Context:
         check(self._L.plsa_ctx_create(int(device), ctypes.byref(self._h)))
         self.device = int(device)
         self.k = 0
+        if os.environ.get("ENSTOP_B200_CHUNK"):     # work-item length experiments
+            self.set_option("chunk", int(os.environ["ENSTOP_B200_CHUNK"]))
+        if os.environ.get("ENSTOP_B200_VARIANT"):   # kernel-variant experiments
+            self.set_option("variant", int(os.environ["ENSTOP_B200_VARIANT"]))
 
     def close(self):
         if self._h:

@@ -63,7 +63,10 @@ struct Corpus {
     std::vector<int32_t> h_indptr;
 };
 
-static inline size_t ent_bytes(int64_t nnz) { return (size_t)(nnz + ENT_SLACK) * sizeof(int2); }
+/* readable, zeroed entries past the end: kernels read ahead of a row's end, the group-per-row
+ * kernel by up to one work-item length */
+constexpr int64_t ENT_PAD = ENT_SLACK + 4096;
+static inline size_t ent_bytes(int64_t nnz) { return (size_t)(nnz + ENT_PAD) * sizeof(int2); }
 
 struct ItemSet {
     DevBuf items, split_rows, slot_begin;
@@ -91,12 +94,15 @@ struct plsa_ctx {
     bool t_ready = false, t_weighted_ready = false;
 
     ItemSet doc_items, term_items;
-    int64_t chunk = 2048;
+    int64_t chunk = 256;
+    int variant = 0; /* VAR_* bits of the row-pass kernel */
+    cudaTextureObject_t texA[2] = {0, 0}, texB[2] = {0, 0};
+    size_t tex_max_texels = 0;
 
     /* model */
     int32_t k = 0, kp = 0, strideA = 0, strideB = 0;
     DevBuf A[2], B[2], scale, ones, colnorm, colpart, partialA, partialB;
-    DevBuf sw, ll_part, ll_out, stage, topics_dev;
+    DevBuf sw, ll_part, ll_out, stage, topics_dev, tickets;
     int32_t stash_slots = 0;
     size_t stash_per = 0;
     int curA = 0, curB = 0;
@@ -193,42 +199,74 @@ static void prof_collect(plsa_ctx *ctx)
 /* ---- kernel dispatch ------------------------------------------------------------------------ */
 typedef void (*pass_fn)(const PassArgs);
 
-template <int G, int KV> static pass_fn pick_mode(int mode)
+template <int G, int KV, int VAR> static pass_fn pick_mode(int mode)
 {
-    switch (mode) {
-    case MODE_DOC: return row_pass_kernel<G, KV, MODE_DOC>;
-    case MODE_TERM: return row_pass_kernel<G, KV, MODE_TERM>;
-    default: return row_pass_kernel<G, KV, MODE_LOGLIK>;
+    if constexpr (VAR & VAR_GROW) {
+        switch (mode) {
+        case MODE_DOC: return row_group_kernel<G, KV, MODE_DOC, VAR>;
+        case MODE_TERM: return row_group_kernel<G, KV, MODE_TERM, VAR>;
+        default: return row_group_kernel<G, KV, MODE_LOGLIK, VAR>;
+        }
+    } else {
+        switch (mode) {
+        case MODE_DOC: return row_pass_kernel<G, KV, MODE_DOC, VAR>;
+        case MODE_TERM: return row_pass_kernel<G, KV, MODE_TERM, VAR>;
+        default: return row_pass_kernel<G, KV, MODE_LOGLIK, VAR>;
+        }
     }
 }
 
-static pass_fn pick_kernel(int kp, int mode)
+template <int G, int KV> static pass_fn pick_var(int mode, int var)
+{
+    switch (var & 3) {
+    case 1: return pick_mode<G, KV, 1>(mode);
+    case 2: return pick_mode<G, KV, 2>(mode);
+    case 3: return pick_mode<G, KV, 3>(mode);
+    default: return pick_mode<G, KV, 0>(mode);
+    }
+}
+
+static int pass_group_lanes(int kp)
+{
+    const int nv = kp / 4;
+    return nv <= 8 ? nv : nv <= 16 ? 16 : 32;
+}
+
+static pass_fn pick_kernel(int kp, int mode, int var)
 {
     const int nv = kp / 4; /* float4 vectors per factor row */
     switch (nv) {
-    case 1: return pick_mode<1, 1>(mode);
-    case 2: return pick_mode<2, 1>(mode);
-    case 3: return pick_mode<3, 1>(mode);
-    case 4: return pick_mode<4, 1>(mode);
-    case 5: return pick_mode<5, 1>(mode);
-    case 6: return pick_mode<6, 1>(mode);
-    case 7: return pick_mode<7, 1>(mode);
-    case 8: return pick_mode<8, 1>(mode);
+    case 1: return pick_var<1, 1>(mode, var);
+    case 2: return pick_var<2, 1>(mode, var);
+    case 3: return pick_var<3, 1>(mode, var);
+    case 4: return pick_var<4, 1>(mode, var);
+    case 5: return pick_var<5, 1>(mode, var);
+    case 6: return pick_var<6, 1>(mode, var);
+    case 7: return pick_var<7, 1>(mode, var);
+    case 8: return pick_var<8, 1>(mode, var);
     default: break;
     }
-    if (nv <= 16) return pick_mode<16, 1>(mode);
-    if (nv <= 32) return pick_mode<32, 1>(mode);
-    if (nv <= 64) return pick_mode<32, 2>(mode);
-    if (nv <= 128) return pick_mode<32, 4>(mode);
-    return pick_mode<32, 8>(mode);
+    if (nv <= 16) return pick_var<16, 1>(mode, var);
+    if (nv <= 32) return pick_var<32, 1>(mode, var);
+    if (nv <= 64) return pick_var<32, 2>(mode, var);
+    if (nv <= 128) return pick_var<32, 4>(mode, var);
+    return pick_var<32, 8>(mode, var);
+}
+
+static int64_t pass_grid(const plsa_ctx *ctx, int64_t n_items, int kp)
+{
+    const int rows_per_warp = (ctx->variant & VAR_GROW) ? 32 / pass_group_lanes(kp) : 1;
+    return cdiv(n_items, (int64_t)8 * rows_per_warp);
 }
 
 static int launch_pass(plsa_ctx *ctx, int mode, const PassArgs &a)
 {
     if (a.n_items == 0) return PLSA_OK;
-    pass_fn fn = pick_kernel(a.kp, mode);
+    int var = ctx->variant;
+    if (!a.gat_tex) var &= ~VAR_TEX;
+    pass_fn fn = pick_kernel(a.kp, mode, var);
     const int warps = 8;
-    const int64_t grid = cdiv(a.n_items, warps);
+    const int64_t grid = pass_grid(ctx, a.n_items, a.kp);
     fn<<<(unsigned)grid, warps * 32, 0, ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -319,7 +357,7 @@ static int build_term_major(plsa_ctx *ctx)
     } while (0)
     const size_t nz = (size_t)std::max<int64_t>(nnz, 1);
     CKT(ctx->t_ent.ensure(ent_bytes(nnz)));
-    CKT(cudaMemsetAsync(ctx->t_ent.as<int2>() + nnz, 0, ENT_SLACK * sizeof(int2), s));
+    CKT(cudaMemsetAsync(ctx->t_ent.as<int2>() + nnz, 0, ENT_PAD * sizeof(int2), s));
     ctx->h_tindptr.assign((size_t)m + 1, 0);
     if (nnz > 0) {
         CKT(rows_exp.ensure(nz * 4));
@@ -369,7 +407,7 @@ static int ensure_weighted_vals(plsa_ctx *ctx)
     if (ctx->t_weighted_ready) return PLSA_OK;
     const int64_t nnz = ctx->cur().nnz;
     CK(ctx->t_entw.ensure(ent_bytes(nnz)));
-    CK(cudaMemsetAsync(ctx->t_entw.as<int2>() + nnz, 0, ENT_SLACK * sizeof(int2), ctx->stream));
+    CK(cudaMemsetAsync(ctx->t_entw.as<int2>() + nnz, 0, ENT_PAD * sizeof(int2), ctx->stream));
     if (nnz > 0) {
         weight_vals_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, ctx->stream>>>(
             ctx->t_ent.as<int2>(), ctx->sw.as<float>(), ctx->t_entw.as<int2>(), nnz);
@@ -434,6 +472,11 @@ API int plsa_ctx_create(int device, plsa_ctx **out)
         delete ctx;
         return PLSA_ECUDA;
     }
+    int max_lin = 0;
+    if (cudaDeviceGetAttribute(&max_lin, cudaDevAttrMaxTexture1DLinearWidth, device) == cudaSuccess &&
+        max_lin > 0)
+        ctx->tex_max_texels = (size_t)max_lin;
+    ctx->variant = VAR_TEX | VAR_GROW;
     *out = ctx;
     return PLSA_OK;
 }
@@ -453,9 +496,13 @@ API int plsa_ctx_destroy(plsa_ctx *ctx)
                       &ctx->term_items.items, &ctx->term_items.split_rows,
                       &ctx->term_items.slot_begin, &ctx->A[0], &ctx->A[1], &ctx->B[0], &ctx->B[1],
                       &ctx->scale, &ctx->ones, &ctx->colnorm, &ctx->colpart, &ctx->partialA,
-                      &ctx->partialB, &ctx->sw, &ctx->ll_part, &ctx->ll_out, &ctx->stage,
+                      &ctx->partialB, &ctx->sw, &ctx->ll_part, &ctx->ll_out, &ctx->stage, &ctx->tickets,
                       &ctx->topics_dev})
         b->release();
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->texA[i]) cudaDestroyTextureObject(ctx->texA[i]);
+        if (ctx->texB[i]) cudaDestroyTextureObject(ctx->texB[i]);
+    }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -483,7 +530,7 @@ static int upload_csr_impl(plsa_ctx *ctx, const int32_t *indptr, const int32_t *
     c.h_indptr.assign(indptr, indptr + n + 1);
     CK(c.indptr.ensure((size_t)(n + 1) * 4));
     CK(c.ent.ensure(ent_bytes(nnz)));
-    CK(cudaMemsetAsync(c.ent.as<int2>() + nnz, 0, ENT_SLACK * sizeof(int2), ctx->stream));
+    CK(cudaMemsetAsync(c.ent.as<int2>() + nnz, 0, ENT_PAD * sizeof(int2), ctx->stream));
     CK(cudaMemcpyAsync(c.indptr.p, indptr, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
     if (nnz > 0) {
         CK(ctx->up_cols.ensure((size_t)nnz * 4));
@@ -554,7 +601,7 @@ API int plsa_bootstrap(plsa_ctx *ctx, const int32_t *row_idx, int64_t n_rows)
     c.n = n_rows; c.m = b.m; c.nnz = run;
     CK(c.indptr.ensure((size_t)(n_rows + 1) * 4));
     CK(c.ent.ensure(ent_bytes(run)));
-    CK(cudaMemsetAsync(c.ent.as<int2>() + run, 0, ENT_SLACK * sizeof(int2), ctx->stream));
+    CK(cudaMemsetAsync(c.ent.as<int2>() + run, 0, ENT_PAD * sizeof(int2), ctx->stream));
     CK(ctx->stage.ensure((size_t)std::max<int64_t>(n_rows, 1) * 4));
     CK(cudaMemcpyAsync(c.indptr.p, c.h_indptr.data(), (size_t)(n_rows + 1) * 4,
                        cudaMemcpyHostToDevice, ctx->stream));
@@ -584,6 +631,28 @@ API int plsa_corpus_shape(const plsa_ctx *ctx, int64_t *n_docs, int64_t *n_terms
 }
 
 /* ---- model state -------------------------------------------------------------------------------- */
+/* A factor buffer as a linear float4 texture: the row pass gathers through the texture pipe,
+ * which leaves the LSU/shared-memory pipe to the shuffles.  0 if the buffer is too large. */
+static int make_texture(plsa_ctx *ctx, cudaTextureObject_t *tex, void *ptr, size_t bytes)
+{
+    if (*tex) {
+        cudaDestroyTextureObject(*tex);
+        *tex = 0;
+    }
+    if (bytes / 16 > ctx->tex_max_texels) return PLSA_OK; /* kernels fall back to LDG */
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypeLinear;
+    rd.res.linear.devPtr = ptr;
+    rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+    rd.res.linear.sizeInBytes = bytes;
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof(td));
+    td.readMode = cudaReadModeElementType;
+    CK(cudaCreateTextureObject(tex, &rd, &td, nullptr));
+    return PLSA_OK;
+}
+
 static int32_t row_stride(int32_t kp)
 {
     if (kp * 4 <= 128) { /* rows never straddle a 128-byte line */
@@ -624,12 +693,17 @@ API int plsa_set_factors(plsa_ctx *ctx, const float *p_z_given_d, const float *p
         CK(ctx->B[i].ensure(bytesB));
         CK(cudaMemsetAsync(ctx->A[i].p, 0, bytesA, ctx->stream));
         CK(cudaMemsetAsync(ctx->B[i].p, 0, bytesB, ctx->stream));
+        int trc;
+        if ((trc = make_texture(ctx, &ctx->texA[i], ctx->A[i].p, bytesA))) return trc;
+        if ((trc = make_texture(ctx, &ctx->texB[i], ctx->B[i].p, bytesB))) return trc;
     }
     CK(ctx->scale.ensure((size_t)kp * 4));
     CK(ctx->ones.ensure((size_t)kp * 4));
     CK(ctx->colnorm.ensure((size_t)kp * 8));
     CK(ctx->colpart.ensure((size_t)COLSUM_CTAS * kp * 8));
     CK(ctx->ll_out.ensure(8));
+    CK(ctx->tickets.ensure(16));
+    CK(cudaMemsetAsync(ctx->tickets.p, 0, 16, ctx->stream));
     int rc;
     if ((rc = fill(ctx, ctx->scale.as<float>(), kp, 1.f))) return rc;
     if ((rc = fill(ctx, ctx->ones.as<float>(), kp, 1.f))) return rc;
@@ -720,7 +794,7 @@ static int run_loglik(plsa_ctx *ctx, double *out)
     int rc = ensure_doc_items(ctx);
     if (rc) return rc;
     if (!ctx->have_sw && (rc = plsa_set_sample_weight(ctx, nullptr))) return rc;
-    const int64_t grid = cdiv(ctx->doc_items.n_items, 8);
+    const int64_t grid = pass_grid(ctx, ctx->doc_items.n_items, ctx->kp);
     if (grid == 0) {
         *out = 0.0;
         return PLSA_OK;
@@ -737,14 +811,13 @@ static int run_loglik(plsa_ctx *ctx, double *out)
         a.own_scale = ctx->scale.as<float>();
         a.row_weight = ctx->sw.as<float>();
         a.ll_partial = ctx->ll_part.as<double>();
+        a.gat_tex = ctx->texB[ctx->curB];
+        a.ticket = ctx->tickets.as<unsigned int>() + 1;
+        a.ll_out = ctx->ll_out.as<double>();
         a.stride_own = ctx->strideA;
         a.stride_gat = ctx->strideB;
         a.kp = ctx->kp;
         if ((rc = launch_pass(ctx, MODE_LOGLIK, a))) return rc;
-        sum_doubles_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->ll_part.as<double>(), grid,
-                                                       ctx->ll_out.as<double>());
-        ctx->launches++;
-        CK(cudaGetLastError());
     }
     CK(cudaMemcpyAsync(out, ctx->ll_out.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -773,7 +846,7 @@ static int run_fixup(plsa_ctx *ctx, const ItemSet &is, const float *partial, flo
     f.kp = ctx->kp;
     f.stride_own = stride;
     f.normalise = normalise;
-    fixup_kernel<<<(unsigned)is.n_split, 256, 0, ctx->stream>>>(f);
+    fixup_kernel<<<(unsigned)cdiv(is.n_split, 8), 256, 0, ctx->stream>>>(f);
     ctx->launches++;
     CK(cudaGetLastError());
     return PLSA_OK;
@@ -829,6 +902,7 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
             a.own_scale = ctx->scale.as<float>();
             a.own_new = ctx->A[nA].as<float>();
             a.partial = ctx->partialA.as<float>();
+            a.gat_tex = ctx->texB[ctx->curB];
             a.stride_own = ctx->strideA;
             a.stride_gat = ctx->strideB;
             a.kp = kp;
@@ -850,6 +924,7 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                 a.own_scale = ctx->scale.as<float>();
                 a.own_new = ctx->B[nB].as<float>();
                 a.partial = ctx->partialB.as<float>();
+                a.gat_tex = ctx->texA[ctx->curA];
                 a.stride_own = ctx->strideB;
                 a.stride_gat = ctx->strideA;
                 a.kp = kp;
@@ -861,13 +936,11 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                 return rc;
             {   /* plsa.py:196-198: per-topic normaliser of P(w|z), applied lazily */
                 ProfScope ps(ctx, PLSA_PROF_NORMALIZE);
-                colsum_partial_kernel<<<COLSUM_CTAS, 256, 0, ctx->stream>>>(
-                    ctx->B[nB].as<float>(), c.m, ctx->strideB, kp, ctx->colpart.as<double>());
-                colsum_final_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->colpart.as<double>(),
-                                                                COLSUM_CTAS, kp,
-                                                                ctx->scale.as<float>(),
-                                                                ctx->colnorm.as<double>());
-                ctx->launches += 2;
+                colsum_kernel<<<COLSUM_CTAS, 256, 0, ctx->stream>>>(
+                    ctx->B[nB].as<float>(), c.m, ctx->strideB, kp, ctx->colpart.as<double>(),
+                    ctx->tickets.as<unsigned int>(), ctx->scale.as<float>(),
+                    ctx->colnorm.as<double>());
+                ctx->launches += 1;
                 CK(cudaGetLastError());
             }
             ctx->curB = nB;
@@ -941,11 +1014,16 @@ API int plsa_set_option(plsa_ctx *ctx, const char *name, int64_t value)
 {
     if (!ctx || !name) return PLSA_EINVAL;
     if (!strcmp(name, "chunk")) {
-        if (value < 32 || value > (1 << 20)) return ctx->fail(PLSA_EINVAL, "chunk out of range");
+        if (value < 32 || value > ENT_PAD - ENT_SLACK)
+            return ctx->fail(PLSA_EINVAL, "chunk out of range (32..4096)");
         ctx->chunk = value;
         ctx->doc_items.ready = false;
         ctx->term_items.ready = false;
         ctx->t_ready = false; /* term items are rebuilt with the term-major copy */
+        return PLSA_OK;
+    }
+    if (!strcmp(name, "variant")) {
+        ctx->variant = (int)value;
         return PLSA_OK;
     }
     return ctx->fail(PLSA_EINVAL, std::string("unknown option: ") + name);
