@@ -71,7 +71,7 @@ static inline size_t ent_bytes(int64_t nnz) { return (size_t)(nnz + ENT_PAD) * s
 struct ItemSet {
     DevBuf items, split_rows, slot_begin;
     int64_t n_items = 0;
-    int32_t n_split = 0, n_slots = 0;
+    int32_t n_split = 0, n_heavy = 0, n_slots = 0;
     bool ready = false;
 };
 
@@ -95,7 +95,7 @@ struct plsa_ctx {
 
     ItemSet doc_items, term_items;
     int64_t chunk = 256;
-    int variant = 0; /* VAR_* bits of the row-pass kernel */
+    bool use_texture = true; /* gather through the texture pipe when the factor fits */
     cudaTextureObject_t texA[2] = {0, 0}, texB[2] = {0, 0};
     size_t tex_max_texels = 0;
 
@@ -199,75 +199,53 @@ static void prof_collect(plsa_ctx *ctx)
 /* ---- kernel dispatch ------------------------------------------------------------------------ */
 typedef void (*pass_fn)(const PassArgs);
 
-template <int G, int KV, int VAR> static pass_fn pick_mode(int mode)
+template <int G, int KV> static pass_fn pick_mode(int mode, bool tex)
 {
-    if constexpr (VAR & VAR_GROW) {
-        switch (mode) {
-        case MODE_DOC: return row_group_kernel<G, KV, MODE_DOC, VAR>;
-        case MODE_TERM: return row_group_kernel<G, KV, MODE_TERM, VAR>;
-        default: return row_group_kernel<G, KV, MODE_LOGLIK, VAR>;
-        }
-    } else {
-        switch (mode) {
-        case MODE_DOC: return row_pass_kernel<G, KV, MODE_DOC, VAR>;
-        case MODE_TERM: return row_pass_kernel<G, KV, MODE_TERM, VAR>;
-        default: return row_pass_kernel<G, KV, MODE_LOGLIK, VAR>;
-        }
+    switch (mode) {
+    case MODE_DOC: return tex ? row_pass_kernel<G, KV, MODE_DOC, true> : row_pass_kernel<G, KV, MODE_DOC, false>;
+    case MODE_TERM: return tex ? row_pass_kernel<G, KV, MODE_TERM, true> : row_pass_kernel<G, KV, MODE_TERM, false>;
+    default: return tex ? row_pass_kernel<G, KV, MODE_LOGLIK, true> : row_pass_kernel<G, KV, MODE_LOGLIK, false>;
     }
 }
 
-template <int G, int KV> static pass_fn pick_var(int mode, int var)
-{
-    switch (var & 3) {
-    case 1: return pick_mode<G, KV, 1>(mode);
-    case 2: return pick_mode<G, KV, 2>(mode);
-    case 3: return pick_mode<G, KV, 3>(mode);
-    default: return pick_mode<G, KV, 0>(mode);
-    }
-}
-
+/* lanes per work item for a factor row of kp floats */
 static int pass_group_lanes(int kp)
 {
     const int nv = kp / 4;
     return nv <= 8 ? nv : nv <= 16 ? 16 : 32;
 }
 
-static pass_fn pick_kernel(int kp, int mode, int var)
+static pass_fn pick_kernel(int kp, int mode, bool tex)
 {
     const int nv = kp / 4; /* float4 vectors per factor row */
     switch (nv) {
-    case 1: return pick_var<1, 1>(mode, var);
-    case 2: return pick_var<2, 1>(mode, var);
-    case 3: return pick_var<3, 1>(mode, var);
-    case 4: return pick_var<4, 1>(mode, var);
-    case 5: return pick_var<5, 1>(mode, var);
-    case 6: return pick_var<6, 1>(mode, var);
-    case 7: return pick_var<7, 1>(mode, var);
-    case 8: return pick_var<8, 1>(mode, var);
+    case 1: return pick_mode<1, 1>(mode, tex);
+    case 2: return pick_mode<2, 1>(mode, tex);
+    case 3: return pick_mode<3, 1>(mode, tex);
+    case 4: return pick_mode<4, 1>(mode, tex);
+    case 5: return pick_mode<5, 1>(mode, tex);
+    case 6: return pick_mode<6, 1>(mode, tex);
+    case 7: return pick_mode<7, 1>(mode, tex);
+    case 8: return pick_mode<8, 1>(mode, tex);
     default: break;
     }
-    if (nv <= 16) return pick_var<16, 1>(mode, var);
-    if (nv <= 32) return pick_var<32, 1>(mode, var);
-    if (nv <= 64) return pick_var<32, 2>(mode, var);
-    if (nv <= 128) return pick_var<32, 4>(mode, var);
-    return pick_var<32, 8>(mode, var);
+    if (nv <= 16) return pick_mode<16, 1>(mode, tex);
+    if (nv <= 32) return pick_mode<32, 1>(mode, tex);
+    if (nv <= 64) return pick_mode<32, 2>(mode, tex);
+    if (nv <= 128) return pick_mode<32, 4>(mode, tex);
+    return pick_mode<32, 8>(mode, tex);
 }
 
-static int64_t pass_grid(const plsa_ctx *ctx, int64_t n_items, int kp)
+static int64_t pass_grid(int64_t n_items, int kp)
 {
-    const int rows_per_warp = (ctx->variant & VAR_GROW) ? 32 / pass_group_lanes(kp) : 1;
-    return cdiv(n_items, (int64_t)8 * rows_per_warp);
+    return cdiv(n_items, (int64_t)8 * (32 / pass_group_lanes(kp))); /* 8 warps per CTA */
 }
 
 static int launch_pass(plsa_ctx *ctx, int mode, const PassArgs &a)
 {
     if (a.n_items == 0) return PLSA_OK;
-    int var = ctx->variant;
-    if (!a.gat_tex) var &= ~VAR_TEX;
-    pass_fn fn = pick_kernel(a.kp, mode, var);
-    const int warps = 8;
-    const int64_t grid = pass_grid(ctx, a.n_items, a.kp);
-    fn<<<(unsigned)grid, warps * 32, 0, ctx->stream>>>(a);
+    pass_fn fn = pick_kernel(a.kp, mode, ctx->use_texture && a.gat_tex != 0);
+    fn<<<(unsigned)pass_grid(a.n_items, a.kp), 256, 0, ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
     return PLSA_OK;
@@ -284,9 +262,23 @@ static int build_items(plsa_ctx *ctx, const std::vector<int32_t> &indptr, int64_
     const int64_t chunk = ctx->chunk;
     std::vector<Item> items;
     items.reserve((size_t)rows + 1024);
+    /* split rows, those with more than 32 chunks first (fixup_kernel gives them a CTA) */
+    std::vector<int64_t> heavy, light;
+    for (int64_t r = 0; r < rows; ++r) {
+        const int64_t len = indptr[r + 1] - indptr[r];
+        if (len > chunk) (cdiv(len, chunk) > 32 ? heavy : light).push_back(r);
+    }
     std::vector<int32_t> split_rows, slot_begin;
     slot_begin.push_back(0);
+    std::vector<int32_t> first_slot((size_t)rows, -1);
     int32_t slots = 0;
+    for (const std::vector<int64_t> *lst : {&heavy, &light})
+        for (int64_t r : *lst) {
+            first_slot[(size_t)r] = slots;
+            slots += (int32_t)cdiv(indptr[r + 1] - indptr[r], chunk);
+            split_rows.push_back((int32_t)r);
+            slot_begin.push_back(slots);
+        }
     for (int64_t r = 0; r < rows; ++r) {
         const int64_t s = indptr[r], len = indptr[r + 1] - s;
         if (len <= chunk) {
@@ -295,11 +287,9 @@ static int build_items(plsa_ctx *ctx, const std::vector<int32_t> &indptr, int64_
             const int64_t nc = cdiv(len, chunk);
             for (int64_t c = 0; c < nc; ++c) {
                 const int64_t b = c * chunk;
-                items.push_back(
-                    Item{s + b, (int32_t)r, (int32_t)std::min(chunk, len - b), slots++, 0});
+                items.push_back(Item{s + b, (int32_t)r, (int32_t)std::min(chunk, len - b),
+                                     first_slot[(size_t)r] + (int32_t)c, 0});
             }
-            split_rows.push_back((int32_t)r);
-            slot_begin.push_back(slots);
         }
     }
     /* counting sort by length, descending, stable */
@@ -316,6 +306,7 @@ static int build_items(plsa_ctx *ctx, const std::vector<int32_t> &indptr, int64_
 
     out.n_items = (int64_t)sorted.size();
     out.n_split = (int32_t)split_rows.size();
+    out.n_heavy = (int32_t)heavy.size();
     out.n_slots = slots;
     CK(out.items.ensure(sorted.size() * sizeof(Item)));
     CK(cudaMemcpyAsync(out.items.p, sorted.data(), sorted.size() * sizeof(Item),
@@ -476,7 +467,6 @@ API int plsa_ctx_create(int device, plsa_ctx **out)
     if (cudaDeviceGetAttribute(&max_lin, cudaDevAttrMaxTexture1DLinearWidth, device) == cudaSuccess &&
         max_lin > 0)
         ctx->tex_max_texels = (size_t)max_lin;
-    ctx->variant = VAR_TEX | VAR_GROW;
     *out = ctx;
     return PLSA_OK;
 }
@@ -653,6 +643,11 @@ static int make_texture(plsa_ctx *ctx, cudaTextureObject_t *tex, void *ptr, size
     return PLSA_OK;
 }
 
+static inline float *cur_scale(plsa_ctx *ctx)
+{
+    return reinterpret_cast<float *>(ctx->scale.p) + (size_t)ctx->curB * ctx->kp;
+}
+
 static int32_t row_stride(int32_t kp)
 {
     if (kp * 4 <= 128) { /* rows never straddle a 128-byte line */
@@ -697,15 +692,14 @@ API int plsa_set_factors(plsa_ctx *ctx, const float *p_z_given_d, const float *p
         if ((trc = make_texture(ctx, &ctx->texA[i], ctx->A[i].p, bytesA))) return trc;
         if ((trc = make_texture(ctx, &ctx->texB[i], ctx->B[i].p, bytesB))) return trc;
     }
-    CK(ctx->scale.ensure((size_t)kp * 4));
+    CK(ctx->scale.ensure((size_t)kp * 4 * 2)); /* one per P(w|z) ping-pong buffer */
     CK(ctx->ones.ensure((size_t)kp * 4));
     CK(ctx->colnorm.ensure((size_t)kp * 8));
-    CK(ctx->colpart.ensure((size_t)COLSUM_CTAS * kp * 8));
     CK(ctx->ll_out.ensure(8));
     CK(ctx->tickets.ensure(16));
     CK(cudaMemsetAsync(ctx->tickets.p, 0, 16, ctx->stream));
     int rc;
-    if ((rc = fill(ctx, ctx->scale.as<float>(), kp, 1.f))) return rc;
+    if ((rc = fill(ctx, ctx->scale.as<float>(), 2 * kp, 1.f))) return rc;
     if ((rc = fill(ctx, ctx->ones.as<float>(), kp, 1.f))) return rc;
 
     const size_t stage_bytes = (size_t)std::max<int64_t>(std::max(n, m), 1) * k * 4;
@@ -770,7 +764,7 @@ API int plsa_get_factors(plsa_ctx *ctx, float *p_z_given_d, float *p_w_given_z)
     }
     if (p_w_given_z && m > 0) {
         unpack_rows_kernel<<<(unsigned)cdiv(m * k, 256), 256, 0, ctx->stream>>>(
-            ctx->B[ctx->curB].as<float>(), ctx->scale.as<float>(), ctx->stage.as<float>(), m, k,
+            ctx->B[ctx->curB].as<float>(), cur_scale(ctx), ctx->stage.as<float>(), m, k,
             ctx->strideB, 1);
         ctx->launches++;
         CK(cudaGetLastError());
@@ -794,7 +788,7 @@ static int run_loglik(plsa_ctx *ctx, double *out)
     int rc = ensure_doc_items(ctx);
     if (rc) return rc;
     if (!ctx->have_sw && (rc = plsa_set_sample_weight(ctx, nullptr))) return rc;
-    const int64_t grid = pass_grid(ctx, ctx->doc_items.n_items, ctx->kp);
+    const int64_t grid = pass_grid(ctx->doc_items.n_items, ctx->kp);
     if (grid == 0) {
         *out = 0.0;
         return PLSA_OK;
@@ -808,11 +802,11 @@ static int run_loglik(plsa_ctx *ctx, double *out)
         a.ent = c.ent.as<int2>();
         a.own_old = ctx->A[ctx->curA].as<float>();
         a.gat_old = ctx->B[ctx->curB].as<float>();
-        a.own_scale = ctx->scale.as<float>();
+        a.own_scale = cur_scale(ctx);
         a.row_weight = ctx->sw.as<float>();
-        a.ll_partial = ctx->ll_part.as<double>();
+        a.cta_partial = ctx->ll_part.as<double>();
         a.gat_tex = ctx->texB[ctx->curB];
-        a.ticket = ctx->tickets.as<unsigned int>() + 1;
+        a.ticket = ctx->tickets.as<unsigned int>();
         a.ll_out = ctx->ll_out.as<double>();
         a.stride_own = ctx->strideA;
         a.stride_gat = ctx->strideB;
@@ -832,21 +826,34 @@ API int plsa_log_likelihood(plsa_ctx *ctx, double *ll)
     return run_loglik(ctx, ll);
 }
 
-static int run_fixup(plsa_ctx *ctx, const ItemSet &is, const float *partial, float *own_new,
-                     int stride, int normalise)
+static int run_fixup(plsa_ctx *ctx, float *newA, float *newB)
 {
-    if (is.n_split == 0) return PLSA_OK;
+    const ItemSet &ia = ctx->doc_items, &ib = ctx->term_items;
+    const int na = ia.n_split, nb = newB ? ib.n_split : 0;
+    if (na + nb == 0) return PLSA_OK;
     ProfScope ps(ctx, PLSA_PROF_FIXUP);
-    FixArgs f{};
-    f.rows = is.split_rows.as<int32_t>();
-    f.slot_begin = is.slot_begin.as<int32_t>();
-    f.partial = partial;
-    f.own_new = own_new;
-    f.n_split = is.n_split;
-    f.kp = ctx->kp;
-    f.stride_own = stride;
-    f.normalise = normalise;
-    fixup_kernel<<<(unsigned)cdiv(is.n_split, 8), 256, 0, ctx->stream>>>(f);
+    FixArgs fa{}, fb{};
+    fa.rows = ia.split_rows.as<int32_t>();
+    fa.slot_begin = ia.slot_begin.as<int32_t>();
+    fa.partial = ctx->partialA.as<float>();
+    fa.own_new = newA;
+    fa.n_split = na;
+    fa.n_heavy = std::min(ia.n_heavy, na);
+    fa.kp = ctx->kp;
+    fa.stride_own = ctx->strideA;
+    fa.normalise = 1;
+    fb.rows = ib.split_rows.as<int32_t>();
+    fb.slot_begin = ib.slot_begin.as<int32_t>();
+    fb.partial = ctx->partialB.as<float>();
+    fb.own_new = newB;
+    fb.n_split = nb;
+    fb.n_heavy = std::min(ib.n_heavy, nb);
+    fb.kp = ctx->kp;
+    fb.stride_own = ctx->strideB;
+    fb.normalise = 0;
+    const int blocks_a = fa.n_heavy + (int)cdiv(na - fa.n_heavy, 8);
+    const int blocks_b = fb.n_heavy + (int)cdiv(nb - fb.n_heavy, 8);
+    fixup_kernel<<<(unsigned)(blocks_a + blocks_b), 256, 0, ctx->stream>>>(fa, fb);
     ctx->launches++;
     CK(cudaGetLastError());
     return PLSA_OK;
@@ -899,7 +906,7 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
             a.ent = c.ent.as<int2>();
             a.own_old = ctx->A[ctx->curA].as<float>();
             a.gat_old = ctx->B[ctx->curB].as<float>();
-            a.own_scale = ctx->scale.as<float>();
+            a.own_scale = cur_scale(ctx);
             a.own_new = ctx->A[nA].as<float>();
             a.partial = ctx->partialA.as<float>();
             a.gat_tex = ctx->texB[ctx->curB];
@@ -909,9 +916,6 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
             a.thresh = e_step_thresh;
             if ((rc = launch_pass(ctx, MODE_DOC, a))) return rc;
         }
-        if ((rc = run_fixup(ctx, ctx->doc_items, ctx->partialA.as<float>(),
-                            ctx->A[nA].as<float>(), ctx->strideA, 1)))
-            return rc;
         if (!refit) {
             {   /* E-step + M-step of P(w|z): plsa.py:91-105, :189-193 (P(w|z) part) */
                 ProfScope ps(ctx, PLSA_PROF_WORD_PASS);
@@ -921,30 +925,32 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                 a.ent = use_sample_weights ? ctx->t_entw.as<int2>() : ctx->t_ent.as<int2>();
                 a.own_old = ctx->B[ctx->curB].as<float>();
                 a.gat_old = ctx->A[ctx->curA].as<float>();
-                a.own_scale = ctx->scale.as<float>();
+                a.own_scale = cur_scale(ctx);
                 a.own_new = ctx->B[nB].as<float>();
                 a.partial = ctx->partialB.as<float>();
                 a.gat_tex = ctx->texA[ctx->curA];
+                /* plsa.py:196-198: per-topic normaliser of the new P(w|z), applied lazily */
+                const int64_t tgrid = pass_grid(a.n_items, kp);
+                CK(ctx->colpart.ensure((size_t)(tgrid + tgrid / 32 + 2) * kp * 8));
+                if (ctx->tickets.cap < (size_t)(tgrid / 32 + 8) * 4) {
+                    CK(ctx->tickets.ensure((size_t)(tgrid / 32 + 8) * 4 * 2));
+                    CK(cudaMemsetAsync(ctx->tickets.p, 0, ctx->tickets.cap, ctx->stream));
+                }
+                a.cta_partial = ctx->colpart.as<double>();
+                a.ticket = ctx->tickets.as<unsigned int>() + 1; /* [0] is the log-likelihood's */
+                a.scale_out = reinterpret_cast<float *>(ctx->scale.p) + (size_t)nB * kp;
+                a.colnorm_out = ctx->colnorm.as<double>();
                 a.stride_own = ctx->strideB;
                 a.stride_gat = ctx->strideA;
                 a.kp = kp;
                 a.thresh = e_step_thresh;
                 if ((rc = launch_pass(ctx, MODE_TERM, a))) return rc;
             }
-            if ((rc = run_fixup(ctx, ctx->term_items, ctx->partialB.as<float>(),
-                                ctx->B[nB].as<float>(), ctx->strideB, 0)))
-                return rc;
-            {   /* plsa.py:196-198: per-topic normaliser of P(w|z), applied lazily */
-                ProfScope ps(ctx, PLSA_PROF_NORMALIZE);
-                colsum_kernel<<<COLSUM_CTAS, 256, 0, ctx->stream>>>(
-                    ctx->B[nB].as<float>(), c.m, ctx->strideB, kp, ctx->colpart.as<double>(),
-                    ctx->tickets.as<unsigned int>(), ctx->scale.as<float>(),
-                    ctx->colnorm.as<double>());
-                ctx->launches += 1;
-                CK(cudaGetLastError());
-            }
-            ctx->curB = nB;
         }
+        /* split rows of both factors: ordered sums of their chunk partials */
+        if ((rc = run_fixup(ctx, ctx->A[nA].as<float>(), refit ? nullptr : ctx->B[nB].as<float>())))
+            return rc;
+        if (!refit) ctx->curB = nB;
         ctx->curA = nA;
         done = i + 1;
         if (want_ll && i % n_iter_per_test == 0) { /* plsa.py:630-638 / :909-918 */
@@ -1022,8 +1028,8 @@ API int plsa_set_option(plsa_ctx *ctx, const char *name, int64_t value)
         ctx->t_ready = false; /* term items are rebuilt with the term-major copy */
         return PLSA_OK;
     }
-    if (!strcmp(name, "variant")) {
-        ctx->variant = (int)value;
+    if (!strcmp(name, "texture")) {
+        ctx->use_texture = value != 0;
         return PLSA_OK;
     }
     return ctx->fail(PLSA_EINVAL, std::string("unknown option: ") + name);
@@ -1098,7 +1104,7 @@ API int plsa_stash_topics(plsa_ctx *ctx, int32_t slot, int32_t n_slots)
     }
     if (m > 0) {
         unpack_rows_kernel<<<(unsigned)cdiv(m * ctx->k, 256), 256, 0, ctx->stream>>>(
-            ctx->B[ctx->curB].as<float>(), ctx->scale.as<float>(),
+            ctx->B[ctx->curB].as<float>(), cur_scale(ctx),
             ctx->topics_dev.as<float>() + per * (size_t)slot, m, ctx->k, ctx->strideB, 1);
         ctx->launches++;
         CK(cudaGetLastError());

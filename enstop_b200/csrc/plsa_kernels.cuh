@@ -13,13 +13,25 @@
  * and adds x * v_z / norm to the row's k accumulators — that is the E-step posterior
  * (plsa.py:104-105) consumed immediately by the M-step sums (plsa.py:182-194) without the
  * nnz x k P(z|d,w) array ever existing in memory.  The doc pass row-normalises its result
- * (plsa.py:199-202); the term pass leaves raw sums and a column-sum kernel produces the
- * per-topic normalisers (plsa.py:196-198) that the NEXT pass folds into the owned row.
+ * (plsa.py:199-202); the term pass leaves raw sums and also produces the per-topic
+ * normalisers (plsa.py:196-198) that the NEXT pass folds into the owned row.
  *
- * Lane mapping: a row of k floats is KV*G float4 vectors; G lanes cooperate on one stored
- * entry (lane j of the group holds topics 4j..4j+3), 32/G entries are in flight per warp
- * step, the normaliser is a G-lane shuffle reduction.  k = 20 -> G = 5, six entries per
- * step; k = 128 -> G = 32.
+ * Lane mapping ("group per row"): a factor row of k floats is KV*G float4 vectors; a group of
+ * G lanes owns ONE work item (a row, or a chunk of a long row) and walks it one entry per
+ * step — lane j of the group holds topics 4j..4j+3 of the owned row, of the accumulators and
+ * of every gathered row, so a gather is one 16-byte fetch per lane and the G lanes cover one
+ * contiguous row segment (80 B at k=20).  A warp carries 32/G items at once (k=20: G=5, six
+ * items; k=128: G=32, one item), U entries of each in flight; the posterior normaliser is a
+ * G-lane shuffle reduction.  The serial latency chain at the start of an item (item header
+ * -> entries + owned row -> first gathered rows) is thereby shared by 32/G items, and there
+ * is no cross-group fold at the end.  Items are sorted by length so the items of a warp are
+ * (nearly) equally long; rows longer than `chunk` entries are split so that no group walks
+ * a long serial chain.
+ *
+ * Gathers go through the texture pipe (tex1Dfetch on a linear float4 view of the factor)
+ * when the factor fits a 1-D linear texture: measured on B200 the LSU data path and the
+ * shuffles compete for the same pipe, the texture path does not (scripts/microbench_gather.cu,
+ * profiles/).  Otherwise plain read-only 16-byte loads are used.
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -27,7 +39,7 @@
 
 namespace plsa {
 
-struct Item {          /* one unit of warp work: a row, or a chunk of a long row        */
+struct Item {          /* one unit of group work: a row, or a chunk of a long row       */
     int64_t start;     /* first stored entry                                            */
     int32_t row;       /* row whose factor this item owns                               */
     int32_t len;       /* stored entries in this item                                   */
@@ -41,27 +53,22 @@ struct PassArgs {
     const Item *items;
     int64_t n_items;
     const int2 *ent;         /* stored entries {gather-row index, float bits of the value};
-                                the array carries ENT_SLACK readable entries past its end   */
+                                readable (zeroed) padding follows the last entry          */
     const float *own_old;    /* [rows, stride_own]                                      */
     const float *gat_old;    /* [cols, stride_gat]                                      */
     const float *own_scale;  /* [kp] folded into the owned row (1/column-sum of P(w|z)) */
     float *own_new;          /* [rows, stride_own]                                      */
     float *partial;          /* [slots, kp] raw sums of split rows                      */
     const float *row_weight; /* MODE_LOGLIK: sample_weight[d]                           */
-    double *ll_partial;      /* MODE_LOGLIK: one double per CTA                         */
+    double *cta_partial;     /* MODE_LOGLIK: [grid]; MODE_TERM: [grid, kp] per-CTA sums  */
+    unsigned int *ticket;    /* zeroed counters (1 + grid/32): last-arrival reductions       */
+    double *ll_out;          /* MODE_LOGLIK: the log-likelihood                          */
+    float *scale_out;        /* MODE_TERM: [kp] 1 / column sum of the new P(w|z)         */
+    double *colnorm_out;     /* MODE_TERM: [kp] the column sums                          */
+    cudaTextureObject_t gat_tex; /* gat_old as a linear float4 texture (TEX kernels)     */
     int32_t stride_own, stride_gat, kp;
     float thresh;
-    cudaTextureObject_t gat_tex; /* gat_old as a linear float4 texture (VAR_TEX kernels)   */
-    unsigned int *ticket;        /* MODE_LOGLIK: zeroed counter, last CTA does the final sum */
-    double *ll_out;              /* MODE_LOGLIK: the log-likelihood                          */
 };
-
-/* kernel variants (template parameter VAR) */
-enum { VAR_TEX = 1,  /* gather through the texture pipe instead of LDG                       */
-       VAR_GROW = 2, /* group-per-row kernel: each G-lane group walks its own row             */
-       VAR_REGS = 4, /* allow ~85 registers (3 CTAs/SM) instead of 64 (4 CTAs/SM)            */
-       VAR_X_NOTHRESH = 8,  /* TIMING EXPERIMENT ONLY (wrong results): skip the threshold   */
-       VAR_X_NOSHFL = 16    /* TIMING EXPERIMENT ONLY (wrong results): skip the group sum   */ };
 
 constexpr int ENT_SLACK = 256;
 
@@ -117,9 +124,6 @@ __device__ __forceinline__ float group_sum(float v, int gbase, int j)
     }
 }
 
-#ifndef PLSA_U_OVERRIDE
-#define PLSA_U_OVERRIDE 0
-#endif
 /* Log-likelihood reduction, deterministic: lanes (butterfly), warps in order, one double per
  * CTA; the CTA that arrives last adds the per-CTA values in index order (fixed tree). */
 __device__ __forceinline__ void finish_loglik(const PassArgs &a, double ll_acc)
@@ -134,7 +138,7 @@ __device__ __forceinline__ void finish_loglik(const PassArgs &a, double ll_acc)
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sm[i];
-        a.ll_partial[blockIdx.x] = t;
+        a.cta_partial[blockIdx.x] = t;
         __threadfence();
         last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
     }
@@ -142,7 +146,7 @@ __device__ __forceinline__ void finish_loglik(const PassArgs &a, double ll_acc)
     if (!last) return;
     __threadfence();
     double s = 0.0;
-    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) s += a.ll_partial[i];
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) s += a.cta_partial[i];
     sm[threadIdx.x] = s;
     __syncthreads();
     for (int off = (int)blockDim.x >> 1; off > 0; off >>= 1) {
@@ -155,250 +159,111 @@ __device__ __forceinline__ void finish_loglik(const PassArgs &a, double ll_acc)
     }
 }
 
-template <int G, int KV> struct PassShape {
-    static constexpr int NG = 32 / G;                       /* entries per warp step      */
-    static constexpr int U0 = (PLSA_U_OVERRIDE && KV == 1 && NG < 8) ? PLSA_U_OVERRIDE
-                              : (KV >= 4) ? 1 : (KV == 2) ? 2 : (NG >= 8) ? 2 : (NG >= 4) ? 3 : 4;
-    static constexpr int U = (NG * U0 > 32) ? (32 / NG) : U0; /* a chunk is <= one entry per lane */
-    static constexpr int CH = NG * U;                       /* entries per loop iteration */
-};
-
-/* One loop iteration: U steps of NG entries.  TAIL: entries at or past `len` are read (the
- * next row's, or the slack) but their value is forced to 0 so they add nothing. */
+/* Column sums of the new raw P(w|z)^T (plsa.py:196-198), fused into the term pass: the sum
+ * over rows of P(w|z)^T[w,z] is the sum over ALL work items (whole rows and chunks alike) of
+ * their accumulators.  Deterministic: groups of a warp are folded in a fixed shuffle tree
+ * (float), the 8 warps of a CTA are added in order (float64) into cta_partial[cta, :], and
+ * the CTA that arrives last adds the per-CTA values in index order and writes the scale. */
 template <int G, int KV>
-__device__ __forceinline__ void load_entries(const int2 *__restrict__ ent, int base, int grp,
-                                             int2 (&e)[PassShape<G, KV>::U])
-{
-#pragma unroll
-    for (int u = 0; u < PassShape<G, KV>::U; ++u)
-        e[u] = __ldg(ent + base + u * PassShape<G, KV>::NG + grp);
-}
-
-/* issue the gathers of one iteration: U steps x KV float4 per lane */
-template <int G, int KV, int VAR>
-__device__ __forceinline__ void issue_gathers(const PassArgs &a,
-                                              const int2 (&e)[PassShape<G, KV>::U],
-                                              const char *gat_base, const uint32_t (&lane_off)[KV],
-                                              uint32_t stride_bytes,
-                                              float4 (&g)[PassShape<G, KV>::U][KV])
-{
-    constexpr int U = PassShape<G, KV>::U;
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        if constexpr (VAR & VAR_TEX) {
-            const int t0 = e[u].x * (int)(stride_bytes >> 4);
-#pragma unroll
-            for (int q = 0; q < KV; ++q)
-                g[u][q] = tex1Dfetch<float4>(a.gat_tex, t0 + (int)(lane_off[q] >> 4));
-        } else if constexpr (KV == 1) { /* lane offset is folded into gat_base */
-            g[u][0] = ldg_f4_bytes(gat_base + (uint64_t)(uint32_t)e[u].x * stride_bytes);
-        } else {
-            const char *row = gat_base + (uint64_t)(uint32_t)e[u].x * stride_bytes;
-#pragma unroll
-            for (int q = 0; q < KV; ++q) g[u][q] = ldg_f4_bytes(row + lane_off[q]);
-        }
-    }
-}
-
-/* E-step + M-step sums of one iteration's entries.  TAIL: entries at or past `len` were
- * read (the next row's, or the slack) but their value is forced to 0 so they add nothing. */
-template <int G, int KV, int MODE, bool TAIL, int VAR = 0>
-__device__ __forceinline__ void consume_iteration(const int2 (&e)[PassShape<G, KV>::U],
-                                                  float4 (&g)[PassShape<G, KV>::U][KV], int base,
-                                                  int len, const float4 (&own)[KV],
-                                                  float4 (&acc)[KV], double &ll_acc, float rw,
-                                                  float thresh, int grp, int j, int gbase)
-{
-    constexpr int NG = PassShape<G, KV>::NG;
-    constexpr int U = PassShape<G, KV>::U;
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        float x = __int_as_float(e[u].y);
-        if constexpr (TAIL) x = (base + u * NG + grp < len) ? x : 0.f;
-        float part;
-#pragma unroll
-        for (int q = 0; q < KV; ++q) {
-            float4 v;
-            v.x = g[u][q].x * own[q].x;
-            v.y = g[u][q].y * own[q].y;
-            v.z = g[u][q].z * own[q].z;
-            v.w = g[u][q].w * own[q].w;
-            if constexpr (MODE != MODE_LOGLIK && !(VAR & VAR_X_NOTHRESH)) { /* plsa.py:98-102 */
-                v.x = v.x > thresh ? v.x : 0.f;
-                v.y = v.y > thresh ? v.y : 0.f;
-                v.z = v.z > thresh ? v.z : 0.f;
-                v.w = v.w > thresh ? v.w : 0.f;
-            }
-            g[u][q] = v;
-            const float s4 = (v.x + v.y) + (v.z + v.w);
-            part = (q == 0) ? s4 : part + s4;
-        }
-        const float norm = (VAR & VAR_X_NOSHFL) ? part : group_sum<G>(part, gbase, j);
-        if constexpr (MODE == MODE_LOGLIK) {
-            /* plsa.py:383-384; one lane per entry contributes, x == 0 marks a non-entry */
-            if (j == 0 && grp < NG && x != 0.f) ll_acc += (double)(x * __logf(norm) * rw);
-        } else {
-            /* plsa.py:104: posterior = v / norm if norm > 0.  Products that survive the
-             * threshold are normal floats (the host passes thresh >= FLT_MIN), so norm is
-             * 0 or normal; norm == 0 gives x * inf (or NaN), clamped to a finite c that
-             * multiplies v == 0. */
-            const float c = fminf(x * rcp_fast(norm), 3.0e38f);
-#pragma unroll
-            for (int q = 0; q < KV; ++q) {
-                acc[q].x = fmaf(c, g[u][q].x, acc[q].x);
-                acc[q].y = fmaf(c, g[u][q].y, acc[q].y);
-                acc[q].z = fmaf(c, g[u][q].z, acc[q].z);
-                acc[q].w = fmaf(c, g[u][q].w, acc[q].w);
-            }
-        }
-    }
-}
-
-template <int G, int KV, int MODE, int VAR>
-__global__ void __launch_bounds__(256, (KV == 1) ? ((VAR & VAR_REGS) ? 3 : 4) : (KV == 2) ? 2 : 1)
-    row_pass_kernel(const PassArgs a)
-{
-    constexpr int NG = PassShape<G, KV>::NG;
-    constexpr int CH = PassShape<G, KV>::CH;
-
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int64_t item_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-
-    const int grp = lane / G;      /* == NG for the 32 % G idle lanes: they read valid memory,
-                                      own zeros, and are never folded in                    */
-    const int j = lane - grp * G;
-    const int gbase = grp * G;
-
-    double ll_acc = 0.0;
-    if (item_id < a.n_items) {
-        const Item it = a.items[item_id];
-
-        /* the owned row, with the lazily applied P(w|z) normaliser folded in */
-        float4 own[KV];
-#pragma unroll
-        for (int q = 0; q < KV; ++q) {
-            const int c = 4 * (j + G * q);
-            if (grp < NG && c < a.kp) {
-                const float4 o = ldg_f4(a.own_old + (int64_t)it.row * a.stride_own + c);
-                const float4 s = ldg_f4(a.own_scale + c);
-                own[q] = make_float4(o.x * s.x, o.y * s.y, o.z * s.z, o.w * s.w);
-            } else {
-                own[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-        float4 acc[KV];
-#pragma unroll
-        for (int q = 0; q < KV; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        float rw = 1.f;
-        if constexpr (MODE == MODE_LOGLIK) rw = a.row_weight[it.row];
-
-        const int2 *ent = a.ent + it.start;
-        const int len = it.len;
-        const float thresh = a.thresh;
-        const uint32_t stride_bytes = (uint32_t)a.stride_gat * 4u;
-        /* lanes whose 4 topics lie in the padding (c >= kp) re-read the row's first vector:
-         * always in bounds, and their `own` is zero */
-        uint32_t lane_off[KV];
-#pragma unroll
-        for (int q = 0; q < KV; ++q) {
-            const int c = 4 * (j + G * q);
-            lane_off[q] = (c < a.kp) ? (uint32_t)c * 4u : 0u;
-        }
-        const char *gat_base = opaque_ptr(reinterpret_cast<const char *>(a.gat_old) +
-                                          (KV == 1 ? lane_off[0] : 0u));
-
-        constexpr int U = PassShape<G, KV>::U;
-        /* Entries are fetched by one broadcast 8-byte load per group per step; reads past
-         * the row end land in the next row or in the array's slack and are ignored. */
-        {
-            int2 e[U];
-            load_entries<G, KV>(ent, 0, grp, e);
-            int base = 0;
-            for (; base + CH <= len; base += CH) {
-                int2 en[U];
-                float4 g[U][KV];
-                load_entries<G, KV>(ent, base + CH, grp, en);
-                issue_gathers<G, KV, VAR>(a, e, gat_base, lane_off, stride_bytes, g);
-                consume_iteration<G, KV, MODE, false, VAR>(e, g, base, len, own, acc, ll_acc, rw,
-                                                      thresh, grp, j, gbase);
-#pragma unroll
-                for (int u = 0; u < U; ++u) e[u] = en[u];
-            }
-            if (base < len) {
-                float4 g[U][KV];
-                issue_gathers<G, KV, VAR>(a, e, gat_base, lane_off, stride_bytes, g);
-                consume_iteration<G, KV, MODE, true, VAR>(e, g, base, len, own, acc, ll_acc, rw, thresh,
-                                                     grp, j, gbase);
-            }
-        }
-
-        if constexpr (MODE != MODE_LOGLIK) {
-            /* fold the NG groups: group 0 ends up with the row's sums */
-#pragma unroll
-            for (int off = G; off < 32; off <<= 1) {
-#pragma unroll
-                for (int q = 0; q < KV; ++q) {
-                    const float tx = __shfl_down_sync(0xffffffffu, acc[q].x, off & 31);
-                    const float ty = __shfl_down_sync(0xffffffffu, acc[q].y, off & 31);
-                    const float tz = __shfl_down_sync(0xffffffffu, acc[q].z, off & 31);
-                    const float tw = __shfl_down_sync(0xffffffffu, acc[q].w, off & 31);
-                    if (lane + off < NG * G) {
-                        acc[q].x += tx; acc[q].y += ty; acc[q].z += tz; acc[q].w += tw;
-                    }
-                }
-            }
-            float inv = 1.f;
-            if constexpr (MODE == MODE_DOC) {
-                if (it.slot < 0) { /* plsa.py:199-202: divide by the row's total if > 0 */
-                    float part = 0.f;
-#pragma unroll
-                    for (int q = 0; q < KV; ++q)
-                        part += (acc[q].x + acc[q].y) + (acc[q].z + acc[q].w);
-                    float tot = (grp == 0) ? part : 0.f;
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1)
-                        tot += __shfl_xor_sync(0xffffffffu, tot, off);
-                    inv = tot > 0.f ? 1.f / tot : 1.f;
-                }
-            }
-            if (grp == 0) {
-                float *dst = (it.slot < 0)
-                                 ? a.own_new + (int64_t)it.row * a.stride_own
-                                 : a.partial + (int64_t)it.slot * a.kp;
-#pragma unroll
-                for (int q = 0; q < KV; ++q) {
-                    const int c = 4 * (j + G * q);
-                    if (c < a.kp)
-                        *reinterpret_cast<float4 *>(dst + c) = make_float4(
-                            acc[q].x * inv, acc[q].y * inv, acc[q].z * inv, acc[q].w * inv);
-                }
-            }
-        }
-    }
-
-    if constexpr (MODE == MODE_LOGLIK) finish_loglik(a, ll_acc);
-}
-
-/* ==========================================================================================
- * Group-per-row variant.  Instead of one row per warp (32/G entries of the SAME row per step,
- * folded at the row end), every G-lane group owns its OWN row and walks it one entry per
- * step: a warp carries 32/G rows at once.  The serial latency chain at the start of a row
- * (work item -> entries + owned row -> first gathered rows) is then paid by 32/G rows
- * concurrently, and the end-of-row fold across groups disappears.  Items are sorted by
- * length, so the rows of a warp are of (nearly) equal length.
- * ========================================================================================== */
-template <int G, int KV, int MODE, int VAR>
-__global__ void __launch_bounds__(256, (KV == 1) ? 4 : (KV == 2) ? 2 : 1)
-    row_group_kernel(const PassArgs a)
+__device__ __forceinline__ void finish_colsum(const PassArgs &a, float4 (&acc)[KV], int lane,
+                                              int warp, int j, bool lane_on)
 {
     constexpr int NG = 32 / G;
-    constexpr int U = (KV >= 4) ? 1 : (KV == 2) ? 2 : 4;   /* entries of a row in flight */
+    __shared__ float wsum[8][128];
+    __shared__ bool last;
+    /* fold the NG groups of the warp: group 0 ends up with the warp's sums */
+#pragma unroll
+    for (int off = G; off < 32; off <<= 1) {
+#pragma unroll
+        for (int q = 0; q < KV; ++q) {
+            const float tx = __shfl_down_sync(0xffffffffu, acc[q].x, off & 31);
+            const float ty = __shfl_down_sync(0xffffffffu, acc[q].y, off & 31);
+            const float tz = __shfl_down_sync(0xffffffffu, acc[q].z, off & 31);
+            const float tw = __shfl_down_sync(0xffffffffu, acc[q].w, off & 31);
+            if (lane + off < NG * G) {
+                acc[q].x += tx; acc[q].y += ty; acc[q].z += tz; acc[q].w += tw;
+            }
+        }
+    }
+    (void)lane_on;
+    const int kp = a.kp;
+    double *mine = a.cta_partial + (int64_t)blockIdx.x * kp;
+#pragma unroll
+    for (int q = 0; q < KV; ++q) {   /* 128 topics per sweep (G == 32 when KV > 1) */
+        const int c = 4 * (j + G * q);
+        __syncthreads();
+        if (lane < G && c < kp) {
+            const int cc = c - 128 * q * (G == 32 ? 1 : 0);
+            wsum[warp][cc] = acc[q].x; wsum[warp][cc + 1] = acc[q].y;
+            wsum[warp][cc + 2] = acc[q].z; wsum[warp][cc + 3] = acc[q].w;
+        }
+        __syncthreads();
+        const int zb = (G == 32) ? 128 * q : 0;
+        const int width = min(128, kp - zb);
+        if ((int)threadIdx.x < width) {
+            double t = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += (double)wsum[w][threadIdx.x];
+            mine[zb + threadIdx.x] = t;
+        }
+    }
+    /* two-level "last arrival" reduction, summation order fixed by index:
+     *   level 1: CTAs in groups of 32; the last of a group adds the group's partials
+     *   level 2: the last group adds the group sums and writes the scale */
+    const unsigned n_groups = (gridDim.x + 31u) >> 5;
+    const unsigned grp_id = blockIdx.x >> 5;
+    const unsigned grp_size = min(32u, gridDim.x - (grp_id << 5));
+    unsigned int *ticket1 = a.ticket + 1 + grp_id;
+    double *gpartial = a.cta_partial + (int64_t)gridDim.x * kp; /* [n_groups, kp] */
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd(ticket1, 1u) == grp_size - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const int nw = blockDim.x >> 5;
+    for (int z = warp; z < kp; z += nw) { /* one warp per topic, fixed-order butterfly */
+        double t = (lane < (int)grp_size)
+                       ? a.cta_partial[(int64_t)((grp_id << 5) + lane) * kp + z] : 0.0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        if (lane == 0) gpartial[(int64_t)grp_id * kp + z] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *ticket1 = 0u;
+        __threadfence();
+        last = atomicAdd(a.ticket, 1u) == n_groups - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (int z = warp; z < kp; z += nw) {
+        double t = 0.0;
+        for (unsigned i = lane; i < n_groups; i += 32) t += gpartial[(int64_t)i * kp + z];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        if (lane == 0) {
+            a.colnorm_out[z] = t;
+            a.scale_out[z] = t > 0.0 ? (float)(1.0 / t) : 1.f;
+        }
+    }
+    if (threadIdx.x == 0) *a.ticket = 0u;
+}
+
+template <int G, int KV, int MODE, bool TEX>
+__global__ void __launch_bounds__(256, (KV == 1) ? 4 : (KV == 2) ? 2 : 1)
+    row_pass_kernel(const PassArgs a)
+{
+    constexpr int NG = 32 / G;
+    constexpr int U = (KV >= 4) ? 1 : (KV == 2) ? 2 : 4;   /* entries of an item in flight */
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int grp_raw = lane / G;
-    const int grp = grp_raw < NG ? grp_raw : NG - 1;        /* idle lanes shadow the last group */
+    const int grp = grp_raw < NG ? grp_raw : NG - 1;        /* 32 % G idle lanes shadow the
+                                                               last group and never write  */
     const int j = lane - grp_raw * G;
     const int gbase = grp_raw * G;
     const bool lane_on = grp_raw < NG;
@@ -414,6 +279,9 @@ __global__ void __launch_bounds__(256, (KV == 1) ? 4 : (KV == 2) ? 2 : 1)
     for (int off = 16; off > 0; off >>= 1)
         maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, off));
 
+    /* the owned row, with the lazily applied P(w|z) normaliser folded in; lanes whose four
+     * topics lie in the padding (c >= kp) own zeros and re-read the gathered row's first
+     * vector, which is always in bounds */
     float4 own[KV], acc[KV];
     uint32_t lane_off[KV];
 #pragma unroll
@@ -440,8 +308,8 @@ __global__ void __launch_bounds__(256, (KV == 1) ? 4 : (KV == 2) ? 2 : 1)
                                       (KV == 1 ? lane_off[0] : 0u));
     double ll_acc = 0.0;
 
-    /* entries one iteration ahead; reads past a row's end land in following rows or in the
-     * array's slack and get value 0 */
+    /* entries one iteration ahead (one broadcast 8-byte load per group per entry); reads
+     * past an item's end land in following rows or in the array's padding and count as 0 */
     int2 e[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) e[u] = __ldg(ent + u);
@@ -452,12 +320,12 @@ __global__ void __launch_bounds__(256, (KV == 1) ? 4 : (KV == 2) ? 2 : 1)
         float4 g[U][KV];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if constexpr (VAR & VAR_TEX) {
+            if constexpr (TEX) {
                 const int t0 = e[u].x * (int)(stride_bytes >> 4);
 #pragma unroll
                 for (int q = 0; q < KV; ++q)
                     g[u][q] = tex1Dfetch<float4>(a.gat_tex, t0 + (int)(lane_off[q] >> 4));
-            } else if constexpr (KV == 1) {
+            } else if constexpr (KV == 1) { /* lane offset is folded into gat_base */
                 g[u][0] = ldg_f4_bytes(gat_base + (uint64_t)(uint32_t)e[u].x * stride_bytes);
             } else {
                 const char *row = gat_base + (uint64_t)(uint32_t)e[u].x * stride_bytes;
@@ -488,9 +356,14 @@ __global__ void __launch_bounds__(256, (KV == 1) ? 4 : (KV == 2) ? 2 : 1)
             }
             const float norm = group_sum<G>(part, gbase, j);
             if constexpr (MODE == MODE_LOGLIK) {
+                /* plsa.py:383-384; one lane per entry contributes, x == 0 marks a non-entry */
                 if (j == 0 && lane_on && x != 0.f) ll_acc += (double)(x * __logf(norm) * rw);
             } else {
-                const float c = fminf(x * rcp_fast(norm), 3.0e38f); /* see consume_iteration */
+                /* plsa.py:104: posterior = v / norm if norm > 0.  Products that survive the
+                 * threshold are normal floats (the host passes thresh >= FLT_MIN), so norm
+                 * is 0 or normal; norm == 0 gives x * inf (or NaN), clamped to a finite c
+                 * that multiplies v == 0. */
+                const float c = fminf(x * rcp_fast(norm), 3.0e38f);
 #pragma unroll
                 for (int q = 0; q < KV; ++q) {
                     acc[q].x = fmaf(c, g[u][q].x, acc[q].x);
@@ -504,7 +377,9 @@ __global__ void __launch_bounds__(256, (KV == 1) ? 4 : (KV == 2) ? 2 : 1)
         for (int u = 0; u < U; ++u) e[u] = en[u];
     }
 
-    if constexpr (MODE != MODE_LOGLIK) {
+    if constexpr (MODE == MODE_LOGLIK) {
+        finish_loglik(a, ll_acc);
+    } else {
         float inv = 1.f;
         if constexpr (MODE == MODE_DOC) { /* plsa.py:199-202: divide by the row's total if > 0 */
             float part = 0.f;
@@ -524,35 +399,53 @@ __global__ void __launch_bounds__(256, (KV == 1) ? 4 : (KV == 2) ? 2 : 1)
                         acc[q].x * inv, acc[q].y * inv, acc[q].z * inv, acc[q].w * inv);
             }
         }
-    } else {
-        finish_loglik(a, ll_acc);
+        if constexpr (MODE == MODE_TERM) finish_colsum<G, KV>(a, acc, lane, warp, j, lane_on);
     }
 }
 
-/* Split rows: add the partial sums of each split row in slot order (float64), write the
- * row; document rows are normalised here (plsa.py:199-202). */
+/* Split rows: add the partial sums of each split row (float64, fixed order), write the row;
+ * document rows are normalised here (plsa.py:199-202).  One launch serves both factors.
+ * Rows are listed heavy first: a row with more than 32 chunks gets a whole CTA (its chunks
+ * spread over 256 threads), the others one warp each — so that no thread walks a long
+ * serial chain of dependent loads. */
 struct FixArgs {
-    const int32_t *rows;       /* [n_split]   */
+    const int32_t *rows;       /* [n_split], rows with > 32 slots first                  */
     const int32_t *slot_begin; /* [n_split+1] */
     const float *partial;      /* [slots, kp] */
     float *own_new;
-    int32_t n_split, kp, stride_own, normalise;
+    int32_t n_split, n_heavy, kp, stride_own, normalise;
 };
 
-/* one warp per split row: lane l adds slots l, l+32, ... (four loads in flight, combined in a
- * fixed order), then a fixed butterfly across lanes */
-__global__ void __launch_bounds__(256) fixup_kernel(const FixArgs a)
+/* sum over the workers (a warp, or the 8 warps of a CTA) of one double per thread; every
+ * thread receives the total; fixed order */
+template <bool CTA>
+__device__ __forceinline__ double fix_reduce(double t, double *sm /* [8] */)
 {
-    const int lane = threadIdx.x & 31;
-    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (r >= a.n_split) return;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+    if constexpr (CTA) {
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = t;
+        __syncthreads();
+        t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sm[w];
+    }
+    return t;
+}
+
+template <bool CTA>
+__device__ __forceinline__ void fixup_row(const FixArgs &a, int r, double *sm)
+{
+    const int nthr = CTA ? 256 : 32;
+    const int tid = CTA ? (int)threadIdx.x : (int)(threadIdx.x & 31);
     const int s0 = a.slot_begin[r], s1 = a.slot_begin[r + 1];
     const float *p = a.partial;
     const int kp = a.kp;
     double inv = 1.0;
     if (a.normalise) {
         double t0 = 0.0, t1 = 0.0;
-        for (int sl = s0 + lane; sl < s1; sl += 32) {
+        for (int sl = s0 + tid; sl < s1; sl += nthr) {
             const float4 *row = reinterpret_cast<const float4 *>(p + (int64_t)sl * kp);
             int c = 0;
             for (; c + 1 < kp / 4; c += 2) {
@@ -565,23 +458,21 @@ __global__ void __launch_bounds__(256) fixup_kernel(const FixArgs a)
                 t0 += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
             }
         }
-        double t = t0 + t1;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        const double t = fix_reduce<CTA>(t0 + t1, sm);
         inv = t > 0.0 ? 1.0 / t : 1.0;
     }
     float *dst = a.own_new + (int64_t)a.rows[r] * a.stride_own;
     for (int zb = 0; zb < kp; zb += 8) {
         const bool two = zb + 8 <= kp; /* kp is a multiple of 4: a block is 8 or 4 floats */
-        double acc[4][8];
+        double acc[2][8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 2; ++u)
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[u][i] = 0.0;
-        for (int sl = s0 + lane; sl < s1; sl += 128) {
+        for (int sl = s0 + tid; sl < s1; sl += 2 * nthr) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int s = sl + 32 * u;
+            for (int u = 0; u < 2; ++u) {
+                const int s = sl + nthr * u;
                 if (s < s1) {
                     const float4 *row = reinterpret_cast<const float4 *>(p + (int64_t)s * kp + zb);
                     const float4 v = row[0];
@@ -598,74 +489,30 @@ __global__ void __launch_bounds__(256) fixup_kernel(const FixArgs a)
         double mine = 0.0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            double t = (acc[0][i] + acc[1][i]) + (acc[2][i] + acc[3][i]);
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-            if (lane == i) mine = t;
+            const double t = fix_reduce<CTA>(acc[0][i] + acc[1][i], sm);
+            if (tid == i) mine = t;
         }
-        if (lane < (two ? 8 : 4)) dst[zb + lane] = (float)(mine * inv);
+        if (tid < (two ? 8 : 4)) dst[zb + tid] = (float)(mine * inv);
     }
 }
 
-/* Column sums of the raw P(w|z)^T accumulators -> per-topic scale 1/sum (plsa.py:196-198).
- * Deterministic: per-CTA float64 partials over a slab of rows; the CTA that arrives last
- * adds the per-CTA values in index order. */
-constexpr int COLSUM_CTAS = 592;
-
-__global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ B, int64_t n_rows,
-                                                     int stride, int kp,
-                                                     double *__restrict__ partial,
-                                                     unsigned int *ticket, float *__restrict__ scale,
-                                                     double *__restrict__ colnorm)
+__device__ __forceinline__ int fix_blocks(const FixArgs &a)
 {
-    __shared__ double sm[256];
-    __shared__ bool last;
-    const int64_t per = (n_rows + gridDim.x - 1) / gridDim.x;
-    const int64_t r0 = per * blockIdx.x;
-    const int64_t r1 = min(n_rows, r0 + per);
-    for (int zb = 0; zb < kp; zb += 256) {
-        const int width = min(256, kp - zb);       /* columns handled in this sweep    */
-        const int rl = 256 / width;                /* row lanes                        */
-        const int z = threadIdx.x % width, rr = threadIdx.x / width;
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        if (rr < rl) {
-            const float *col = B + zb + z;
-            int64_t r = r0 + rr;
-            for (; r + 3 * rl < r1; r += 4 * rl) { /* four independent loads in flight */
-                const float v0 = col[r * stride], v1 = col[(r + rl) * stride],
-                            v2 = col[(r + 2 * rl) * stride], v3 = col[(r + 3 * rl) * stride];
-                s0 += (double)v0; s1 += (double)v1; s2 += (double)v2; s3 += (double)v3;
-            }
-            for (; r < r1; r += rl) s0 += (double)col[r * stride];
-        }
-        sm[threadIdx.x] = (s0 + s1) + (s2 + s3);
-        __syncthreads();
-        if (threadIdx.x < width) {
-            double t = 0.0;
-            for (int i = 0; i < rl; ++i) t += sm[i * width + threadIdx.x];
-            partial[(int64_t)blockIdx.x * kp + zb + threadIdx.x] = t;
-        }
-        __syncthreads();
+    return a.n_heavy + (a.n_split - a.n_heavy + 7) / 8;
+}
+
+__global__ void __launch_bounds__(256) fixup_kernel(const FixArgs fa, const FixArgs fb)
+{
+    __shared__ double sm[8];
+    int b = blockIdx.x;
+    const FixArgs &a = (b < fix_blocks(fa)) ? fa : fb;
+    if (b >= fix_blocks(fa)) b -= fix_blocks(fa);
+    if (b < a.n_heavy) {
+        fixup_row<true>(a, b, sm);
+    } else {
+        const int r = a.n_heavy + (b - a.n_heavy) * 8 + (int)(threadIdx.x >> 5);
+        if (r < a.n_split) fixup_row<false>(a, r, sm);
     }
-    if (threadIdx.x == 0) {
-        __threadfence();
-        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-    }
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int z = warp; z < kp; z += nw) { /* one warp per topic, fixed-order butterfly */
-        double t = 0.0;
-        for (int i = lane; i < (int)gridDim.x; i += 32) t += partial[(int64_t)i * kp + z];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-        if (lane == 0) {
-            colnorm[z] = t;
-            scale[z] = t > 0.0 ? (float)(1.0 / t) : 1.f;
-        }
-    }
-    if (threadIdx.x == 0) *ticket = 0u;
 }
 
 /* ---- layout conversion between the reference's arrays and the device layout ---------- */
