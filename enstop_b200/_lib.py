@@ -44,6 +44,8 @@ SIGNATURES = {
     "plsa_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_ctx)]),
     "plsa_ctx_destroy": (ctypes.c_int, [_ctx]),
     "plsa_upload_csr": (ctypes.c_int, [_ctx, _i32p, _i32p, _f32p, _i64, _i64, _i64]),
+    "plsa_upload_csr_typed": (ctypes.c_int, [_ctx, _i32p, _i32p, ctypes.c_void_p, _i32, _i64, _i64,
+                                             _i64]),
     "plsa_upload_coo": (ctypes.c_int, [_ctx, _i32p, _i32p, _f32p, _i64, _i64, _i64]),
     "plsa_bootstrap": (ctypes.c_int, [_ctx, _i32p, _i64]),
     "plsa_corpus_shape": (ctypes.c_int, [_ctx, _i64p, _i64p, _i64p]),
@@ -54,6 +56,7 @@ SIGNATURES = {
     "plsa_topics_device": (ctypes.c_int, [_ctx, ctypes.POINTER(ctypes.c_void_p), _i64p]),
     "plsa_em": (ctypes.c_int, [_ctx, _i32, _i32, _f64, _f32, _i32, _i32, _i32p, _f64p, _i32,
                                _i32p]),
+    "plsa_prepare": (ctypes.c_int, [_ctx, _i32]),
     "plsa_log_likelihood": (ctypes.c_int, [_ctx, _f64p]),
     "plsa_last_em_ms": (ctypes.c_int, [_ctx, _f32p]),
     "plsa_set_profiling": (ctypes.c_int, [_ctx, _i32]),
@@ -194,14 +197,28 @@ class Context:
         self.close()
 
     # -- corpus -----------------------------------------------------------------------
+    _DTYPES = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.int32): 2,
+               np.dtype(np.int64): 3}
+
     def upload_csr(self, X):
-        """X: scipy CSR matrix (any value dtype; converted to float32 as plsa.py:714)."""
+        """X: scipy CSR matrix.  Values go up in their own dtype when it is float32/64 or
+        int32/64 and are cast to float32 on the device (plsa.py:714); other dtypes are cast
+        on the host first."""
         indptr = _as(X.indptr, np.int32)
         indices = _as(X.indices, np.int32)
-        data = _as(X.data, np.float32)
+        data = np.ascontiguousarray(X.data)
+        if data.dtype not in self._DTYPES:
+            data = data.astype(np.float32)
         n, m = X.shape
-        check(self._L.plsa_upload_csr(self._h, _ptr(indptr, _i32p), _ptr(indices, _i32p),
-                                      _ptr(data, _f32p), n, m, data.shape[0]), self._h)
+        check(self._L.plsa_upload_csr_typed(self._h, _ptr(indptr, _i32p), _ptr(indices, _i32p),
+                                            data.ctypes.data_as(ctypes.c_void_p),
+                                            self._DTYPES[data.dtype], n, m, data.shape[0]),
+              self._h)
+
+    def prepare(self, refit=False):
+        """Build work items (and the term-major copy for a full fit) now rather than inside
+        the first em() — the host overlaps its seeded initialisation with this."""
+        check(self._L.plsa_prepare(self._h, int(bool(refit))), self._h)
 
     def upload_coo(self, rows, cols, vals, n, m):
         rows, cols, vals = _as(rows, np.int32), _as(cols, np.int32), _as(vals, np.float32)
@@ -298,6 +315,42 @@ class Context:
 
     def stash_topics(self, slot, n_slots):
         check(self._L.plsa_stash_topics(self._h, int(slot), int(n_slots)), self._h)
+
+
+# ---- context pool ---------------------------------------------------------------------------
+# A fit that is not handed a context borrows one from here and gives it back afterwards, so
+# repeated fits (PLSA.fit then transform, cross-validation loops, ...) reuse the device
+# buffers instead of paying cudaMalloc/cudaFree each time.  release_device_memory() frees them.
+_pool = {}
+_pool_lock = threading.Lock()
+_POOL_MAX_PER_DEVICE = 2
+
+
+def acquire_context(device=0):
+    device = int(device)
+    with _pool_lock:
+        free = _pool.get(device)
+        if free:
+            return free.pop()
+    return Context(device)
+
+
+def release_context(ctx):
+    with _pool_lock:
+        free = _pool.setdefault(ctx.device, [])
+        if len(free) < _POOL_MAX_PER_DEVICE and ctx._h:
+            free.append(ctx)
+            return
+    ctx.close()
+
+
+def release_device_memory():
+    """Destroy the pooled contexts (and with them every cached device buffer)."""
+    with _pool_lock:
+        ctxs = [c for free in _pool.values() for c in free]
+        _pool.clear()
+    for c in ctxs:
+        c.close()
 
 
 def gather_topics(contexts, n_slots):

@@ -89,7 +89,7 @@ struct plsa_ctx {
     const Corpus &cur() const { return use_boot ? boot : base; }
 
     /* term-major copy of the working corpus */
-    DevBuf t_ent, t_entw, up_cols, up_vals;
+    DevBuf t_ent, t_entw, up_cols, up_vals, flag;
     std::vector<int32_t> h_tindptr;
     bool t_ready = false, t_weighted_ready = false;
 
@@ -481,7 +481,7 @@ API int plsa_ctx_destroy(plsa_ctx *ctx)
     for (Corpus *c : {&ctx->base, &ctx->boot}) {
         c->indptr.release(); c->ent.release();
     }
-    for (DevBuf *b : {&ctx->t_ent, &ctx->t_entw, &ctx->up_cols, &ctx->up_vals,
+    for (DevBuf *b : {&ctx->t_ent, &ctx->t_entw, &ctx->up_cols, &ctx->up_vals, &ctx->flag,
                       &ctx->doc_items.items, &ctx->doc_items.split_rows, &ctx->doc_items.slot_begin,
                       &ctx->term_items.items, &ctx->term_items.split_rows,
                       &ctx->term_items.slot_begin, &ctx->A[0], &ctx->A[1], &ctx->B[0], &ctx->B[1],
@@ -501,9 +501,20 @@ API int plsa_ctx_destroy(plsa_ctx *ctx)
 }
 
 /* ---- corpus ----------------------------------------------------------------------------------- */
-static int upload_csr_impl(plsa_ctx *ctx, const int32_t *indptr, const int32_t *indices,
-                           const float *data, int64_t n, int64_t m, int64_t nnz)
+static size_t dtype_size(int dtype)
 {
+    switch (dtype) {
+    case PLSA_F32: case PLSA_I32: return 4;
+    case PLSA_F64: case PLSA_I64: return 8;
+    default: return 0;
+    }
+}
+
+static int upload_csr_impl(plsa_ctx *ctx, const int32_t *indptr, const int32_t *indices,
+                           const void *data, int dtype, int64_t n, int64_t m, int64_t nnz)
+{
+    const size_t vsz = dtype_size(dtype);
+    if (!vsz) return ctx->fail(PLSA_EINVAL, "upload: unknown value dtype");
     if (n < 0 || m < 0 || nnz < 0 || (nnz > 0 && (!indices || !data)) || !indptr)
         return ctx->fail(PLSA_EINVAL, "upload: null pointer or negative size");
     if (nnz >= ((int64_t)1 << 31) || n >= ((int64_t)1 << 31) - 1 || m >= ((int64_t)1 << 31) - 1)
@@ -512,31 +523,42 @@ static int upload_csr_impl(plsa_ctx *ctx, const int32_t *indptr, const int32_t *
         return ctx->fail(PLSA_EINVAL, "upload: indptr[0] != 0 or indptr[n] != nnz");
     for (int64_t r = 0; r < n; ++r)
         if (indptr[r + 1] < indptr[r]) return ctx->fail(PLSA_EINVAL, "upload: indptr decreases");
-    for (int64_t i = 0; i < nnz; ++i)
-        if ((uint32_t)indices[i] >= (uint32_t)m)
-            return ctx->fail(PLSA_EINVAL, "upload: column index out of range");
     Corpus &c = ctx->base;
     c.n = n; c.m = m; c.nnz = nnz;
     c.h_indptr.assign(indptr, indptr + n + 1);
     CK(c.indptr.ensure((size_t)(n + 1) * 4));
     CK(c.ent.ensure(ent_bytes(nnz)));
+    CK(ctx->flag.ensure(4));
+    CK(cudaMemsetAsync(ctx->flag.p, 0, 4, ctx->stream));
     CK(cudaMemsetAsync(c.ent.as<int2>() + nnz, 0, ENT_PAD * sizeof(int2), ctx->stream));
     CK(cudaMemcpyAsync(c.indptr.p, indptr, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    int bad = 0;
     if (nnz > 0) {
         CK(ctx->up_cols.ensure((size_t)nnz * 4));
-        CK(ctx->up_vals.ensure((size_t)nnz * 4));
+        CK(ctx->up_vals.ensure((size_t)nnz * vsz));
         CK(cudaMemcpyAsync(ctx->up_cols.p, indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->up_vals.p, data, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
-        interleave_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, ctx->stream>>>(
-            ctx->up_cols.as<int32_t>(), ctx->up_vals.as<float>(), nnz, c.ent.as<int2>());
+        CK(cudaMemcpyAsync(ctx->up_vals.p, data, (size_t)nnz * vsz, cudaMemcpyHostToDevice, ctx->stream));
+        const unsigned grid = (unsigned)cdiv(nnz, 256);
+        int2 *ent = c.ent.as<int2>();
+        int *flag = ctx->flag.as<int>();
+        const int32_t *cols = ctx->up_cols.as<int32_t>();
+        switch (dtype) { /* the float32 cast of plsa.py:714 happens on the device */
+        case PLSA_F32: interleave_kernel<float><<<grid, 256, 0, ctx->stream>>>(cols, ctx->up_vals.as<float>(), nnz, m, ent, flag); break;
+        case PLSA_F64: interleave_kernel<double><<<grid, 256, 0, ctx->stream>>>(cols, ctx->up_vals.as<double>(), nnz, m, ent, flag); break;
+        case PLSA_I32: interleave_kernel<int32_t><<<grid, 256, 0, ctx->stream>>>(cols, ctx->up_vals.as<int32_t>(), nnz, m, ent, flag); break;
+        default: interleave_kernel<int64_t><<<grid, 256, 0, ctx->stream>>>(cols, ctx->up_vals.as<int64_t>(), nnz, m, ent, flag); break;
+        }
         ctx->launches++;
         CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&bad, ctx->flag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->up_cols.release(); /* staging only */
-    ctx->up_vals.release();
     ctx->use_boot = false;
     corpus_changed(ctx);
+    if (bad) {
+        c.h_indptr.clear();
+        return ctx->fail(PLSA_EINVAL, "upload: column index out of range");
+    }
     return PLSA_OK;
 }
 
@@ -544,7 +566,15 @@ API int plsa_upload_csr(plsa_ctx *ctx, const int32_t *indptr, const int32_t *ind
                         const float *data, int64_t n_docs, int64_t n_terms, int64_t nnz)
 {
     CHECK_CTX(ctx);
-    return upload_csr_impl(ctx, indptr, indices, data, n_docs, n_terms, nnz);
+    return upload_csr_impl(ctx, indptr, indices, data, PLSA_F32, n_docs, n_terms, nnz);
+}
+
+API int plsa_upload_csr_typed(plsa_ctx *ctx, const int32_t *indptr, const int32_t *indices,
+                              const void *data, int32_t dtype, int64_t n_docs, int64_t n_terms,
+                              int64_t nnz)
+{
+    CHECK_CTX(ctx);
+    return upload_csr_impl(ctx, indptr, indices, data, dtype, n_docs, n_terms, nnz);
 }
 
 API int plsa_upload_coo(plsa_ctx *ctx, const int32_t *rows, const int32_t *cols,
@@ -563,7 +593,7 @@ API int plsa_upload_coo(plsa_ctx *ctx, const int32_t *rows, const int32_t *cols,
         indptr[(size_t)rows[i] + 1]++;
     }
     for (int64_t r = 0; r < n_docs; ++r) indptr[(size_t)r + 1] += indptr[(size_t)r];
-    return upload_csr_impl(ctx, indptr.data(), cols, vals, n_docs, n_terms, nnz);
+    return upload_csr_impl(ctx, indptr.data(), cols, vals, PLSA_F32, n_docs, n_terms, nnz);
 }
 
 API int plsa_bootstrap(plsa_ctx *ctx, const int32_t *row_idx, int64_t n_rows)
@@ -815,6 +845,18 @@ static int run_loglik(plsa_ctx *ctx, double *out)
     }
     CK(cudaMemcpyAsync(out, ctx->ll_out.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return PLSA_OK;
+}
+
+/* Build everything a later plsa_em needs that depends only on the corpus (work items, and
+ * for a full fit the term-major copy), so that it can overlap host-side initialisation. */
+API int plsa_prepare(plsa_ctx *ctx, int32_t refit)
+{
+    CHECK_CTX(ctx);
+    if (ctx->cur().h_indptr.empty()) return ctx->fail(PLSA_EINVAL, "prepare: no corpus uploaded");
+    int rc = ensure_doc_items(ctx);
+    if (rc) return rc;
+    if (!refit && !ctx->t_ready && (rc = build_term_major(ctx))) return rc;
     return PLSA_OK;
 }
 

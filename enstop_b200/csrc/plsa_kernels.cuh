@@ -548,12 +548,21 @@ __global__ void unpack_rows_kernel(const float *__restrict__ src, const float *_
 }
 
 /* ---- corpus preparation ------------------------------------------------------------------ */
-/* separate index / value arrays (the caller's CSR) -> interleaved entries */
-__global__ void interleave_kernel(const int32_t *__restrict__ cols, const float *__restrict__ vals,
-                                  int64_t n, int2 *__restrict__ ent)
+/* separate index / value arrays (the caller's CSR, values of any numeric type) ->
+ * interleaved entries with float32 values (plsa.py:714 `.astype(np.float32)`); an index
+ * outside [0, n_cols) raises *bad */
+template <typename T>
+__global__ void interleave_kernel(const int32_t *__restrict__ cols, const T *__restrict__ vals,
+                                  int64_t n, int64_t n_cols, int2 *__restrict__ ent, int *bad)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) ent[i] = make_int2(cols[i], __float_as_int(vals[i]));
+    if (i >= n) return;
+    int32_t c = cols[i];
+    if ((uint32_t)c >= (uint32_t)n_cols) {
+        *bad = 1;
+        c = 0;
+    }
+    ent[i] = make_int2(c, __float_as_int((float)vals[i]));
 }
 
 /* per entry: its row (expanded indptr) and its column as a sort key; one warp per row */

