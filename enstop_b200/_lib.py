@@ -176,8 +176,8 @@ class Context:
         self.k = 0
         if os.environ.get("ENSTOP_B200_CHUNK"):     # work-item length experiments
             self.set_option("chunk", int(os.environ["ENSTOP_B200_CHUNK"]))
-        if os.environ.get("ENSTOP_B200_VARIANT"):   # kernel-variant experiments
-            self.set_option("variant", int(os.environ["ENSTOP_B200_VARIANT"]))
+        if os.environ.get("ENSTOP_B200_TEXTURE"):   # 0: gather with LDG instead of the texture pipe
+            self.set_option("texture", int(os.environ["ENSTOP_B200_TEXTURE"]))
 
     def close(self):
         if self._h:

@@ -108,15 +108,15 @@ __device__ __forceinline__ float group_sum(float v, int gbase, int j)
         return v;
     } else {
         float w = v, total = 0.f;
+        bool first = true;
 #pragma unroll
         for (int b = 0; (1 << b) <= G; ++b) {
             const int s = 1 << b;
             if (G & s) {
                 const int off = G & ~((s << 1) - 1); /* set bits above b */
-                if (off == 0)
-                    total += w;
-                else
-                    total += __shfl_sync(0xffffffffu, w, gbase + (j + off) % G);
+                const float t = (off == 0) ? w : __shfl_sync(0xffffffffu, w, gbase + (j + off) % G);
+                total = first ? t : total + t;
+                first = false;
             }
             if ((s << 1) <= G) w += __shfl_sync(0xffffffffu, w, gbase + (j + s) % G);
         }
@@ -252,6 +252,75 @@ __device__ __forceinline__ void finish_colsum(const PassArgs &a, float4 (&acc)[K
     if (threadIdx.x == 0) *a.ticket = 0u;
 }
 
+/* U consecutive entries of every group's item: gather the factor rows, E-step, M-step sums.
+ * TAIL: entries at or past the item's end (read from following rows or the padding) count
+ * as value 0. */
+template <int G, int KV, int U, int MODE, bool TEX, bool TAIL>
+__device__ __forceinline__ void pass_block(const PassArgs &a, const int2 (&e)[U], int base, int len,
+                                           const char *gat_base, const uint32_t (&lane_off)[KV],
+                                           uint32_t stride_bytes, const float4 (&own)[KV],
+                                           float4 (&acc)[KV], double &ll_acc, float rw,
+                                           float thresh, int j, int gbase, bool lane_on)
+{
+    float4 g[U][KV];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if constexpr (TEX) {
+            const int t0 = e[u].x * (int)(stride_bytes >> 4);
+#pragma unroll
+            for (int q = 0; q < KV; ++q)
+                g[u][q] = tex1Dfetch<float4>(a.gat_tex, t0 + (int)(lane_off[q] >> 4));
+        } else if constexpr (KV == 1) { /* lane offset is folded into gat_base */
+            g[u][0] = ldg_f4_bytes(gat_base + (uint64_t)(uint32_t)e[u].x * stride_bytes);
+        } else {
+            const char *row = gat_base + (uint64_t)(uint32_t)e[u].x * stride_bytes;
+#pragma unroll
+            for (int q = 0; q < KV; ++q) g[u][q] = ldg_f4_bytes(row + lane_off[q]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        float x = __int_as_float(e[u].y);
+        if constexpr (TAIL) x = (base + u < len) ? x : 0.f;
+        float part;
+#pragma unroll
+        for (int q = 0; q < KV; ++q) {
+            float4 v;
+            v.x = g[u][q].x * own[q].x;
+            v.y = g[u][q].y * own[q].y;
+            v.z = g[u][q].z * own[q].z;
+            v.w = g[u][q].w * own[q].w;
+            if constexpr (MODE != MODE_LOGLIK) { /* plsa.py:98-102 */
+                v.x = v.x > thresh ? v.x : 0.f;
+                v.y = v.y > thresh ? v.y : 0.f;
+                v.z = v.z > thresh ? v.z : 0.f;
+                v.w = v.w > thresh ? v.w : 0.f;
+            }
+            g[u][q] = v;
+            const float s4 = (v.x + v.y) + (v.z + v.w);
+            part = (q == 0) ? s4 : part + s4;
+        }
+        const float norm = group_sum<G>(part, gbase, j);
+        if constexpr (MODE == MODE_LOGLIK) {
+            /* plsa.py:383-384; one lane per entry contributes, x == 0 marks a non-entry */
+            if (j == 0 && lane_on && x != 0.f) ll_acc += (double)(x * __logf(norm) * rw);
+        } else {
+            /* plsa.py:104: posterior = v / norm if norm > 0.  Products that survive the
+             * threshold are normal floats (the host passes thresh >= FLT_MIN), so norm is 0
+             * or normal; norm == 0 gives x * inf (or NaN), clamped to a finite c that
+             * multiplies v == 0. */
+            const float c = fminf(x * rcp_fast(norm), 3.0e38f);
+#pragma unroll
+            for (int q = 0; q < KV; ++q) {
+                acc[q].x = fmaf(c, g[u][q].x, acc[q].x);
+                acc[q].y = fmaf(c, g[u][q].y, acc[q].y);
+                acc[q].z = fmaf(c, g[u][q].z, acc[q].z);
+                acc[q].w = fmaf(c, g[u][q].w, acc[q].w);
+            }
+        }
+    }
+}
+
 template <int G, int KV, int MODE, bool TEX>
 __global__ void __launch_bounds__(256, (KV == 1) ? 4 : (KV == 2) ? 2 : 1)
     row_pass_kernel(const PassArgs a)
@@ -308,8 +377,11 @@ __global__ void __launch_bounds__(256, (KV == 1) ? 4 : (KV == 2) ? 2 : 1)
                                       (KV == 1 ? lane_off[0] : 0u));
     double ll_acc = 0.0;
 
-    /* entries one iteration ahead (one broadcast 8-byte load per group per entry); reads
-     * past an item's end land in following rows or in the array's padding and count as 0 */
+    /* Entries are fetched one block ahead (one broadcast 8-byte load per group per entry);
+     * reads past an item's end land in following rows or in the array's padding and count
+     * as value 0.  (Measured alternatives that were slower on B200: alternating entry sets
+     * without the register rotation, an unpredicated main loop, two-deep software pipelining
+     * of the gathers, L1 prefetch of the next rows — profiles/r1_kernel_experiments.md.) */
     int2 e[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) e[u] = __ldg(ent + u);
@@ -317,62 +389,8 @@ __global__ void __launch_bounds__(256, (KV == 1) ? 4 : (KV == 2) ? 2 : 1)
         int2 en[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) en[u] = __ldg(ent + base + U + u);
-        float4 g[U][KV];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if constexpr (TEX) {
-                const int t0 = e[u].x * (int)(stride_bytes >> 4);
-#pragma unroll
-                for (int q = 0; q < KV; ++q)
-                    g[u][q] = tex1Dfetch<float4>(a.gat_tex, t0 + (int)(lane_off[q] >> 4));
-            } else if constexpr (KV == 1) { /* lane offset is folded into gat_base */
-                g[u][0] = ldg_f4_bytes(gat_base + (uint64_t)(uint32_t)e[u].x * stride_bytes);
-            } else {
-                const char *row = gat_base + (uint64_t)(uint32_t)e[u].x * stride_bytes;
-#pragma unroll
-                for (int q = 0; q < KV; ++q) g[u][q] = ldg_f4_bytes(row + lane_off[q]);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const float x = (base + u < len) ? __int_as_float(e[u].y) : 0.f;
-            float part;
-#pragma unroll
-            for (int q = 0; q < KV; ++q) {
-                float4 v;
-                v.x = g[u][q].x * own[q].x;
-                v.y = g[u][q].y * own[q].y;
-                v.z = g[u][q].z * own[q].z;
-                v.w = g[u][q].w * own[q].w;
-                if constexpr (MODE != MODE_LOGLIK) { /* plsa.py:98-102 */
-                    v.x = v.x > thresh ? v.x : 0.f;
-                    v.y = v.y > thresh ? v.y : 0.f;
-                    v.z = v.z > thresh ? v.z : 0.f;
-                    v.w = v.w > thresh ? v.w : 0.f;
-                }
-                g[u][q] = v;
-                const float s4 = (v.x + v.y) + (v.z + v.w);
-                part = (q == 0) ? s4 : part + s4;
-            }
-            const float norm = group_sum<G>(part, gbase, j);
-            if constexpr (MODE == MODE_LOGLIK) {
-                /* plsa.py:383-384; one lane per entry contributes, x == 0 marks a non-entry */
-                if (j == 0 && lane_on && x != 0.f) ll_acc += (double)(x * __logf(norm) * rw);
-            } else {
-                /* plsa.py:104: posterior = v / norm if norm > 0.  Products that survive the
-                 * threshold are normal floats (the host passes thresh >= FLT_MIN), so norm
-                 * is 0 or normal; norm == 0 gives x * inf (or NaN), clamped to a finite c
-                 * that multiplies v == 0. */
-                const float c = fminf(x * rcp_fast(norm), 3.0e38f);
-#pragma unroll
-                for (int q = 0; q < KV; ++q) {
-                    acc[q].x = fmaf(c, g[u][q].x, acc[q].x);
-                    acc[q].y = fmaf(c, g[u][q].y, acc[q].y);
-                    acc[q].z = fmaf(c, g[u][q].z, acc[q].z);
-                    acc[q].w = fmaf(c, g[u][q].w, acc[q].w);
-                }
-            }
-        }
+        pass_block<G, KV, U, MODE, TEX, true>(a, e, base, len, gat_base, lane_off, stride_bytes,
+                                              own, acc, ll_acc, rw, thresh, j, gbase, lane_on);
 #pragma unroll
         for (int u = 0; u < U; ++u) e[u] = en[u];
     }

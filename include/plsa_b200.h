@@ -107,9 +107,9 @@ int plsa_last_em_ms(const plsa_ctx *ctx, float *ms);
 /* With profiling on, every kernel launch inside plsa_em is bracketed by CUDA events on
  * the context's stream.  Slots: see PLSA_PROF_* . */
 #define PLSA_PROF_DOC_PASS 0   /* E-step + P(z|d) M-step over the doc-major copy        */
-#define PLSA_PROF_WORD_PASS 1  /* E-step + P(w|z) M-step over the term-major copy      */
-#define PLSA_PROF_FIXUP 2      /* ordered sums of split rows                           */
-#define PLSA_PROF_NORMALIZE 3  /* column sums + P(w|z) renormalisation                 */
+#define PLSA_PROF_WORD_PASS 1  /* E-step + P(w|z) M-step + column sums, term-major copy */
+#define PLSA_PROF_FIXUP 2      /* ordered sums of split rows (both factors)            */
+#define PLSA_PROF_NORMALIZE 3  /* unused since the column sums moved into the word pass */
 #define PLSA_PROF_LOGLIK 4     /* log-likelihood pass                                  */
 #define PLSA_PROF_SLOTS 5
 int plsa_set_profiling(plsa_ctx *ctx, int32_t on);
@@ -117,7 +117,8 @@ int plsa_get_profile(plsa_ctx *ctx, double *ms /*[PLSA_PROF_SLOTS]*/,
                      int64_t *launches /*[PLSA_PROF_SLOTS]*/);
 /* Kernel launches issued by this context since creation (bench "gpu_launches"). */
 int plsa_launch_count(const plsa_ctx *ctx, int64_t *launches);
-/* Tunables: "chunk" (max stored entries per work item; longer rows are split). */
+/* Tunables: "chunk" (max stored entries per work item, 32..4096; longer rows are split),
+ * "texture" (1: gather factor rows through the texture pipe when they fit, 0: plain loads). */
 int plsa_set_option(plsa_ctx *ctx, const char *name, int64_t value);
 
 /* ---- one-shot drop-ins for the reference's raw-array seam --------------------------------- */
