@@ -96,6 +96,9 @@ struct plsa_ctx {
     ItemSet doc_items, term_items;
     int64_t chunk = 256;
     bool use_texture = true; /* gather through the texture pipe when the factor fits */
+    bool fuse_ll = true;     /* take the periodic log-likelihood from the next doc pass */
+    double *mail = nullptr;  /* pinned host mailbox {ll, flag} */
+    cudaEvent_t ev_ll = nullptr;
     cudaTextureObject_t texA[2] = {0, 0}, texB[2] = {0, 0};
     size_t tex_max_texels = 0;
 
@@ -204,6 +207,7 @@ template <int G, int KV> static pass_fn pick_mode(int mode, bool tex)
     switch (mode) {
     case MODE_DOC: return tex ? row_pass_kernel<G, KV, MODE_DOC, true> : row_pass_kernel<G, KV, MODE_DOC, false>;
     case MODE_TERM: return tex ? row_pass_kernel<G, KV, MODE_TERM, true> : row_pass_kernel<G, KV, MODE_TERM, false>;
+    case MODE_DOC_LL: return tex ? row_pass_kernel<G, KV, MODE_DOC_LL, true> : row_pass_kernel<G, KV, MODE_DOC_LL, false>;
     default: return tex ? row_pass_kernel<G, KV, MODE_LOGLIK, true> : row_pass_kernel<G, KV, MODE_LOGLIK, false>;
     }
 }
@@ -458,7 +462,8 @@ API int plsa_ctx_create(int device, plsa_ctx **out)
     if ((e = cudaSetDevice(device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess ||
-        (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) {
+        (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->ev_ll, cudaEventDisableTiming)) != cudaSuccess) {
         g_err = std::string("context setup: ") + cudaGetErrorString(e);
         delete ctx;
         return PLSA_ECUDA;
@@ -493,6 +498,8 @@ API int plsa_ctx_destroy(plsa_ctx *ctx)
         if (ctx->texA[i]) cudaDestroyTextureObject(ctx->texA[i]);
         if (ctx->texB[i]) cudaDestroyTextureObject(ctx->texB[i]);
     }
+    if (ctx->mail) cudaFreeHost(ctx->mail);
+    if (ctx->ev_ll) cudaEventDestroy(ctx->ev_ll);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -929,10 +936,39 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
     /* plsa.py:913 — the refit loop's early stop is guarded by LL > 0, which a
      * log-likelihood never satisfies: LL is evaluated there only when a trace is asked for */
     const bool want_ll = !refit || ll_trace != nullptr;
+    /* Fused evaluation: the log-likelihood "after iteration t" is the log-likelihood of the
+     * factors iteration t+1 reads, so the doc pass of iteration t+1 returns it for free
+     * (MODE_DOC_LL) instead of a separate gather pass.  Iteration t+1 is then launched
+     * speculatively; if the test says stop, its output (in the ping-pong buffers) is simply
+     * not adopted — the returned model is exactly the reference's (plsa.py:630-638). */
+    const bool fuse = want_ll && !refit && ctx->fuse_ll && e_step_thresh <= PLSA_FUSED_LL_MAX_THRESH;
+    if (fuse) {
+        if (!ctx->mail) CK(cudaHostAlloc((void **)&ctx->mail, 16, cudaHostAllocDefault));
+        CK(ctx->flag.ensure(4));
+        CK(ctx->ll_part.ensure((size_t)std::max<int64_t>(pass_grid(ctx->doc_items.n_items, kp), 1) * 8));
+    }
     int32_t nl = 0;
     double prev = 0.0;
+    bool stopped = false;
+    /* plsa.py:632-637: returns true when the loop must stop */
+    auto judge = [&](double cur) {
+        if (ll_trace && nl < ll_cap) ll_trace[nl] = cur;
+        nl++;
+        if (!refit) {
+            /* the reference holds the log-likelihood in float32 (plsa.py:322) */
+            const float curf = (float)cur, prevf = (float)prev;
+            const float change = fabsf(curf - prevf);
+            if (change == 0.f || (double)(change / fabsf(curf)) < tolerance) return true;
+            prev = cur;
+        } else if (cur > 0.0) { /* plsa.py:913 */
+            const float change = fabsf((float)cur - (float)prev);
+            if ((double)(change / fabsf((float)cur)) < tolerance) return true;
+            prev = cur;
+        }
+        return false;
+    };
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (want_ll) {
+    if (want_ll && (!fuse || n_iter == 0)) {
         if ((rc = run_loglik(ctx, &prev))) return rc; /* plsa.py:591 */
         if (ll_trace && nl < ll_cap) ll_trace[nl] = prev;
         nl++;
@@ -940,6 +976,7 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
     int32_t done = 0;
     for (int32_t i = 0; i < n_iter; ++i) {
         const int nA = ctx->curA ^ 1, nB = ctx->curB ^ 1;
+        const bool fused_now = fuse && (i == 0 || (i - 1) % n_iter_per_test == 0);
         {   /* E-step + M-step of P(z|d): plsa.py:91-105, :189-194 (P(z|d) part), :199-202 */
             ProfScope ps(ctx, PLSA_PROF_DOC_PASS);
             PassArgs a{};
@@ -956,7 +993,20 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
             a.stride_gat = ctx->strideB;
             a.kp = kp;
             a.thresh = e_step_thresh;
-            if ((rc = launch_pass(ctx, MODE_DOC, a))) return rc;
+            if (fused_now) {
+                a.row_weight = ctx->sw.as<float>();
+                a.cta_partial = ctx->ll_part.as<double>();
+                a.ticket = ctx->tickets.as<unsigned int>();
+                a.ll_out = ctx->ll_out.as<double>();
+                a.flag = ctx->flag.as<int>();
+                CK(cudaMemsetAsync(ctx->flag.p, 0, 4, ctx->stream));
+            }
+            if ((rc = launch_pass(ctx, fused_now ? MODE_DOC_LL : MODE_DOC, a))) return rc;
+            if (fused_now) {
+                CK(cudaMemcpyAsync(&ctx->mail[0], ctx->ll_out.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaMemcpyAsync(&ctx->mail[1], ctx->flag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaEventRecord(ctx->ev_ll, ctx->stream));
+            }
         }
         if (!refit) {
             {   /* E-step + M-step of P(w|z): plsa.py:91-105, :189-193 (P(w|z) part) */
@@ -992,26 +1042,35 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
         /* split rows of both factors: ordered sums of their chunk partials */
         if ((rc = run_fixup(ctx, ctx->A[nA].as<float>(), refit ? nullptr : ctx->B[nB].as<float>())))
             return rc;
+        if (fused_now) {
+            CK(cudaEventSynchronize(ctx->ev_ll));
+            double v;
+            int bad;
+            memcpy(&v, &ctx->mail[0], 8);
+            memcpy(&bad, &ctx->mail[1], 4);
+            if (bad && (rc = run_loglik(ctx, &v))) return rc; /* exact pass on the same factors */
+            if (i == 0) { /* plsa.py:591, the value before the loop */
+                prev = v;
+                if (ll_trace && nl < ll_cap) ll_trace[nl] = v;
+                nl++;
+            } else if (judge(v)) { /* the test of iteration i-1: iteration i is not adopted */
+                stopped = true;
+                break;
+            }
+        }
         if (!refit) ctx->curB = nB;
         ctx->curA = nA;
         done = i + 1;
-        if (want_ll && i % n_iter_per_test == 0) { /* plsa.py:630-638 / :909-918 */
+        if (want_ll && !fuse && i % n_iter_per_test == 0) { /* plsa.py:630-638 / :909-918 */
             double cur = 0.0;
             if ((rc = run_loglik(ctx, &cur))) return rc;
-            if (ll_trace && nl < ll_cap) ll_trace[nl] = cur;
-            nl++;
-            if (!refit) {
-                /* the reference holds the log-likelihood in float32 (plsa.py:322) */
-                const float curf = (float)cur, prevf = (float)prev;
-                const float change = fabsf(curf - prevf);
-                if (change == 0.f || (double)(change / fabsf(curf)) < tolerance) break;
-                prev = cur;
-            } else if (cur > 0.0) {
-                const float change = fabsf((float)cur - (float)prev);
-                if ((double)(change / fabsf((float)cur)) < tolerance) break;
-                prev = cur;
-            }
+            if (judge(cur)) break;
         }
+    }
+    if (fuse && !stopped && n_iter > 0 && (n_iter - 1) % n_iter_per_test == 0) {
+        double cur = 0.0; /* the test after the last iteration: no later pass to ride on */
+        if ((rc = run_loglik(ctx, &cur))) return rc;
+        judge(cur);
     }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1068,6 +1127,10 @@ API int plsa_set_option(plsa_ctx *ctx, const char *name, int64_t value)
         ctx->doc_items.ready = false;
         ctx->term_items.ready = false;
         ctx->t_ready = false; /* term items are rebuilt with the term-major copy */
+        return PLSA_OK;
+    }
+    if (!strcmp(name, "fuse_ll")) {
+        ctx->fuse_ll = value != 0;
         return PLSA_OK;
     }
     if (!strcmp(name, "texture")) {

@@ -47,7 +47,15 @@ struct Item {          /* one unit of group work: a row, or a chunk of a long ro
     int32_t pad;
 };
 
-enum { MODE_DOC = 0, MODE_TERM = 1, MODE_LOGLIK = 2 };
+enum { MODE_DOC = 0, MODE_TERM = 1, MODE_LOGLIK = 2,
+       MODE_DOC_LL = 3 /* doc pass that also returns the log-likelihood of the factors it reads */ };
+
+/* MODE_DOC_LL takes log(sum of the THRESHOLDED products).  That equals the reference's
+ * log(sum of all products) (plsa.py:381-384) to float precision as long as the dropped
+ * products (each <= thresh <= 1e-30) are negligible next to the sum; a sum below this bound
+ * raises PassArgs::flag and the host recomputes with the exact MODE_LOGLIK pass. */
+#define PLSA_FUSED_LL_MIN_NORM 1e-20f
+#define PLSA_FUSED_LL_MAX_THRESH 1e-30f
 
 struct PassArgs {
     const Item *items;
@@ -59,10 +67,11 @@ struct PassArgs {
     const float *own_scale;  /* [kp] folded into the owned row (1/column-sum of P(w|z)) */
     float *own_new;          /* [rows, stride_own]                                      */
     float *partial;          /* [slots, kp] raw sums of split rows                      */
-    const float *row_weight; /* MODE_LOGLIK: sample_weight[d]                           */
+    const float *row_weight; /* MODE_LOGLIK / MODE_DOC_LL: sample_weight[d]                */
     double *cta_partial;     /* MODE_LOGLIK: [grid]; MODE_TERM: [grid, kp] per-CTA sums  */
     unsigned int *ticket;    /* zeroed counters (1 + grid/32): last-arrival reductions       */
-    double *ll_out;          /* MODE_LOGLIK: the log-likelihood                          */
+    double *ll_out;          /* MODE_LOGLIK / MODE_DOC_LL: the log-likelihood              */
+    int *flag;               /* MODE_DOC_LL: set when the fused value cannot be trusted    */
     float *scale_out;        /* MODE_TERM: [kp] 1 / column sum of the new P(w|z)         */
     double *colnorm_out;     /* MODE_TERM: [kp] the column sums                          */
     cudaTextureObject_t gat_tex; /* gat_old as a linear float4 texture (TEX kernels)     */
@@ -305,6 +314,12 @@ __device__ __forceinline__ void pass_block(const PassArgs &a, const int2 (&e)[U]
             /* plsa.py:383-384; one lane per entry contributes, x == 0 marks a non-entry */
             if (j == 0 && lane_on && x != 0.f) ll_acc += (double)(x * __logf(norm) * rw);
         } else {
+            if constexpr (MODE == MODE_DOC_LL) {
+                if (j == 0 && lane_on && x != 0.f) {
+                    ll_acc += (double)(x * __logf(norm) * rw);
+                    if (norm < PLSA_FUSED_LL_MIN_NORM) *a.flag = 1;
+                }
+            }
             /* plsa.py:104: posterior = v / norm if norm > 0.  Products that survive the
              * threshold are normal floats (the host passes thresh >= FLT_MIN), so norm is 0
              * or normal; norm == 0 gives x * inf (or NaN), clamped to a finite c that
@@ -367,7 +382,7 @@ __global__ void __launch_bounds__(256, (KV == 1) ? 4 : (KV == 2) ? 2 : 1)
         }
     }
     float rw = 1.f;
-    if constexpr (MODE == MODE_LOGLIK) rw = has ? a.row_weight[it.row] : 0.f;
+    if constexpr (MODE == MODE_LOGLIK || MODE == MODE_DOC_LL) rw = has ? a.row_weight[it.row] : 0.f;
 
     const int2 *ent = a.ent + it.start;
     const int len = it.len;
@@ -399,7 +414,7 @@ __global__ void __launch_bounds__(256, (KV == 1) ? 4 : (KV == 2) ? 2 : 1)
         finish_loglik(a, ll_acc);
     } else {
         float inv = 1.f;
-        if constexpr (MODE == MODE_DOC) { /* plsa.py:199-202: divide by the row's total if > 0 */
+        if constexpr (MODE == MODE_DOC || MODE == MODE_DOC_LL) { /* plsa.py:199-202 */
             float part = 0.f;
 #pragma unroll
             for (int q = 0; q < KV; ++q) part += (acc[q].x + acc[q].y) + (acc[q].z + acc[q].w);
@@ -418,6 +433,7 @@ __global__ void __launch_bounds__(256, (KV == 1) ? 4 : (KV == 2) ? 2 : 1)
             }
         }
         if constexpr (MODE == MODE_TERM) finish_colsum<G, KV>(a, acc, lane, warp, j, lane_on);
+        if constexpr (MODE == MODE_DOC_LL) finish_loglik(a, ll_acc);
     }
 }
 

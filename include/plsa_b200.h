@@ -118,7 +118,8 @@ int plsa_get_profile(plsa_ctx *ctx, double *ms /*[PLSA_PROF_SLOTS]*/,
 /* Kernel launches issued by this context since creation (bench "gpu_launches"). */
 int plsa_launch_count(const plsa_ctx *ctx, int64_t *launches);
 /* Tunables: "chunk" (max stored entries per work item, 32..4096; longer rows are split),
- * "texture" (1: gather factor rows through the texture pipe when they fit, 0: plain loads). */
+ * "texture" (1: gather factor rows through the texture pipe when they fit, 0: plain loads),
+ * "fuse_ll" (1: the periodic log-likelihood rides on the next doc pass, 0: separate pass). */
 int plsa_set_option(plsa_ctx *ctx, const char *name, int64_t value);
 
 /* ---- one-shot drop-ins for the reference's raw-array seam --------------------------------- */

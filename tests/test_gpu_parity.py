@@ -182,6 +182,33 @@ def test_split_rows(chunk, golden_c1_planted):
     assert abs(ll - oracle.log_likelihood(X, ew, ez)) / abs(ll) < 1e-6
 
 
+@pytest.mark.parametrize("n_iter,per_test,tol", [(50, 10, 0.001), (21, 5, 0.0), (1, 10, 0.0),
+                                                 (12, 1, 1e-4), (10, 3, 0.0)])
+def test_fused_loglik_is_the_separate_pass(golden_c1_planted, n_iter, per_test, tol):
+    """The periodic log-likelihood taken from the next doc pass (speculative iteration,
+    dropped on stop) gives the same model, iteration count and trace as the reference's
+    order of operations (separate log-likelihood pass after the M-step, plsa.py:630-638)."""
+    g, X = golden_c1_planted
+    sw = np.ones(X.shape[0], dtype=np.float32)
+    out = []
+    for fuse in (1, 0):
+        with _lib.Context(0) as ctx:
+            ctx.set_option("fuse_ll", fuse)
+            ctx.upload_csr(X)
+            pzd, pwz, info = plsa.plsa_fit(X, 10, sw, init=(g["pzd0"], g["pwz0"]), n_iter=n_iter,
+                                           n_iter_per_test=per_test, tolerance=tol, context=ctx,
+                                           return_info=True)
+        out.append((pzd, pwz, info))
+    a, b = out
+    assert a[2]["n_iter"] == b[2]["n_iter"]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert len(a[2]["ll_trace"]) == len(b[2]["ll_trace"])
+    assert np.allclose(a[2]["ll_trace"], b[2]["ll_trace"], rtol=1e-9)
+    _, _, oinfo = oracle.plsa_fit(X, 10, sw, init=(g["pzd0"], g["pwz0"]), n_iter=n_iter,
+                                  n_iter_per_test=per_test, tolerance=tol, return_info=True)
+    assert a[2]["n_iter"] == oinfo["n_iter"] and len(a[2]["ll_trace"]) == len(oinfo["ll_trace"])
+
+
 def test_bit_repeatable(golden_c1_zipf):
     """The reference CPU path is bit-repeatable run to run; so is this one
     (no atomics on the data path, fixed summation orders)."""
