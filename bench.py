@@ -163,6 +163,17 @@ class Plumbing:
             self.dist.destroy_process_group()
 
 
+def measured_traffic(config):
+    """DRAM bytes per launch of the doc pass from the committed `ncu --set full` capture of
+    this same command (profiles/traffic.json, written by scripts/ncu_summary.py --traffic)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(config)
+        return None if t is None else t["doc_pass"]["dram_bytes_read"] + t["doc_pass"]["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 def algorithmic_bytes(n, m, nnz, k):
     """per EM iteration 8*nnz + 4*(n+1) + 8*k*(n+m); E-step reads
     8*nnz + 4*(n+1) + 4*k*(n+m)."""
@@ -334,7 +345,7 @@ def main():
     roofline = {
         "bound": "hbm", "kernel": "row_pass_kernel<doc> (E-step + P(z|d) M-step)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "peak_source": peak_src, "traffic": None,
+        "peak_source": peak_src, "traffic": measured_traffic(args.config) if world == 1 else None,
         "algorithmic_bytes_per_launch": b_e, "avg_launch_ms": doc_ms,
         "frac_of_spec_8TBs": achieved / SPEC_HBM_GBS,
         "word_pass": {"avg_launch_ms": word_ms,

@@ -56,7 +56,7 @@ SIGNATURES = {
     "plsa_topics_device": (ctypes.c_int, [_ctx, ctypes.POINTER(ctypes.c_void_p), _i64p]),
     "plsa_em": (ctypes.c_int, [_ctx, _i32, _i32, _f64, _f32, _i32, _i32, _i32p, _f64p, _i32,
                                _i32p]),
-    "plsa_prepare": (ctypes.c_int, [_ctx, _i32]),
+    "plsa_prepare": (ctypes.c_int, [_ctx, _i32, _i32]),
     "plsa_log_likelihood": (ctypes.c_int, [_ctx, _f64p]),
     "plsa_last_em_ms": (ctypes.c_int, [_ctx, _f32p]),
     "plsa_set_profiling": (ctypes.c_int, [_ctx, _i32]),
@@ -215,10 +215,11 @@ class Context:
                                             self._DTYPES[data.dtype], n, m, data.shape[0]),
               self._h)
 
-    def prepare(self, refit=False):
-        """Build work items (and the term-major copy for a full fit) now rather than inside
-        the first em() — the host overlaps its seeded initialisation with this."""
-        check(self._L.plsa_prepare(self._h, int(bool(refit))), self._h)
+    def prepare(self, k, refit=False):
+        """Build work items sized for k topics (and the term-major copy for a full fit) now
+        rather than inside the first em() — the host overlaps its seeded initialisation
+        with this."""
+        check(self._L.plsa_prepare(self._h, int(bool(refit)), int(k)), self._h)
 
     def upload_coo(self, rows, cols, vals, n, m):
         rows, cols, vals = _as(rows, np.int32), _as(cols, np.int32), _as(vals, np.float32)

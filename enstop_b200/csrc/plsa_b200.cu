@@ -73,6 +73,7 @@ struct ItemSet {
     int64_t n_items = 0;
     int32_t n_split = 0, n_heavy = 0, n_slots = 0;
     bool ready = false;
+    int64_t chunk = 0;
 };
 
 } // namespace
@@ -94,7 +95,9 @@ struct plsa_ctx {
     bool t_ready = false, t_weighted_ready = false;
 
     ItemSet doc_items, term_items;
-    int64_t chunk = 256;
+    int64_t chunk_user = 0;  /* option "chunk": 0 = chosen per corpus size and k */
+    int64_t chunk_built = 0; /* work-item length the item sets were built with */
+    int32_t k_hint = 0;      /* plsa_prepare: k the items should be sized for */
     bool use_texture = true; /* gather through the texture pipe when the factor fits */
     bool fuse_ll = true;     /* take the periodic log-likelihood from the next doc pass */
     double *mail = nullptr;  /* pinned host mailbox {ll, flag} */
@@ -260,10 +263,24 @@ static int launch_pass(plsa_ctx *ctx, int mode, const PassArgs &a)
  * partial sums are added in order by fixup_kernel.  Items are ordered longest first
  * (counting sort) so that the 8 warps of a CTA carry rows of similar length and the
  * hardware CTA scheduler sees the heavy work first. */
-static int build_items(plsa_ctx *ctx, const std::vector<int32_t> &indptr, int64_t rows,
-                       ItemSet &out)
+/* Work-item length.  A group walks its item serially (U entries per ~0.45 us iteration), so
+ * the item length bounds the pass from below; short items cost a header chain and a partial
+ * sum each.  Measured on B200 (profiles/r1_kernel_experiments.md): 256 is best at 10 M
+ * entries with 6 items per warp, 64 or less at 0.2 M entries, 2048 when a warp carries a
+ * single item (k > 64). */
+static int64_t choose_chunk(const plsa_ctx *ctx, int kp)
 {
-    const int64_t chunk = ctx->chunk;
+    if (ctx->chunk_user > 0) return ctx->chunk_user;
+    const int64_t nnz = ctx->cur().nnz;
+    const bool one_item_per_warp = kp > 0 && 32 / pass_group_lanes(kp) < 3;
+    const int64_t cap = one_item_per_warp ? 2048 : 256;
+    const int64_t want = nnz / (one_item_per_warp ? 4096 : 32768);
+    return std::max<int64_t>(32, std::min(cap, (want + 31) / 32 * 32));
+}
+
+static int build_items(plsa_ctx *ctx, const std::vector<int32_t> &indptr, int64_t rows,
+                       ItemSet &out, int64_t chunk)
+{
     std::vector<Item> items;
     items.reserve((size_t)rows + 1024);
     /* split rows, those with more than 32 chunks first (fixup_kernel gives them a CTA) */
@@ -325,6 +342,7 @@ static int build_items(plsa_ctx *ctx, const std::vector<int32_t> &indptr, int64_
                        cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream)); /* host vectors die here */
     out.ready = true;
+    out.chunk = chunk;
     return PLSA_OK;
 }
 
@@ -390,8 +408,7 @@ static int build_term_major(plsa_ctx *ctx)
     }
     cleanup();
 #undef CKT
-    int rc = build_items(ctx, ctx->h_tindptr, m, ctx->term_items);
-    if (rc) return rc;
+    ctx->term_items.ready = false;
     ctx->t_ready = true;
     ctx->t_weighted_ready = false;
     return PLSA_OK;
@@ -813,16 +830,27 @@ API int plsa_get_factors(plsa_ctx *ctx, float *p_z_given_d, float *p_w_given_z)
 }
 
 /* ---- EM ------------------------------------------------------------------------------------------ */
-static int ensure_doc_items(plsa_ctx *ctx)
+/* work items of the doc pass (and of the term pass for a full fit), sized for kp */
+static int ensure_items(plsa_ctx *ctx, bool refit, int kp)
 {
-    if (ctx->doc_items.ready) return PLSA_OK;
-    return build_items(ctx, ctx->cur().h_indptr, ctx->cur().n, ctx->doc_items);
+    const int64_t chunk = choose_chunk(ctx, kp);
+    int rc;
+    if (!ctx->doc_items.ready || ctx->doc_items.chunk != chunk)
+        if ((rc = build_items(ctx, ctx->cur().h_indptr, ctx->cur().n, ctx->doc_items, chunk)))
+            return rc;
+    if (!refit) {
+        if (!ctx->t_ready && (rc = build_term_major(ctx))) return rc;
+        if (!ctx->term_items.ready || ctx->term_items.chunk != chunk)
+            if ((rc = build_items(ctx, ctx->h_tindptr, ctx->cur().m, ctx->term_items, chunk)))
+                return rc;
+    }
+    return PLSA_OK;
 }
 
 static int run_loglik(plsa_ctx *ctx, double *out)
 {
     const Corpus &c = ctx->cur();
-    int rc = ensure_doc_items(ctx);
+    int rc = ensure_items(ctx, true, ctx->kp);
     if (rc) return rc;
     if (!ctx->have_sw && (rc = plsa_set_sample_weight(ctx, nullptr))) return rc;
     const int64_t grid = pass_grid(ctx->doc_items.n_items, ctx->kp);
@@ -857,14 +885,12 @@ static int run_loglik(plsa_ctx *ctx, double *out)
 
 /* Build everything a later plsa_em needs that depends only on the corpus (work items, and
  * for a full fit the term-major copy), so that it can overlap host-side initialisation. */
-API int plsa_prepare(plsa_ctx *ctx, int32_t refit)
+API int plsa_prepare(plsa_ctx *ctx, int32_t refit, int32_t k)
 {
     CHECK_CTX(ctx);
     if (ctx->cur().h_indptr.empty()) return ctx->fail(PLSA_EINVAL, "prepare: no corpus uploaded");
-    int rc = ensure_doc_items(ctx);
-    if (rc) return rc;
-    if (!refit && !ctx->t_ready && (rc = build_term_major(ctx))) return rc;
-    return PLSA_OK;
+    if (k < 1 || k > PLSA_MAX_K) return ctx->fail(PLSA_EINVAL, "prepare: k out of range");
+    return ensure_items(ctx, refit != 0, (k + 3) / 4 * 4);
 }
 
 API int plsa_log_likelihood(plsa_ctx *ctx, double *ll)
@@ -920,12 +946,9 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
         return ctx->fail(PLSA_EINVAL, "em: n_iter < 0 or n_iter_per_test < 1");
     Corpus &c = ctx->cur();
     int rc;
-    if ((rc = ensure_doc_items(ctx))) return rc;
+    if ((rc = ensure_items(ctx, refit != 0, ctx->kp))) return rc;
     if (!ctx->have_sw && (rc = plsa_set_sample_weight(ctx, nullptr))) return rc;
-    if (!refit) {
-        if (!ctx->t_ready && (rc = build_term_major(ctx))) return rc;
-        if (use_sample_weights && (rc = ensure_weighted_vals(ctx))) return rc;
-    }
+    if (!refit && use_sample_weights && (rc = ensure_weighted_vals(ctx))) return rc;
     const int kp = ctx->kp;
     /* products at or below the threshold are dropped (plsa.py:98-102); subnormal products
      * are dropped as well so that a surviving posterior normaliser is never subnormal */
@@ -1121,12 +1144,9 @@ API int plsa_set_option(plsa_ctx *ctx, const char *name, int64_t value)
 {
     if (!ctx || !name) return PLSA_EINVAL;
     if (!strcmp(name, "chunk")) {
-        if (value < 32 || value > ENT_PAD - ENT_SLACK)
+        if (value != 0 && (value < 32 || value > ENT_PAD - ENT_SLACK))
             return ctx->fail(PLSA_EINVAL, "chunk out of range (32..4096)");
-        ctx->chunk = value;
-        ctx->doc_items.ready = false;
-        ctx->term_items.ready = false;
-        ctx->t_ready = false; /* term items are rebuilt with the term-major copy */
+        ctx->chunk_user = value; /* item sets are rebuilt on the next prepare / em */
         return PLSA_OK;
     }
     if (!strcmp(name, "fuse_ll")) {

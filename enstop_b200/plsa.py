@@ -92,21 +92,21 @@ class _Staging:
     """Uploads the corpus and builds its device-side structures on a helper thread while the
     caller draws the seeded initial factors on the host (ctypes releases the GIL)."""
 
-    def __init__(self, X, device, context, refit):
+    def __init__(self, X, k, device, context, refit):
         self.owned = context is None
         self.error = None
         self.thread = None
         if self.owned:
             self.ctx = _lib.acquire_context(default_device() if device is None else device)
-            self.thread = threading.Thread(target=self._run, args=(_as_csr(X), refit))
+            self.thread = threading.Thread(target=self._run, args=(_as_csr(X), k, refit))
             self.thread.start()
         else:
             self.ctx = context
 
-    def _run(self, X, refit):
+    def _run(self, X, k, refit):
         try:
             self.ctx.upload_csr(X)
-            self.ctx.prepare(refit)
+            self.ctx.prepare(k, refit)
         except BaseException as exc:  # re-raised by wait()
             self.error = exc
 
@@ -138,7 +138,7 @@ def plsa_fit(X, k, sample_weight, init="random", n_iter=100, n_iter_per_test=10,
     Drop-in for enstop.plsa.plsa_fit (plsa.py:643-730).  ``context`` (an
     ``enstop_b200._lib.Context`` whose resident corpus is X) skips the upload — used by the
     ensemble for its bootstrapped members."""
-    staging = _Staging(X, device, context, refit=False)
+    staging = _Staging(X, k, device, context, refit=False)
     try:
         rng = check_random_state(random_state)
         p_z_given_d, p_w_given_z = plsa_init(X, k, init=init, rng=rng)
@@ -169,10 +169,10 @@ def plsa_refit(X, topics, sample_weight, n_iter=50, n_iter_per_test=10, toleranc
     Drop-in for enstop.plsa.plsa_refit (plsa.py:923-997): fresh ``rng.rand(n, k)`` start,
     E-step + P(z|d)-only M-step; as in the reference the loop always runs ``n_iter``
     iterations (its early stop is guarded by ``LL > 0``, plsa.py:913)."""
-    staging = _Staging(X, device, context, refit=True)
+    topics = np.ascontiguousarray(topics, dtype=np.float32)
+    k = topics.shape[0]
+    staging = _Staging(X, k, device, context, refit=True)
     try:
-        topics = np.ascontiguousarray(topics, dtype=np.float32)
-        k = topics.shape[0]
         rng = check_random_state(random_state)
         p_z_given_d = rng.rand(X.shape[0], k)
         normalize(p_z_given_d, axis=1)

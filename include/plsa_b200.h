@@ -96,8 +96,9 @@ int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double toler
             float e_step_thresh, int32_t refit, int32_t use_sample_weights,
             int32_t *iters_run, double *ll_trace, int32_t ll_cap, int32_t *n_ll);
 /* Build what a later plsa_em needs from the corpus alone (work items; for a full fit also
- * the term-major copy) — lets the host overlap its RNG initialisation with it. */
-int plsa_prepare(plsa_ctx *ctx, int32_t refit);
+ * the term-major copy; items are sized for k topics) — lets the host overlap its RNG
+ * initialisation with it. */
+int plsa_prepare(plsa_ctx *ctx, int32_t refit, int32_t k);
 /* log_likelihood (plsa.py:329-386) of the resident model, float64 reduction. */
 int plsa_log_likelihood(plsa_ctx *ctx, double *ll);
 
@@ -117,7 +118,8 @@ int plsa_get_profile(plsa_ctx *ctx, double *ms /*[PLSA_PROF_SLOTS]*/,
                      int64_t *launches /*[PLSA_PROF_SLOTS]*/);
 /* Kernel launches issued by this context since creation (bench "gpu_launches"). */
 int plsa_launch_count(const plsa_ctx *ctx, int64_t *launches);
-/* Tunables: "chunk" (max stored entries per work item, 32..4096; longer rows are split),
+/* Tunables: "chunk" (max stored entries per work item, 32..4096, 0 = automatic; longer rows
+ * are split),
  * "texture" (1: gather factor rows through the texture pipe when they fit, 0: plain loads),
  * "fuse_ll" (1: the periodic log-likelihood rides on the next doc pass, 0: separate pass). */
 int plsa_set_option(plsa_ctx *ctx, const char *name, int64_t value);

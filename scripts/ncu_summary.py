@@ -33,7 +33,39 @@ KEYS = ['Kernel Name', 'launch__grid_size', 'launch__block_size', 'launch__regis
         'smsp__thread_inst_executed_per_inst_executed.ratio']
 
 
+def traffic(rep, config, out_json):
+    """--traffic REP CONFIG OUT: per-launch DRAM bytes of the doc / term / log-likelihood pass."""
+    import json
+    import os
+    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], stdout=subprocess.PIPE,
+                         stderr=subprocess.DEVNULL, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+
+    def val(r, key):
+        i = hdr.index(key)
+        v = float(r[i])
+        return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[units[i]]
+    names = {'0': 'doc_pass', '3': 'doc_pass', '1': 'term_pass', '2': 'loglik_pass'}
+    data = json.load(open(out_json)) if os.path.exists(out_json) else {}
+    entry = data.setdefault(config, {})
+    for r in rows[2:]:
+        kn = r[hdr.index('Kernel Name')]
+        if 'row_pass_kernel' not in kn:
+            continue
+        mode = kn.split('<')[1].split(',')[2].strip()
+        entry[names.get(mode, mode)] = {
+            'kernel': kn.strip(), 'dram_bytes_read': val(r, 'dram__bytes_read.sum'),
+            'dram_bytes_write': val(r, 'dram__bytes_write.sum'),
+            'duration_us_under_ncu': float(r[hdr.index('gpu__time_duration.sum')]),
+            'source': os.path.basename(rep)}
+    json.dump(data, open(out_json, 'w'), indent=1, sort_keys=True)
+    print(json.dumps(entry, indent=1))
+
+
 def main():
+    if sys.argv[1] == '--traffic':
+        return traffic(sys.argv[2], sys.argv[3], sys.argv[4])
     rep = sys.argv[1]
     raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], stdout=subprocess.PIPE,
                          stderr=subprocess.DEVNULL, text=True).stdout
