@@ -102,6 +102,9 @@ struct plsa_ctx {
     bool fuse_ll = true;     /* take the periodic log-likelihood from the next doc pass */
     double *mail = nullptr;  /* pinned host mailbox {ll, flag} */
     cudaEvent_t ev_ll = nullptr;
+    bool overlap = true;     /* doc pass and term pass of an iteration on two streams */
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_go = nullptr;
     cudaTextureObject_t texA[2] = {0, 0}, texB[2] = {0, 0};
     size_t tex_max_texels = 0;
 
@@ -171,18 +174,20 @@ struct ProfScope {
     plsa_ctx *ctx;
     int slot;
     cudaEvent_t a = nullptr, b = nullptr;
-    ProfScope(plsa_ctx *c, int s) : ctx(c), slot(s)
+    cudaStream_t st;
+    ProfScope(plsa_ctx *c, int s, cudaStream_t stream = nullptr)
+        : ctx(c), slot(s), st(stream ? stream : c->stream)
     {
         if (ctx->profiling) {
             a = get_event(ctx);
             b = get_event(ctx);
-            cudaEventRecord(a, ctx->stream);
+            cudaEventRecord(a, st);
         }
     }
     ~ProfScope()
     {
         if (ctx->profiling) {
-            cudaEventRecord(b, ctx->stream);
+            cudaEventRecord(b, st);
             ctx->prof_pending.push_back({slot, a, b});
         }
     }
@@ -248,11 +253,11 @@ static int64_t pass_grid(int64_t n_items, int kp)
     return cdiv(n_items, (int64_t)8 * (32 / pass_group_lanes(kp))); /* 8 warps per CTA */
 }
 
-static int launch_pass(plsa_ctx *ctx, int mode, const PassArgs &a)
+static int launch_pass(plsa_ctx *ctx, int mode, const PassArgs &a, cudaStream_t stream = nullptr)
 {
     if (a.n_items == 0) return PLSA_OK;
     pass_fn fn = pick_kernel(a.kp, mode, ctx->use_texture && a.gat_tex != 0);
-    fn<<<(unsigned)pass_grid(a.n_items, a.kp), 256, 0, ctx->stream>>>(a);
+    fn<<<(unsigned)pass_grid(a.n_items, a.kp), 256, 0, stream ? stream : ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
     return PLSA_OK;
@@ -480,7 +485,11 @@ API int plsa_ctx_create(int device, plsa_ctx **out)
         (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&ctx->ev_ll, cudaEventDisableTiming)) != cudaSuccess) {
+        (e = cudaEventCreateWithFlags(&ctx->ev_ll, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->ev_go, cudaEventDisableTiming)) != cudaSuccess) {
         g_err = std::string("context setup: ") + cudaGetErrorString(e);
         delete ctx;
         return PLSA_ECUDA;
@@ -517,6 +526,10 @@ API int plsa_ctx_destroy(plsa_ctx *ctx)
     }
     if (ctx->mail) cudaFreeHost(ctx->mail);
     if (ctx->ev_ll) cudaEventDestroy(ctx->ev_ll);
+    if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+    if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+    if (ctx->ev_go) cudaEventDestroy(ctx->ev_go);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -901,34 +914,24 @@ API int plsa_log_likelihood(plsa_ctx *ctx, double *ll)
     return run_loglik(ctx, ll);
 }
 
-static int run_fixup(plsa_ctx *ctx, float *newA, float *newB)
+/* split rows of one factor (which = 0: P(z|d), normalised; 1: P(w|z)^T) on `stream` */
+static int run_fixup(plsa_ctx *ctx, int which, float *own_new, cudaStream_t stream)
 {
-    const ItemSet &ia = ctx->doc_items, &ib = ctx->term_items;
-    const int na = ia.n_split, nb = newB ? ib.n_split : 0;
-    if (na + nb == 0) return PLSA_OK;
-    ProfScope ps(ctx, PLSA_PROF_FIXUP);
-    FixArgs fa{}, fb{};
-    fa.rows = ia.split_rows.as<int32_t>();
-    fa.slot_begin = ia.slot_begin.as<int32_t>();
-    fa.partial = ctx->partialA.as<float>();
-    fa.own_new = newA;
-    fa.n_split = na;
-    fa.n_heavy = std::min(ia.n_heavy, na);
-    fa.kp = ctx->kp;
-    fa.stride_own = ctx->strideA;
-    fa.normalise = 1;
-    fb.rows = ib.split_rows.as<int32_t>();
-    fb.slot_begin = ib.slot_begin.as<int32_t>();
-    fb.partial = ctx->partialB.as<float>();
-    fb.own_new = newB;
-    fb.n_split = nb;
-    fb.n_heavy = std::min(ib.n_heavy, nb);
-    fb.kp = ctx->kp;
-    fb.stride_own = ctx->strideB;
-    fb.normalise = 0;
-    const int blocks_a = fa.n_heavy + (int)cdiv(na - fa.n_heavy, 8);
-    const int blocks_b = fb.n_heavy + (int)cdiv(nb - fb.n_heavy, 8);
-    fixup_kernel<<<(unsigned)(blocks_a + blocks_b), 256, 0, ctx->stream>>>(fa, fb);
+    const ItemSet &is = which ? ctx->term_items : ctx->doc_items;
+    if (is.n_split == 0) return PLSA_OK;
+    ProfScope ps(ctx, PLSA_PROF_FIXUP, stream);
+    FixArgs f{}, none{};
+    f.rows = is.split_rows.as<int32_t>();
+    f.slot_begin = is.slot_begin.as<int32_t>();
+    f.partial = which ? ctx->partialB.as<float>() : ctx->partialA.as<float>();
+    f.own_new = own_new;
+    f.n_split = is.n_split;
+    f.n_heavy = std::min(is.n_heavy, is.n_split);
+    f.kp = ctx->kp;
+    f.stride_own = which ? ctx->strideB : ctx->strideA;
+    f.normalise = which ? 0 : 1;
+    const int blocks = f.n_heavy + (int)cdiv(f.n_split - f.n_heavy, 8);
+    fixup_kernel<<<(unsigned)blocks, 256, 0, stream>>>(f, none);
     ctx->launches++;
     CK(cudaGetLastError());
     return PLSA_OK;
@@ -970,6 +973,14 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
         CK(ctx->flag.ensure(4));
         CK(ctx->ll_part.ensure((size_t)std::max<int64_t>(pass_grid(ctx->doc_items.n_items, kp), 1) * 8));
     }
+    if (!refit) { /* per-CTA column sums of the term pass and its last-arrival tickets */
+        const int64_t tgrid = pass_grid(ctx->term_items.n_items, kp);
+        CK(ctx->colpart.ensure((size_t)(tgrid + tgrid / 32 + 2) * kp * 8));
+        if (ctx->tickets.cap < (size_t)(tgrid / 32 + 8) * 4) {
+            CK(ctx->tickets.ensure((size_t)(tgrid / 32 + 8) * 4 * 2));
+            CK(cudaMemsetAsync(ctx->tickets.p, 0, ctx->tickets.cap, ctx->stream));
+        }
+    }
     int32_t nl = 0;
     double prev = 0.0;
     bool stopped = false;
@@ -997,9 +1008,18 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
         nl++;
     }
     int32_t done = 0;
+    /* The doc pass and the term pass of an iteration read the same old factors and write
+     * different new ones: they run on two streams (with their split-row fixups behind them)
+     * and join before the next iteration.  Per-kernel profiling keeps them serial. */
+    const bool two = ctx->overlap && !refit && !ctx->profiling;
+    cudaStream_t s1 = ctx->stream, s2 = two ? ctx->stream2 : ctx->stream;
     for (int32_t i = 0; i < n_iter; ++i) {
         const int nA = ctx->curA ^ 1, nB = ctx->curB ^ 1;
         const bool fused_now = fuse && (i == 0 || (i - 1) % n_iter_per_test == 0);
+        if (two) { /* s2 starts once everything issued so far on s1 (previous join) is done */
+            CK(cudaEventRecord(ctx->ev_go, s1));
+            CK(cudaStreamWaitEvent(s2, ctx->ev_go, 0));
+        }
         {   /* E-step + M-step of P(z|d): plsa.py:91-105, :189-194 (P(z|d) part), :199-202 */
             ProfScope ps(ctx, PLSA_PROF_DOC_PASS);
             PassArgs a{};
@@ -1031,9 +1051,10 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                 CK(cudaEventRecord(ctx->ev_ll, ctx->stream));
             }
         }
+        if ((rc = run_fixup(ctx, 0, ctx->A[nA].as<float>(), s1))) return rc;
         if (!refit) {
             {   /* E-step + M-step of P(w|z): plsa.py:91-105, :189-193 (P(w|z) part) */
-                ProfScope ps(ctx, PLSA_PROF_WORD_PASS);
+                ProfScope ps(ctx, PLSA_PROF_WORD_PASS, s2);
                 PassArgs a{};
                 a.items = ctx->term_items.items.as<Item>();
                 a.n_items = ctx->term_items.n_items;
@@ -1045,12 +1066,6 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                 a.partial = ctx->partialB.as<float>();
                 a.gat_tex = ctx->texA[ctx->curA];
                 /* plsa.py:196-198: per-topic normaliser of the new P(w|z), applied lazily */
-                const int64_t tgrid = pass_grid(a.n_items, kp);
-                CK(ctx->colpart.ensure((size_t)(tgrid + tgrid / 32 + 2) * kp * 8));
-                if (ctx->tickets.cap < (size_t)(tgrid / 32 + 8) * 4) {
-                    CK(ctx->tickets.ensure((size_t)(tgrid / 32 + 8) * 4 * 2));
-                    CK(cudaMemsetAsync(ctx->tickets.p, 0, ctx->tickets.cap, ctx->stream));
-                }
                 a.cta_partial = ctx->colpart.as<double>();
                 a.ticket = ctx->tickets.as<unsigned int>() + 1; /* [0] is the log-likelihood's */
                 a.scale_out = reinterpret_cast<float *>(ctx->scale.p) + (size_t)nB * kp;
@@ -1059,12 +1074,15 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                 a.stride_gat = ctx->strideA;
                 a.kp = kp;
                 a.thresh = e_step_thresh;
-                if ((rc = launch_pass(ctx, MODE_TERM, a))) return rc;
+                if ((rc = launch_pass(ctx, MODE_TERM, a, s2))) return rc;
+            }
+            /* split rows: ordered sums of their chunk partials */
+            if ((rc = run_fixup(ctx, 1, ctx->B[nB].as<float>(), s2))) return rc;
+            if (two) {
+                CK(cudaEventRecord(ctx->ev_b, s2));
+                CK(cudaStreamWaitEvent(s1, ctx->ev_b, 0)); /* join */
             }
         }
-        /* split rows of both factors: ordered sums of their chunk partials */
-        if ((rc = run_fixup(ctx, ctx->A[nA].as<float>(), refit ? nullptr : ctx->B[nB].as<float>())))
-            return rc;
         if (fused_now) {
             CK(cudaEventSynchronize(ctx->ev_ll));
             double v;
@@ -1147,6 +1165,10 @@ API int plsa_set_option(plsa_ctx *ctx, const char *name, int64_t value)
         if (value != 0 && (value < 32 || value > ENT_PAD - ENT_SLACK))
             return ctx->fail(PLSA_EINVAL, "chunk out of range (32..4096)");
         ctx->chunk_user = value; /* item sets are rebuilt on the next prepare / em */
+        return PLSA_OK;
+    }
+    if (!strcmp(name, "overlap")) {
+        ctx->overlap = value != 0;
         return PLSA_OK;
     }
     if (!strcmp(name, "fuse_ll")) {

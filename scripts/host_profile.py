@@ -40,3 +40,24 @@ print("sum of phases %.2f ms" % ((time.perf_counter() - t_all) * 1e3))
 t0 = time.perf_counter()
 plsa.PLSA(n_components=k, n_iter=n_iter, tolerance=0.0, random_state=42).fit(X)
 print("PLSA.fit end to end %.2f ms" % ((time.perf_counter() - t0) * 1e3))
+
+# ---- steady state: phases inside plsa_fit on a pooled context -------------------------
+import threading
+from enstop_b200.plsa import _Staging, plsa_init
+for rep in range(3):
+    t = {}
+    t0 = time.perf_counter()
+    st = _Staging(X, k, None, None, refit=False)
+    t["thread start"] = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    rng = check_random_state(42)
+    p, w = plsa_init(X, k, "random", rng)
+    p = p.astype(np.float32); w = w.astype(np.float32)
+    t["init (main thread)"] = time.perf_counter() - t1
+    t1 = time.perf_counter(); ctx = st.wait(); t["wait for staging"] = time.perf_counter() - t1
+    t1 = time.perf_counter(); ctx.set_factors(p, w); ctx.set_sample_weight(None); t["set_factors"] = time.perf_counter() - t1
+    t1 = time.perf_counter(); ctx.em(n_iter, 10, 0.0); t["em"] = time.perf_counter() - t1
+    t1 = time.perf_counter(); ctx.get_factors(); t["get_factors"] = time.perf_counter() - t1
+    t1 = time.perf_counter(); st.close(); t["release"] = time.perf_counter() - t1
+    t["total"] = time.perf_counter() - t0
+    print("steady", rep, {a: round(b * 1e3, 2) for a, b in t.items()})

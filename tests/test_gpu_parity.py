@@ -191,9 +191,10 @@ def test_fused_loglik_is_the_separate_pass(golden_c1_planted, n_iter, per_test, 
     g, X = golden_c1_planted
     sw = np.ones(X.shape[0], dtype=np.float32)
     out = []
-    for fuse in (1, 0):
+    for fuse in (1, 0):   # fused + two-stream passes  vs  separate pass + one stream
         with _lib.Context(0) as ctx:
             ctx.set_option("fuse_ll", fuse)
+            ctx.set_option("overlap", fuse)
             ctx.upload_csr(X)
             pzd, pwz, info = plsa.plsa_fit(X, 10, sw, init=(g["pzd0"], g["pwz0"]), n_iter=n_iter,
                                            n_iter_per_test=per_test, tolerance=tol, context=ctx,
