@@ -69,7 +69,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 [exe, "-i", str(self.device), "--query-gpu=" + self.QUERY,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
