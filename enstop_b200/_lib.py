@@ -19,12 +19,12 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 SO_PATH = os.environ.get("ENSTOP_B200_LIB") or os.path.join(_HERE, "libplsa_b200.so")
-SOURCES = [os.path.join(_HERE, "csrc", "plsa_b200.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", "plsa_b200.cu"), os.path.join(_HERE, "csrc", "host_init.cpp")]
 HEADERS = [os.path.join(_HERE, "csrc", "plsa_kernels.cuh"),
            os.path.join(ROOT, "include", "plsa_b200.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-diag-suppress", "550"]
+              "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden,-mavx2", "-diag-suppress", "550"]
 
 PLSA_OK, PLSA_EINVAL, PLSA_ECUDA, PLSA_ENOMEM, PLSA_ENCCL = 0, 1, 2, 3, 4
 PROF_SLOTS = ("doc_pass", "word_pass", "fixup", "normalize", "loglik")
@@ -63,6 +63,8 @@ SIGNATURES = {
     "plsa_get_profile": (ctypes.c_int, [_ctx, _f64p, _i64p]),
     "plsa_launch_count": (ctypes.c_int, [_ctx, _i64p]),
     "plsa_set_option": (ctypes.c_int, [_ctx, ctypes.c_char_p, _i64]),
+    "plsa_host_random_rows": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint32), _i32p, _i64, _i64, _f32p,
+                                             _f64p]),
     "plsa_b200_fit_inner": (ctypes.c_int, [_i32p, _i32p, _f32p, _i64, _f32p, _f32p, _f32p, _i64,
                                            _i64, _i32, _i32, _i32, _f64, _f32, _i32, _i32, _i32p]),
     "plsa_b200_refit_inner": (ctypes.c_int, [_i32p, _i32p, _f32p, _i64, _f32p, _f32p, _f32p,
@@ -148,6 +150,29 @@ def check(rc, ctx=None):
         kind = {PLSA_EINVAL: "invalid argument", PLSA_ECUDA: "CUDA error",
                 PLSA_ENOMEM: "out of memory", PLSA_ENCCL: "NCCL error"}.get(rc, "error %d" % rc)
         raise PlsaError("libplsa_b200: %s: %s" % (kind, msg))
+
+
+def random_rows(rng, rows, cols, want_f64=False):
+    """``rng.rand(rows, cols)`` L1-row-normalised in float64 and cast to float32, computed by
+    the library from the RandomState's own MT19937 state (which is advanced exactly as numpy
+    would).  Returns None when ``rng`` is not a legacy MT19937 RandomState (caller falls back
+    to numpy)."""
+    owner = np.random if rng is np.random else rng
+    get_state = getattr(owner, "get_state", None)
+    if get_state is None or not (owner is np.random or isinstance(owner, np.random.RandomState)):
+        return None
+    state = get_state()
+    if not isinstance(state, tuple) or state[0] != "MT19937":
+        return None
+    key = np.ascontiguousarray(state[1], dtype=np.uint32).copy()
+    pos = _i32(int(state[2]))
+    out = np.empty((rows, cols), dtype=np.float32)
+    out64 = np.empty((rows, cols), dtype=np.float64) if want_f64 else None
+    check(lib().plsa_host_random_rows(key.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
+                                      ctypes.byref(pos), rows, cols, _ptr(out, _f32p),
+                                      _ptr(out64, _f64p)))
+    owner.set_state(("MT19937", key, pos.value) + tuple(state[3:]))
+    return (out, out64) if want_f64 else out
 
 
 def device_count():

@@ -1,0 +1,161 @@
+/*
+ * host_init.cpp — host-side fast path of the reference's random initialisation.
+ *
+ * enstop/plsa.py:454-456 draws the initial factors with numpy's legacy RandomState
+ * (`rng.rand(k, m)` then `rng.rand(n, k)`), plsa.py:510-511 L1-normalises their rows in
+ * float64 (enstop/utils.py:22-41) and plsa.py:709-710 casts them to float32.  A seed must
+ * give the same factors here, so the generator cannot be replaced — but it can be run
+ * faster: this file advances a RandomState's MT19937 state exactly as numpy does
+ * (randomkit/mt19937 `genrand` + `random_sample`: (a >> 5, b >> 6) -> 53-bit double),
+ * vectorised with AVX2 where available, and fuses the row normalisation and the float32
+ * cast.  The caller (enstop_b200/plsa.py) reads the state with `rng.get_state()` and
+ * writes it back with `rng.set_state()`, so the stream stays the caller's.
+ *
+ * tests/test_host_cpu.py checks bit-equality with numpy for many seeds, positions and
+ * shapes, and with the reference's own initial factors stored in tests/golden.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#if defined(__AVX2__)
+#include <immintrin.h>
+#endif
+
+#include "../../include/plsa_b200.h"
+
+#define API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+constexpr int MT_N = 624, MT_M = 397;
+constexpr uint32_t MATRIX_A = 0x9908b0dfu, UPPER = 0x80000000u, LOWER = 0x7fffffffu;
+
+inline uint32_t twist(uint32_t cur, uint32_t nxt, uint32_t far)
+{
+    const uint32_t y = (cur & UPPER) | (nxt & LOWER);
+    return far ^ (y >> 1) ^ ((0u - (y & 1u)) & MATRIX_A);
+}
+
+/* regenerate the 624-word block (mt19937_gen) */
+void mt_refill(uint32_t *key)
+{
+    int i = 0;
+#if defined(__AVX2__)
+    const __m256i upper = _mm256_set1_epi32((int)UPPER), lower = _mm256_set1_epi32((int)LOWER),
+                  mat = _mm256_set1_epi32((int)MATRIX_A), one = _mm256_set1_epi32(1),
+                  zero = _mm256_setzero_si256();
+    auto step = [&](int idx, int far_idx) {
+        const __m256i cur = _mm256_loadu_si256((const __m256i *)(key + idx));
+        const __m256i nxt = _mm256_loadu_si256((const __m256i *)(key + idx + 1));
+        const __m256i far = _mm256_loadu_si256((const __m256i *)(key + far_idx));
+        const __m256i y = _mm256_or_si256(_mm256_and_si256(cur, upper), _mm256_and_si256(nxt, lower));
+        const __m256i mag = _mm256_and_si256(_mm256_sub_epi32(zero, _mm256_and_si256(y, one)), mat);
+        const __m256i r = _mm256_xor_si256(_mm256_xor_si256(far, _mm256_srli_epi32(y, 1)), mag);
+        _mm256_storeu_si256((__m256i *)(key + idx), r);
+    };
+    /* i in [0, 227): reads key[i+1] and key[i+397], both still old when 8 lanes are loaded
+     * before the store; 227 = 28*8 + 3 */
+    for (; i + 8 <= MT_N - MT_M; i += 8) step(i, i + MT_M);
+#endif
+    for (; i < MT_N - MT_M; ++i) key[i] = twist(key[i], key[i + 1], key[i + MT_M]);
+#if defined(__AVX2__)
+    /* i in [227, 623): reads key[i-227] (new, written >= 227 words earlier) and key[i+1] (old) */
+    for (; i + 8 <= MT_N - 1; i += 8) step(i, i + (MT_M - MT_N));
+#endif
+    for (; i < MT_N - 1; ++i) key[i] = twist(key[i], key[i + 1], key[i + (MT_M - MT_N)]);
+    key[MT_N - 1] = twist(key[MT_N - 1], key[0], key[MT_M - 1]);
+}
+
+inline uint32_t temper(uint32_t y)
+{
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+
+/* The generator state plus a block of tempered outputs, consumed two words per double
+ * (numpy legacy random_sample / rk_double: (a >> 5, b >> 6) -> 53 bits). */
+struct Stream {
+    uint32_t *key;
+    int pos;
+    uint32_t out[MT_N];
+
+    void temper_from(int from)
+    {
+        for (int i = from; i < MT_N; ++i) out[i] = temper(key[i]); /* auto-vectorised */
+    }
+    void refill()
+    {
+        mt_refill(key);
+        temper_from(0);
+        pos = 0;
+    }
+    static inline double make(uint32_t a, uint32_t b)
+    {
+        return ((a >> 5) * 67108864.0 + (b >> 6)) * (1.0 / 9007199254740992.0);
+    }
+    void fill(double *dst, int64_t n)
+    {
+        while (n > 0) {
+            if (pos == MT_N) refill();
+            int64_t pairs = (MT_N - pos) / 2;
+            if (pairs > n) pairs = n;
+            const uint32_t *src = out + pos;
+            for (int64_t i = 0; i < pairs; ++i) dst[i] = make(src[2 * i], src[2 * i + 1]);
+            dst += pairs;
+            n -= pairs;
+            pos += (int)(2 * pairs);
+            if (n > 0 && pos == MT_N - 1) { /* a double straddling two blocks */
+                const uint32_t a = out[pos];
+                refill();
+                *dst++ = make(a, out[0]);
+                pos = 1;
+                --n;
+            }
+        }
+    }
+};
+
+} // namespace
+
+/* Draw rows*cols doubles (row-major, the order rng.rand(rows, cols) produces them),
+ * L1-normalise every row with a float64 marginal accumulated left to right
+ * (enstop/utils.py:22-41; rows whose marginal is not > 0 are left as drawn) and store
+ * float32 (plsa.py:709-710).  key[624] / *pos are the RandomState's MT19937 state, updated
+ * in place.  out_f64 (optional) receives the normalised float64 values. */
+API int plsa_host_random_rows(uint32_t *key, int32_t *pos, int64_t rows, int64_t cols, float *out,
+                              double *out_f64)
+{
+    if (!key || !pos || !out || rows < 0 || cols < 0 || *pos < 0 || *pos > MT_N) return PLSA_EINVAL;
+    Stream s;
+    s.key = key;
+    s.pos = *pos;
+    s.temper_from(s.pos < MT_N ? s.pos : MT_N);
+    double *buf = (double *)malloc(sizeof(double) * (size_t)(cols > 0 ? cols : 1));
+    if (!buf) return PLSA_ENOMEM;
+    for (int64_t r = 0; r < rows; ++r) {
+        s.fill(buf, cols);
+        double marginal = 0.0;
+        for (int64_t c = 0; c < cols; ++c) marginal += buf[c]; /* left to right, as utils.py:25-29 */
+        float *o = out + r * cols;
+        double *o64 = out_f64 ? out_f64 + r * cols : nullptr;
+        if (marginal > 0.0) {
+            for (int64_t c = 0; c < cols; ++c) {
+                const double v = buf[c] / marginal;
+                o[c] = (float)v;
+                if (o64) o64[c] = v;
+            }
+        } else {
+            for (int64_t c = 0; c < cols; ++c) {
+                o[c] = (float)buf[c];
+                if (o64) o64[c] = buf[c];
+            }
+        }
+    }
+    free(buf);
+    *pos = s.pos;
+    return PLSA_OK;
+}

@@ -124,6 +124,14 @@ int plsa_launch_count(const plsa_ctx *ctx, int64_t *launches);
  * "fuse_ll" (1: the periodic log-likelihood rides on the next doc pass, 0: separate pass). */
 int plsa_set_option(plsa_ctx *ctx, const char *name, int64_t value);
 
+/* ---- host helper: the reference's seeded random initialisation, faster ------------------------ */
+/* plsa.py:454-456 + :510-511 + :709-710: draw rows*cols doubles from a numpy legacy
+ * RandomState (MT19937 state key[624], *pos — from rng.get_state(), written back for
+ * rng.set_state()), L1-normalise each row in float64 (utils.py:22-41) and store float32
+ * (and optionally the float64 values).  Bit-identical to rng.rand + normalize + astype. */
+int plsa_host_random_rows(uint32_t *key, int32_t *pos, int64_t rows, int64_t cols, float *out,
+                          double *out_f64);
+
 /* ---- one-shot drop-ins for the reference's raw-array seam --------------------------------- */
 /* plsa.py:516-640.  p_w_given_z [k, m] and p_z_given_d [n, k] are updated in place. */
 int plsa_b200_fit_inner(const int32_t *X_rows, const int32_t *X_cols, const float *X_vals,

@@ -71,6 +71,45 @@ def test_random_init_is_the_references_stream(golden_c1_zipf):
     assert np.allclose(pzd, opzd, rtol=1e-15) and np.allclose(pwz, opwz, rtol=1e-15)
 
 
+@pytest.mark.parametrize("seed,burn,rows,cols", [(42, 0, 10, 5000), (42, 13, 2000, 10),
+                                                 (7, 1, 5, 3), (123, 311, 1000, 7), (5, 0, 311, 1),
+                                                 (9, 2, 3, 624), (9, 0, 1, 1249), (0, 623, 64, 20)])
+def test_host_random_rows_is_numpy_bit_for_bit(seed, burn, rows, cols):
+    """csrc/host_init.cpp advances the RandomState's MT19937 state exactly as numpy's
+    rand() does and reproduces rand + L1 row normalisation + float32 cast bit for bit."""
+    a, b = np.random.RandomState(seed), np.random.RandomState(seed)
+    if burn:
+        a.randint(0, 10, size=burn)   # odd numbers of 32-bit draws shift the pair alignment
+        b.randint(0, 10, size=burn)
+    x = a.rand(rows, cols)
+    x /= x.sum(axis=1, keepdims=True)
+    y32, y64 = _lib.random_rows(b, rows, cols, want_f64=True)
+    assert np.array_equal(x.astype(np.float32), y32)
+    assert np.allclose(x, y64, rtol=1e-13, atol=0)     # numpy sums pairwise, the reference left to right
+    assert np.array_equal(a.rand(7), b.rand(7))           # the streams stay in step
+    assert a.get_state()[2] == b.get_state()[2]
+
+
+def test_fast_random_init_equals_plsa_init(golden_c1_zipf):
+    g, X = golden_c1_zipf
+    fast = plsa._random_init_f32(X.shape[0], X.shape[1], 10, np.random.RandomState(42))
+    assert np.array_equal(fast[0], g["pzd0"]) and np.array_equal(fast[1], g["pwz0"])
+    # the module-level generator (random_state=None) is advanced in place as well
+    st = np.random.get_state()
+    try:
+        np.random.seed(5)
+        ref = plsa.plsa_init(X, 10, "random", np.random)
+        after_ref = np.random.rand()
+        np.random.seed(5)
+        fast = plsa._random_init_f32(X.shape[0], X.shape[1], 10, np.random)
+        assert np.random.rand() == after_ref
+        assert np.array_equal(fast[0], ref[0].astype(np.float32))
+        assert np.array_equal(fast[1], ref[1].astype(np.float32))
+    finally:
+        np.random.set_state(st)
+    assert plsa._random_init_f32(5, 6, 2, np.random.default_rng(0)) is None   # not MT19937
+
+
 def test_init_variants():
     X = synth.make_corpus(200, 300, 6000, seed=2, planted=True, k_true=4).astype(np.float64)
     for init in ("nndsvd", "nmf"):
