@@ -22,6 +22,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/plsa_b200.h"
@@ -90,7 +91,7 @@ struct plsa_ctx {
     const Corpus &cur() const { return use_boot ? boot : base; }
 
     /* term-major copy of the working corpus */
-    DevBuf t_ent, t_entw, up_cols, up_vals, flag;
+    DevBuf t_ent, t_entw, up_cols, up_vals, flag, scratch[7];
     std::vector<int32_t> h_tindptr;
     bool t_ready = false, t_weighted_ready = false;
 
@@ -104,6 +105,12 @@ struct plsa_ctx {
     cudaEvent_t ev_ll = nullptr;
     bool overlap = true;     /* doc pass and term pass of an iteration on two streams */
     cudaStream_t stream2 = nullptr;
+    /* pinned staging for host->device copies of pageable memory (see h2d_fast) */
+    static constexpr int H2D_THREADS = 4;
+    static constexpr size_t H2D_CHUNK = (size_t)4 << 20;
+    char *pin[H2D_THREADS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t pin_stream[H2D_THREADS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pin_ev[H2D_THREADS][2] = {};
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_go = nullptr;
     cudaTextureObject_t texA[2] = {0, 0}, texB[2] = {0, 0};
     size_t tex_max_texels = 0;
@@ -156,6 +163,61 @@ struct plsa_ctx {
     } while (0)
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+/* ---- fast host -> device copy of pageable memory ------------------------------------------
+ * cudaMemcpy from pageable memory is staged by the driver on one thread (~10 GB/s here).
+ * Large uploads are instead cut into four slices, each moved by its own host thread through
+ * a private pinned double buffer and stream, so the host-side memcpy runs four wide and
+ * overlaps the DMA. */
+static cudaError_t h2d_fast(plsa_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    constexpr int T = plsa_ctx::H2D_THREADS;
+    constexpr size_t CH = plsa_ctx::H2D_CHUNK;
+    if (bytes < 8 * CH) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    cudaError_t e;
+    for (int t = 0; t < T; ++t) {
+        if (!ctx->pin[t]) {
+            if ((e = cudaHostAlloc((void **)&ctx->pin[t], 2 * CH, cudaHostAllocDefault)) != cudaSuccess ||
+                (e = cudaStreamCreateWithFlags(&ctx->pin_stream[t], cudaStreamNonBlocking)) != cudaSuccess ||
+                (e = cudaEventCreateWithFlags(&ctx->pin_ev[t][0], cudaEventDisableTiming)) != cudaSuccess ||
+                (e = cudaEventCreateWithFlags(&ctx->pin_ev[t][1], cudaEventDisableTiming)) != cudaSuccess)
+                return e;
+        }
+    }
+    /* everything queued on ctx->stream so far (e.g. buffer memsets) precedes the copies */
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return e;
+    const size_t slice = (bytes / T + 255) / 256 * 256;
+    cudaError_t errs[T];
+    std::thread th[T];
+    const int device = ctx->device;
+    for (int t = 0; t < T; ++t) {
+        errs[t] = cudaSuccess;
+        th[t] = std::thread([=, &errs]() {
+            cudaSetDevice(device);
+            const size_t lo = std::min(bytes, slice * (size_t)t), hi = std::min(bytes, lo + slice);
+            int b = 0;
+            for (size_t off = lo; off < hi; off += CH, b ^= 1) {
+                const size_t n = std::min(CH, hi - off);
+                cudaError_t r = cudaEventSynchronize(ctx->pin_ev[t][b]); /* buffer free again */
+                if (r == cudaSuccess) {
+                    memcpy(ctx->pin[t] + (size_t)b * CH, (const char *)src + off, n);
+                    r = cudaMemcpyAsync((char *)dst + off, ctx->pin[t] + (size_t)b * CH, n,
+                                        cudaMemcpyHostToDevice, ctx->pin_stream[t]);
+                }
+                if (r == cudaSuccess) r = cudaEventRecord(ctx->pin_ev[t][b], ctx->pin_stream[t]);
+                if (r != cudaSuccess) {
+                    errs[t] = r;
+                    return;
+                }
+            }
+            errs[t] = cudaStreamSynchronize(ctx->pin_stream[t]);
+        });
+    }
+    for (int t = 0; t < T; ++t) th[t].join();
+    for (int t = 0; t < T; ++t)
+        if (errs[t] != cudaSuccess) return errs[t];
+    return cudaSuccess;
+}
 
 /* ---- profiling helpers ------------------------------------------------------------------- */
 static cudaEvent_t get_event(plsa_ctx *ctx)
@@ -359,10 +421,14 @@ static int build_term_major(plsa_ctx *ctx)
     Corpus &c = ctx->cur();
     const int64_t nnz = c.nnz, n = c.n, m = c.m;
     cudaStream_t s = ctx->stream;
-    DevBuf rows_exp, keys_in, perm_in, perm_out, keys_out, tindptr, tmp;
+    /* scratch (20 B per entry) is kept with the context for the next corpus unless it is
+     * large: repeated fits then skip seven cudaMalloc/cudaFree pairs */
+    DevBuf &rows_exp = ctx->scratch[0], &keys_in = ctx->scratch[1], &perm_in = ctx->scratch[2],
+           &perm_out = ctx->scratch[3], &keys_out = ctx->scratch[4], &tindptr = ctx->scratch[5],
+           &tmp = ctx->scratch[6];
     auto cleanup = [&]() {
-        rows_exp.release(); keys_in.release(); perm_in.release(); perm_out.release();
-        keys_out.release(); tindptr.release(); tmp.release();
+        if (nnz > ((int64_t)32 << 20))
+            for (DevBuf &b : ctx->scratch) b.release();
     };
 #define CKT(expr)                                                                             \
     do {                                                                                      \
@@ -512,6 +578,7 @@ API int plsa_ctx_destroy(plsa_ctx *ctx)
     for (Corpus *c : {&ctx->base, &ctx->boot}) {
         c->indptr.release(); c->ent.release();
     }
+    for (DevBuf &b : ctx->scratch) b.release();
     for (DevBuf *b : {&ctx->t_ent, &ctx->t_entw, &ctx->up_cols, &ctx->up_vals, &ctx->flag,
                       &ctx->doc_items.items, &ctx->doc_items.split_rows, &ctx->doc_items.slot_begin,
                       &ctx->term_items.items, &ctx->term_items.split_rows,
@@ -525,6 +592,12 @@ API int plsa_ctx_destroy(plsa_ctx *ctx)
         if (ctx->texB[i]) cudaDestroyTextureObject(ctx->texB[i]);
     }
     if (ctx->mail) cudaFreeHost(ctx->mail);
+    for (int t = 0; t < plsa_ctx::H2D_THREADS; ++t) {
+        if (ctx->pin[t]) cudaFreeHost(ctx->pin[t]);
+        if (ctx->pin_stream[t]) cudaStreamDestroy(ctx->pin_stream[t]);
+        for (int b = 0; b < 2; ++b)
+            if (ctx->pin_ev[t][b]) cudaEventDestroy(ctx->pin_ev[t][b]);
+    }
     if (ctx->ev_ll) cudaEventDestroy(ctx->ev_ll);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
@@ -573,8 +646,8 @@ static int upload_csr_impl(plsa_ctx *ctx, const int32_t *indptr, const int32_t *
     if (nnz > 0) {
         CK(ctx->up_cols.ensure((size_t)nnz * 4));
         CK(ctx->up_vals.ensure((size_t)nnz * vsz));
-        CK(cudaMemcpyAsync(ctx->up_cols.p, indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->up_vals.p, data, (size_t)nnz * vsz, cudaMemcpyHostToDevice, ctx->stream));
+        CK(h2d_fast(ctx, ctx->up_cols.p, indices, (size_t)nnz * 4));
+        CK(h2d_fast(ctx, ctx->up_vals.p, data, (size_t)nnz * vsz));
         const unsigned grid = (unsigned)cdiv(nnz, 256);
         int2 *ent = c.ent.as<int2>();
         int *flag = ctx->flag.as<int>();

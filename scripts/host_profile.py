@@ -51,8 +51,8 @@ for rep in range(3):
     t["thread start"] = time.perf_counter() - t0
     t1 = time.perf_counter()
     rng = check_random_state(42)
-    p, w = plsa_init(X, k, "random", rng)
-    p = p.astype(np.float32); w = w.astype(np.float32)
+    from enstop_b200.plsa import _random_init_f32
+    p, w = _random_init_f32(X.shape[0], X.shape[1], k, rng)
     t["init (main thread)"] = time.perf_counter() - t1
     t1 = time.perf_counter(); ctx = st.wait(); t["wait for staging"] = time.perf_counter() - t1
     t1 = time.perf_counter(); ctx.set_factors(p, w); ctx.set_sample_weight(None); t["set_factors"] = time.perf_counter() - t1
@@ -61,3 +61,15 @@ for rep in range(3):
     t1 = time.perf_counter(); st.close(); t["release"] = time.perf_counter() - t1
     t["total"] = time.perf_counter() - t0
     print("steady", rep, {a: round(b * 1e3, 2) for a, b in t.items()})
+
+# ---- PLSA.fit_transform pieces before plsa_fit
+for rep in range(2):
+    t0 = time.perf_counter(); Xc = check_array(X, accept_sparse="csr"); t1 = time.perf_counter()
+    dm = Xc.data.min(); t2 = time.perf_counter()
+    good = np.diff(Xc.indptr) != 0; allg = np.all(good); t3 = time.perf_counter()
+    sw = _check_sample_weight(None, Xc, dtype=np.float32); t4 = time.perf_counter()
+    print("front", rep, "check_array %.2f min %.2f rows %.2f sw %.2f ms" % ((t1-t0)*1e3,(t2-t1)*1e3,(t3-t2)*1e3,(t4-t3)*1e3))
+for rep in range(5):
+    t0 = time.perf_counter()
+    plsa.PLSA(n_components=k, n_iter=n_iter, tolerance=0.0, random_state=42).fit(X)
+    print("PLSA.fit end to end %.2f ms" % ((time.perf_counter() - t0) * 1e3))

@@ -267,6 +267,34 @@ def test_properties_at_scale():
     assert rel_l2(b[0], a[0][pd_]) < 1e-5 and rel_l2(b[1], a[1][:, pt_]) < 1e-5
 
 
+def test_properties_at_baseline_size():
+    """BASELINE config 2 in full (100k x 50k, ~10M stored entries, k=20), through the public
+    API: the size-independent properties, plus agreement of the fused pipeline (two streams,
+    log-likelihood riding on the doc pass) with the plain one and run-to-run bit equality."""
+    X = synth.make_config("C2")
+    assert abs(X.nnz - 10_000_000) < 300_000
+    sw = np.ones(X.shape[0], dtype=np.float32)
+    pzd, pwz, info = plsa.plsa_fit(X, 20, sw, n_iter=21, n_iter_per_test=10, tolerance=0.0,
+                                   random_state=42, device=0, return_info=True)
+    assert info["n_iter"] == 21 and len(info["ll_trace"]) == 4
+    assert np.allclose(pzd.sum(axis=1), 1.0, atol=3e-6)
+    assert np.allclose(pwz.sum(axis=1), 1.0, atol=3e-6)
+    assert pzd.min() >= 0 and pwz.min() >= 0 and np.isfinite(pzd).all() and np.isfinite(pwz).all()
+    ll = info["ll_trace"]
+    assert np.all(np.diff(ll) > 0)
+    # exact log-likelihood of the returned model (float64 oracle pass over all 10M entries)
+    assert abs(oracle.log_likelihood(X, pwz, pzd) - ll[-1]) / abs(ll[-1]) < 1e-6
+    with _lib.Context(0) as ctx:
+        ctx.set_option("fuse_ll", 0)
+        ctx.set_option("overlap", 0)
+        ctx.set_option("texture", 0)
+        ctx.upload_csr(X)
+        pzd2, pwz2, info2 = plsa.plsa_fit(X, 20, sw, n_iter=21, n_iter_per_test=10, tolerance=0.0,
+                                          random_state=42, context=ctx, return_info=True)
+    assert np.array_equal(pzd, pzd2) and np.array_equal(pwz, pwz2)
+    assert np.allclose(info["ll_trace"], info2["ll_trace"], rtol=1e-9)
+
+
 def test_estimator_semantics(golden_small):
     g, X = golden_small
     k = int(g["k"])
