@@ -203,6 +203,8 @@ class Context:
             self.set_option("chunk", int(os.environ["ENSTOP_B200_CHUNK"]))
         if os.environ.get("ENSTOP_B200_TEXTURE"):   # 0: gather with LDG instead of the texture pipe
             self.set_option("texture", int(os.environ["ENSTOP_B200_TEXTURE"]))
+        if os.environ.get("ENSTOP_B200_VEC"):       # 0: unaligned items, one 8-byte load per entry
+            self.set_option("vec_entries", int(os.environ["ENSTOP_B200_VEC"]))
 
     def close(self):
         if self._h:

@@ -75,6 +75,7 @@ struct ItemSet {
     int32_t n_split = 0, n_heavy = 0, n_slots = 0;
     bool ready = false;
     int64_t chunk = 0;
+    int align = 1; /* items start on multiples of this many entries (Item::skip) */
 };
 
 } // namespace
@@ -100,6 +101,7 @@ struct plsa_ctx {
     int64_t chunk_built = 0; /* work-item length the item sets were built with */
     int32_t k_hint = 0;      /* plsa_prepare: k the items should be sized for */
     bool use_texture = true; /* gather through the texture pipe when the factor fits */
+    bool vec_entries = true; /* items aligned to entry blocks, one wide load per block */
     bool fuse_ll = true;     /* take the periodic log-likelihood from the next doc pass */
     double *mail = nullptr;  /* pinned host mailbox {ll, flag} */
     cudaEvent_t ev_ll = nullptr;
@@ -272,14 +274,23 @@ static void prof_collect(plsa_ctx *ctx)
 /* ---- kernel dispatch ------------------------------------------------------------------------ */
 typedef void (*pass_fn)(const PassArgs);
 
-template <int G, int KV> static pass_fn pick_mode(int mode, bool tex)
+template <int G, int KV, bool VEC> static pass_fn pick_mode_v(int mode, bool tex)
 {
     switch (mode) {
-    case MODE_DOC: return tex ? row_pass_kernel<G, KV, MODE_DOC, true> : row_pass_kernel<G, KV, MODE_DOC, false>;
-    case MODE_TERM: return tex ? row_pass_kernel<G, KV, MODE_TERM, true> : row_pass_kernel<G, KV, MODE_TERM, false>;
-    case MODE_DOC_LL: return tex ? row_pass_kernel<G, KV, MODE_DOC_LL, true> : row_pass_kernel<G, KV, MODE_DOC_LL, false>;
-    default: return tex ? row_pass_kernel<G, KV, MODE_LOGLIK, true> : row_pass_kernel<G, KV, MODE_LOGLIK, false>;
+    case MODE_DOC: return tex ? row_pass_kernel<G, KV, MODE_DOC, true, VEC> : row_pass_kernel<G, KV, MODE_DOC, false, VEC>;
+    case MODE_TERM: return tex ? row_pass_kernel<G, KV, MODE_TERM, true, VEC> : row_pass_kernel<G, KV, MODE_TERM, false, VEC>;
+    case MODE_DOC_LL: return tex ? row_pass_kernel<G, KV, MODE_DOC_LL, true, VEC> : row_pass_kernel<G, KV, MODE_DOC_LL, false, VEC>;
+    default: return tex ? row_pass_kernel<G, KV, MODE_LOGLIK, true, VEC> : row_pass_kernel<G, KV, MODE_LOGLIK, false, VEC>;
     }
+}
+
+/* vec: the items start on entry-block boundaries (ItemSet::align > 1) */
+template <int G, int KV> static pass_fn pick_mode(int mode, bool tex, bool vec)
+{
+    if constexpr (pass_block_entries(KV) > 1) {
+        if (vec) return pick_mode_v<G, KV, true>(mode, tex);
+    }
+    return pick_mode_v<G, KV, false>(mode, tex);
 }
 
 /* lanes per work item for a factor row of kp floats */
@@ -289,25 +300,32 @@ static int pass_group_lanes(int kp)
     return nv <= 8 ? nv : nv <= 16 ? 16 : 32;
 }
 
-static pass_fn pick_kernel(int kp, int mode, bool tex)
+/* entries per block of the kernel that serves kp (pass_block_entries of its KV) */
+static int pass_entry_block(int kp)
+{
+    const int nv = kp / 4;
+    return nv <= 32 ? 4 : nv <= 64 ? 2 : 1;
+}
+
+static pass_fn pick_kernel(int kp, int mode, bool tex, bool vec)
 {
     const int nv = kp / 4; /* float4 vectors per factor row */
     switch (nv) {
-    case 1: return pick_mode<1, 1>(mode, tex);
-    case 2: return pick_mode<2, 1>(mode, tex);
-    case 3: return pick_mode<3, 1>(mode, tex);
-    case 4: return pick_mode<4, 1>(mode, tex);
-    case 5: return pick_mode<5, 1>(mode, tex);
-    case 6: return pick_mode<6, 1>(mode, tex);
-    case 7: return pick_mode<7, 1>(mode, tex);
-    case 8: return pick_mode<8, 1>(mode, tex);
+    case 1: return pick_mode<1, 1>(mode, tex, vec);
+    case 2: return pick_mode<2, 1>(mode, tex, vec);
+    case 3: return pick_mode<3, 1>(mode, tex, vec);
+    case 4: return pick_mode<4, 1>(mode, tex, vec);
+    case 5: return pick_mode<5, 1>(mode, tex, vec);
+    case 6: return pick_mode<6, 1>(mode, tex, vec);
+    case 7: return pick_mode<7, 1>(mode, tex, vec);
+    case 8: return pick_mode<8, 1>(mode, tex, vec);
     default: break;
     }
-    if (nv <= 16) return pick_mode<16, 1>(mode, tex);
-    if (nv <= 32) return pick_mode<32, 1>(mode, tex);
-    if (nv <= 64) return pick_mode<32, 2>(mode, tex);
-    if (nv <= 128) return pick_mode<32, 4>(mode, tex);
-    return pick_mode<32, 8>(mode, tex);
+    if (nv <= 16) return pick_mode<16, 1>(mode, tex, vec);
+    if (nv <= 32) return pick_mode<32, 1>(mode, tex, vec);
+    if (nv <= 64) return pick_mode<32, 2>(mode, tex, vec);
+    if (nv <= 128) return pick_mode<32, 4>(mode, tex, vec);
+    return pick_mode<32, 8>(mode, tex, vec);
 }
 
 static int64_t pass_grid(int64_t n_items, int kp)
@@ -315,10 +333,11 @@ static int64_t pass_grid(int64_t n_items, int kp)
     return cdiv(n_items, (int64_t)8 * (32 / pass_group_lanes(kp))); /* 8 warps per CTA */
 }
 
-static int launch_pass(plsa_ctx *ctx, int mode, const PassArgs &a, cudaStream_t stream = nullptr)
+static int launch_pass(plsa_ctx *ctx, int mode, const PassArgs &a, bool vec,
+                       cudaStream_t stream = nullptr)
 {
     if (a.n_items == 0) return PLSA_OK;
-    pass_fn fn = pick_kernel(a.kp, mode, ctx->use_texture && a.gat_tex != 0);
+    pass_fn fn = pick_kernel(a.kp, mode, ctx->use_texture && a.gat_tex != 0, vec);
     fn<<<(unsigned)pass_grid(a.n_items, a.kp), 256, 0, stream ? stream : ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -346,14 +365,20 @@ static int64_t choose_chunk(const plsa_ctx *ctx, int kp)
 }
 
 static int build_items(plsa_ctx *ctx, const std::vector<int32_t> &indptr, int64_t rows,
-                       ItemSet &out, int64_t chunk)
+                       ItemSet &out, const int64_t chunk_asked, int align)
 {
+    const int64_t chunk = chunk_asked / align * align; /* chunks of a split row stay aligned */
     std::vector<Item> items;
     items.reserve((size_t)rows + 1024);
+    /* align > 1: an item starts on a multiple of `align` entries at or before its first
+     * entry; the entries in between (Item::skip of them, they belong to the row before) are
+     * walked with value 0.  Lengths below include them. */
+    auto lead = [&](int64_t r) { return (int64_t)indptr[r] & (int64_t)(align - 1); };
+    auto span = [&](int64_t r) { return (int64_t)indptr[r + 1] - indptr[r] + lead(r); };
     /* split rows, those with more than 32 chunks first (fixup_kernel gives them a CTA) */
     std::vector<int64_t> heavy, light;
     for (int64_t r = 0; r < rows; ++r) {
-        const int64_t len = indptr[r + 1] - indptr[r];
+        const int64_t len = span(r);
         if (len > chunk) (cdiv(len, chunk) > 32 ? heavy : light).push_back(r);
     }
     std::vector<int32_t> split_rows, slot_begin;
@@ -363,20 +388,21 @@ static int build_items(plsa_ctx *ctx, const std::vector<int32_t> &indptr, int64_
     for (const std::vector<int64_t> *lst : {&heavy, &light})
         for (int64_t r : *lst) {
             first_slot[(size_t)r] = slots;
-            slots += (int32_t)cdiv(indptr[r + 1] - indptr[r], chunk);
+            slots += (int32_t)cdiv(span(r), chunk);
             split_rows.push_back((int32_t)r);
             slot_begin.push_back(slots);
         }
     for (int64_t r = 0; r < rows; ++r) {
-        const int64_t s = indptr[r], len = indptr[r + 1] - s;
+        const int64_t skip = lead(r), s = indptr[r] - skip, len = span(r);
         if (len <= chunk) {
-            items.push_back(Item{s, (int32_t)r, (int32_t)len, -1, 0});
+            items.push_back(Item{s, (int32_t)r, (int32_t)len, -1, (int32_t)skip});
         } else {
-            const int64_t nc = cdiv(len, chunk);
+            const int64_t nc = cdiv(len, chunk); /* chunk is a multiple of 32: chunks stay aligned */
             for (int64_t c = 0; c < nc; ++c) {
                 const int64_t b = c * chunk;
                 items.push_back(Item{s + b, (int32_t)r, (int32_t)std::min(chunk, len - b),
-                                     first_slot[(size_t)r] + (int32_t)c, 0});
+                                     first_slot[(size_t)r] + (int32_t)c,
+                                     (int32_t)(c == 0 ? skip : 0)});
             }
         }
     }
@@ -409,7 +435,8 @@ static int build_items(plsa_ctx *ctx, const std::vector<int32_t> &indptr, int64_
                        cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream)); /* host vectors die here */
     out.ready = true;
-    out.chunk = chunk;
+    out.chunk = chunk_asked;
+    out.align = align;
     return PLSA_OK;
 }
 
@@ -920,14 +947,16 @@ API int plsa_get_factors(plsa_ctx *ctx, float *p_z_given_d, float *p_w_given_z)
 static int ensure_items(plsa_ctx *ctx, bool refit, int kp)
 {
     const int64_t chunk = choose_chunk(ctx, kp);
+    const int align = ctx->vec_entries ? pass_entry_block(kp) : 1;
     int rc;
-    if (!ctx->doc_items.ready || ctx->doc_items.chunk != chunk)
-        if ((rc = build_items(ctx, ctx->cur().h_indptr, ctx->cur().n, ctx->doc_items, chunk)))
+    if (!ctx->doc_items.ready || ctx->doc_items.chunk != chunk || ctx->doc_items.align != align)
+        if ((rc = build_items(ctx, ctx->cur().h_indptr, ctx->cur().n, ctx->doc_items, chunk, align)))
             return rc;
     if (!refit) {
         if (!ctx->t_ready && (rc = build_term_major(ctx))) return rc;
-        if (!ctx->term_items.ready || ctx->term_items.chunk != chunk)
-            if ((rc = build_items(ctx, ctx->h_tindptr, ctx->cur().m, ctx->term_items, chunk)))
+        if (!ctx->term_items.ready || ctx->term_items.chunk != chunk ||
+            ctx->term_items.align != align)
+            if ((rc = build_items(ctx, ctx->h_tindptr, ctx->cur().m, ctx->term_items, chunk, align)))
                 return rc;
     }
     return PLSA_OK;
@@ -962,7 +991,7 @@ static int run_loglik(plsa_ctx *ctx, double *out)
         a.stride_own = ctx->strideA;
         a.stride_gat = ctx->strideB;
         a.kp = ctx->kp;
-        if ((rc = launch_pass(ctx, MODE_LOGLIK, a))) return rc;
+        if ((rc = launch_pass(ctx, MODE_LOGLIK, a, ctx->doc_items.align > 1))) return rc;
     }
     CK(cudaMemcpyAsync(out, ctx->ll_out.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1117,7 +1146,8 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                 a.flag = ctx->flag.as<int>();
                 CK(cudaMemsetAsync(ctx->flag.p, 0, 4, ctx->stream));
             }
-            if ((rc = launch_pass(ctx, fused_now ? MODE_DOC_LL : MODE_DOC, a))) return rc;
+            if ((rc = launch_pass(ctx, fused_now ? MODE_DOC_LL : MODE_DOC, a, ctx->doc_items.align > 1)))
+                return rc;
             if (fused_now) {
                 CK(cudaMemcpyAsync(&ctx->mail[0], ctx->ll_out.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
                 CK(cudaMemcpyAsync(&ctx->mail[1], ctx->flag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1147,7 +1177,7 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                 a.stride_gat = ctx->strideA;
                 a.kp = kp;
                 a.thresh = e_step_thresh;
-                if ((rc = launch_pass(ctx, MODE_TERM, a, s2))) return rc;
+                if ((rc = launch_pass(ctx, MODE_TERM, a, ctx->term_items.align > 1, s2))) return rc;
             }
             /* split rows: ordered sums of their chunk partials */
             if ((rc = run_fixup(ctx, 1, ctx->B[nB].as<float>(), s2))) return rc;
@@ -1250,6 +1280,10 @@ API int plsa_set_option(plsa_ctx *ctx, const char *name, int64_t value)
     }
     if (!strcmp(name, "texture")) {
         ctx->use_texture = value != 0;
+        return PLSA_OK;
+    }
+    if (!strcmp(name, "vec_entries")) {
+        ctx->vec_entries = value != 0; /* item sets are rebuilt on the next prepare / em */
         return PLSA_OK;
     }
     return ctx->fail(PLSA_EINVAL, std::string("unknown option: ") + name);

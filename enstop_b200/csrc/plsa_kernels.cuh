@@ -44,7 +44,9 @@ struct Item {          /* one unit of group work: a row, or a chunk of a long ro
     int32_t row;       /* row whose factor this item owns                               */
     int32_t len;       /* stored entries in this item                                   */
     int32_t slot;      /* < 0: whole row, result goes to own_new; else partial-sum slot */
-    int32_t pad;
+    int32_t skip;      /* aligned items: `start` is rounded down to a multiple of the entry
+                          block, the first `skip` entries (< block) belong to the row before
+                          and count as value 0; `len` includes them                        */
 };
 
 enum { MODE_DOC = 0, MODE_TERM = 1, MODE_LOGLIK = 2,
@@ -101,6 +103,65 @@ __device__ __forceinline__ float rcp_fast(float x)
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+}
+
+/* Packed float32 pairs (sm_100 FMUL2 / FADD2 / FFMA2: one issue slot for two lanes' worth of
+ * a float4's arithmetic).  The row pass is co-limited by issue slots; the products, the
+ * in-lane sum and the accumulation are 13 % of its instructions fewer this way. */
+#ifndef PLSA_PACKED_MATH
+#define PLSA_PACKED_MATH 1
+#endif
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+/* U consecutive entries (8 bytes each) of an item.  VEC: one 8*U-byte load (U = 4: the
+ * 256-bit LDG.E.ENL2.256 of sm_100; the address is a multiple of 8*U bytes because aligned
+ * items start on an entry-block boundary).  The six groups of a warp read six different
+ * places, so every entry load costs one L1 wavefront per group: one wide load per block
+ * instead of one 8-byte load per entry cuts the LSU data-pipe work of the pass by U. */
+template <int U, bool VEC>
+__device__ __forceinline__ void load_entries(const int2 *p, int2 (&e)[U])
+{
+    if constexpr (VEC && U == 4) {
+        asm("ld.global.nc.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=r"(e[0].x), "=r"(e[0].y), "=r"(e[1].x), "=r"(e[1].y), "=r"(e[2].x), "=r"(e[2].y),
+              "=r"(e[3].x), "=r"(e[3].y)
+            : "l"(p));
+    } else if constexpr (VEC && U == 2) {
+        const int4 v = __ldg(reinterpret_cast<const int4 *>(p));
+        e[0] = make_int2(v.x, v.y);
+        e[1] = make_int2(v.z, v.w);
+    } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) e[u] = __ldg(p + u);
+    }
 }
 
 /* Sum over the G lanes of a group; every lane of the group receives the total.
@@ -287,6 +348,16 @@ __device__ __forceinline__ void pass_block(const PassArgs &a, const int2 (&e)[U]
             for (int q = 0; q < KV; ++q) g[u][q] = ldg_f4_bytes(row + lane_off[q]);
         }
     }
+#if PLSA_PACKED_MATH
+    f32x2 own2[KV][2], acc2[KV][2];
+#pragma unroll
+    for (int q = 0; q < KV; ++q) {
+        own2[q][0] = pk2(own[q].x, own[q].y);
+        own2[q][1] = pk2(own[q].z, own[q].w);
+        acc2[q][0] = pk2(acc[q].x, acc[q].y);
+        acc2[q][1] = pk2(acc[q].z, acc[q].w);
+    }
+#endif
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         float x = __int_as_float(e[u].y);
@@ -295,10 +366,15 @@ __device__ __forceinline__ void pass_block(const PassArgs &a, const int2 (&e)[U]
 #pragma unroll
         for (int q = 0; q < KV; ++q) {
             float4 v;
+#if PLSA_PACKED_MATH
+            upk2(mul2(pk2(g[u][q].x, g[u][q].y), own2[q][0]), v.x, v.y);
+            upk2(mul2(pk2(g[u][q].z, g[u][q].w), own2[q][1]), v.z, v.w);
+#else
             v.x = g[u][q].x * own[q].x;
             v.y = g[u][q].y * own[q].y;
             v.z = g[u][q].z * own[q].z;
             v.w = g[u][q].w * own[q].w;
+#endif
             if constexpr (MODE != MODE_LOGLIK) { /* plsa.py:98-102 */
                 v.x = v.x > thresh ? v.x : 0.f;
                 v.y = v.y > thresh ? v.y : 0.f;
@@ -306,7 +382,13 @@ __device__ __forceinline__ void pass_block(const PassArgs &a, const int2 (&e)[U]
                 v.w = v.w > thresh ? v.w : 0.f;
             }
             g[u][q] = v;
+#if PLSA_PACKED_MATH
+            float s_lo, s_hi;
+            upk2(add2(pk2(v.x, v.y), pk2(v.z, v.w)), s_lo, s_hi);
+            const float s4 = s_lo + s_hi;
+#else
             const float s4 = (v.x + v.y) + (v.z + v.w);
+#endif
             part = (q == 0) ? s4 : part + s4;
         }
         const float norm = group_sum<G>(part, gbase, j);
@@ -325,6 +407,14 @@ __device__ __forceinline__ void pass_block(const PassArgs &a, const int2 (&e)[U]
              * or normal; norm == 0 gives x * inf (or NaN), clamped to a finite c that
              * multiplies v == 0. */
             const float c = fminf(x * rcp_fast(norm), 3.0e38f);
+#if PLSA_PACKED_MATH
+            const f32x2 c2 = pk2(c, c);
+#pragma unroll
+            for (int q = 0; q < KV; ++q) {
+                acc2[q][0] = fma2(c2, pk2(g[u][q].x, g[u][q].y), acc2[q][0]);
+                acc2[q][1] = fma2(c2, pk2(g[u][q].z, g[u][q].w), acc2[q][1]);
+            }
+#else
 #pragma unroll
             for (int q = 0; q < KV; ++q) {
                 acc[q].x = fmaf(c, g[u][q].x, acc[q].x);
@@ -332,16 +422,27 @@ __device__ __forceinline__ void pass_block(const PassArgs &a, const int2 (&e)[U]
                 acc[q].z = fmaf(c, g[u][q].z, acc[q].z);
                 acc[q].w = fmaf(c, g[u][q].w, acc[q].w);
             }
+#endif
         }
     }
+#if PLSA_PACKED_MATH
+#pragma unroll
+    for (int q = 0; q < KV; ++q) {
+        upk2(acc2[q][0], acc[q].x, acc[q].y);
+        upk2(acc2[q][1], acc[q].z, acc[q].w);
+    }
+#endif
 }
 
-template <int G, int KV, int MODE, bool TEX>
+/* entries of an item in flight = the entry block aligned items start on */
+__host__ __device__ constexpr int pass_block_entries(int KV) { return (KV >= 4) ? 1 : (KV == 2) ? 2 : 4; }
+
+template <int G, int KV, int MODE, bool TEX, bool VEC>
 __global__ void __launch_bounds__(256, (KV == 1) ? 4 : (KV == 2) ? 2 : 1)
     row_pass_kernel(const PassArgs a)
 {
     constexpr int NG = 32 / G;
-    constexpr int U = (KV >= 4) ? 1 : (KV == 2) ? 2 : 4;   /* entries of an item in flight */
+    constexpr int U = pass_block_entries(KV);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -355,7 +456,7 @@ __global__ void __launch_bounds__(256, (KV == 1) ? 4 : (KV == 2) ? 2 : 1)
     const int64_t item_id = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * NG + grp;
     const bool has = item_id < a.n_items;
     Item it;
-    it.start = 0; it.row = 0; it.len = 0; it.slot = -1; it.pad = 0;
+    it.start = 0; it.row = 0; it.len = 0; it.slot = -1; it.skip = 0;
     if (has) it = a.items[item_id];
 
     int maxlen = it.len;
@@ -398,12 +499,14 @@ __global__ void __launch_bounds__(256, (KV == 1) ? 4 : (KV == 2) ? 2 : 1)
      * without the register rotation, an unpredicated main loop, two-deep software pipelining
      * of the gathers, L1 prefetch of the next rows — profiles/r1_kernel_experiments.md.) */
     int2 e[U];
+    load_entries<U, VEC>(ent, e);
+    if constexpr (VEC && U > 1) { /* entries before the row's first one: value 0 */
 #pragma unroll
-    for (int u = 0; u < U; ++u) e[u] = __ldg(ent + u);
+        for (int u = 0; u < U - 1; ++u) e[u].y = (u < it.skip) ? 0 : e[u].y;
+    }
     for (int base = 0; base < maxlen; base += U) {
         int2 en[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) en[u] = __ldg(ent + base + U + u);
+        load_entries<U, VEC>(ent + base + U, en);
         pass_block<G, KV, U, MODE, TEX, true>(a, e, base, len, gat_base, lane_off, stride_bytes,
                                               own, acc, ll_acc, rw, thresh, j, gbase, lane_on);
 #pragma unroll
