@@ -262,6 +262,97 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def run_shard(args, plumb, rank, world, device):
+    """--mode shard, N > 1: one fit of the whole corpus, documents sharded over the ranks
+    (include/plsa_b200.h plsa_set_shard); strong scaling."""
+    import types
+    from enstop_b200 import _lib, plsa, synth
+    cfg = synth.CONFIGS[args.config]
+    k = cfg["k"]
+    X, info = synth.make_config(args.config, return_info=True)
+    n, m = X.shape
+    bounds = plsa.shard_rows(X.indptr, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    Xs = X[lo:hi]
+    uid = plumb.bcast_bytes(_lib.Comm.unique_id() if rank == 0 else None)
+    comm = _lib.Comm(device, world, rank, uid)
+    rng = np.random.RandomState(42)
+    pzd0, pwz0 = plsa.plsa_init(types.SimpleNamespace(shape=(n, m)), k, "random", rng)
+    ctx = _lib.Context(device)
+    ctx.upload_csr(Xs)
+    ctx.set_shard(comm)
+    ctx.set_factors(pzd0[lo:hi].astype(np.float32), pwz0.astype(np.float32))
+    ctx.set_sample_weight(None)
+    ctx.em(args.warmup, n_iter_per_test=10, tolerance=0.0)
+    sampler = ClockSampler(device)
+    sampler.start()
+    time.sleep(0.25)
+    plumb.barrier()
+    launches0 = ctx.launches
+    t0 = time.time()
+    iters, trace = ctx.em(args.steps, n_iter_per_test=10, tolerance=0.0)
+    em_ms_local = ctx.last_em_ms
+    t1 = time.time()
+    plumb.barrier()
+    launches = plumb.sum(ctx.launches - launches0)
+    clocks = sampler.stop(t0, t1)
+    assert iters == args.steps
+    em_ms = plumb.max(em_ms_local)
+    value = float(X.nnz) * k * args.steps / (em_ms * 1e-3)
+    ctx.set_profiling(True)
+    ctx.em(args.profile_iters, n_iter_per_test=10, tolerance=0.0)
+    prof = ctx.profile()
+    ctx.set_profiling(False)
+    kernel_ms = {s: plumb.max(prof[s]["ms"] / args.profile_iters) for s in prof}
+
+    # end to end: the public call, host buffers, every rank fits its shard (rank 0 reports)
+    sw = np.ones(hi - lo, dtype=np.float32)
+
+    def e2e_call(n_iter):
+        return plsa.plsa_fit_shard(Xs, k, pzd0[lo:hi], pwz0, sw, comm, device, n_iter=n_iter,
+                                   tolerance=0.0)
+    e2e_call(3)
+    runs = []
+    for _ in range(args.e2e_repeats):
+        plumb.barrier()
+        w0 = time.perf_counter()
+        e2e_call(args.steps)
+        dt = time.perf_counter() - w0
+        plumb.barrier()
+        runs.append(plumb.max(dt))
+    e2e_s = statistics.median(runs)
+    ctx.set_shard(None)
+    ctx.close()
+    comm.close()
+    if rank == 0:
+        b_iter, _ = algorithmic_bytes(n, m, X.nnz, k)
+        peak, peak_src = load_peaks()
+        line = {
+            "metric": METRIC % k, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": em_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args.config, cfg, info), "n_docs": n, "n_terms": m,
+                       "nnz": int(X.nnz), "k": k, "shard_bounds": bounds,
+                       "parallelism": "ONE fit, documents sharded over %d GPUs, raw P(w|z) sums "
+                                      "all-reduced (NCCL) once per EM iteration" % world,
+                       "ll_first_last": [float(trace[0]), float(trace[-1])]},
+            "roofline": {"bound": "hbm", "achieved": b_iter / (em_ms / args.steps * 1e-3) / 1e9,
+                         "peak": peak * world, "unit": "GB/s",
+                         "frac": b_iter / (em_ms / args.steps * 1e-3) / 1e9 / (peak * world),
+                         "peak_source": peak_src + " x n_gpus", "traffic": None,
+                         "kernel": "whole EM iteration, aggregate over the GPUs",
+                         "kernel_ms_per_iter_max_over_ranks": kernel_ms},
+            "cpu_baseline": None,
+            "e2e": {"value": float(X.nnz) * k * args.steps / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": (8 * X.nnz + 4 * (n + world) + 4 * k * (n + m * world)) / args.steps,
+                    "d2h_bytes_per_step": 4 * k * (n + m * world) / args.steps, "seconds": e2e_s,
+                    "call": "plsa_fit_shard per rank (upload shard, set factors, EM, download)"},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+
+
 def workload_name(name, cfg, info):
     return ("%s: PLSA(n_components=%d) EM on synthetic Zipf(s=1) token-sampled CSR %dx%d, "
             "%d stored entries (seed %d, %d tokens)"
@@ -275,6 +366,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C5"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="ensemble", choices=["ensemble", "shard"],
+                    help="N > 1: 'ensemble' = one bootstrapped member per GPU (weak scaling, the "
+                         "BASELINE.json multi-GPU config); 'shard' = ONE fit, documents sharded "
+                         "over the GPUs, P(w|z) all-reduced per EM iteration (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-iters", type=int, default=10)
     ap.add_argument("--profile-iters", type=int, default=20)
@@ -292,6 +387,10 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     plumb = Plumbing(rank, world)
     device = local % _lib.device_count()
+    if world > 1 and args.mode == "shard":
+        run_shard(args, plumb, rank, world, device)
+        plumb.close()
+        return
     cfg = synth.CONFIGS[args.config]
     k = cfg["k"]
     X, info = synth.make_config(args.config, return_info=True)

@@ -76,6 +76,7 @@ SIGNATURES = {
                                         ctypes.POINTER(ctypes.c_void_p)]),
     "plsa_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "plsa_comm_gather_topics": (ctypes.c_int, [ctypes.c_void_p, _ctx, _i32p, _i32, _f32p]),
+    "plsa_set_shard": (ctypes.c_int, [_ctx, ctypes.c_void_p]),
 }
 
 _lib = None
@@ -340,6 +341,13 @@ class Context:
 
     def set_option(self, name, value):
         check(self._L.plsa_set_option(self._h, name.encode(), int(value)), self._h)
+
+    def set_shard(self, comm):
+        """Attach (or, with None, detach) the communicator of a document-sharded fit: this
+        context holds one shard of the rows; plsa_em adds the shards' P(w|z) sums and
+        log-likelihoods over it."""
+        check(self._L.plsa_set_shard(self._h, comm._h if comm is not None else None), self._h)
+        self._shard = comm   # keep the communicator alive while attached
 
     def stash_topics(self, slot, n_slots):
         check(self._L.plsa_stash_topics(self._h, int(slot), int(n_slots)), self._h)

@@ -126,6 +126,11 @@ struct plsa_ctx {
     int curA = 0, curB = 0;
     bool have_factors = false, have_sw = false;
 
+    /* document-sharded fit: this context holds one shard of the documents; the ranks' raw
+     * P(w|z) sums and log-likelihoods are added over `shard` (NCCL) inside plsa_em */
+    plsa_comm *shard = nullptr;
+    DevBuf ll2, colpart2;
+
     /* measurement */
     float last_em_ms = 0.f;
     int64_t launches = 0;
@@ -270,6 +275,10 @@ static void prof_collect(plsa_ctx *ctx)
     }
     ctx->prof_pending.clear();
 }
+
+/* ---- document-sharded fit: collectives over the shard communicator (defined with the NCCL
+ * bindings at the end of this file) ------------------------------------------------------------ */
+static int shard_allreduce(plsa_ctx *ctx, void *buf, size_t count, bool f64, cudaStream_t stream);
 
 /* ---- kernel dispatch ------------------------------------------------------------------------ */
 typedef void (*pass_fn)(const PassArgs);
@@ -612,7 +621,7 @@ API int plsa_ctx_destroy(plsa_ctx *ctx)
                       &ctx->term_items.slot_begin, &ctx->A[0], &ctx->A[1], &ctx->B[0], &ctx->B[1],
                       &ctx->scale, &ctx->ones, &ctx->colnorm, &ctx->colpart, &ctx->partialA,
                       &ctx->partialB, &ctx->sw, &ctx->ll_part, &ctx->ll_out, &ctx->stage, &ctx->tickets,
-                      &ctx->topics_dev})
+                      &ctx->topics_dev, &ctx->ll2, &ctx->colpart2})
         b->release();
     for (int i = 0; i < 2; ++i) {
         if (ctx->texA[i]) cudaDestroyTextureObject(ctx->texA[i]);
@@ -993,6 +1002,8 @@ static int run_loglik(plsa_ctx *ctx, double *out)
         a.kp = ctx->kp;
         if ((rc = launch_pass(ctx, MODE_LOGLIK, a, ctx->doc_items.align > 1))) return rc;
     }
+    /* sharded fit: sum of the shards' log-likelihoods, same value on all ranks */
+    if (ctx->shard && (rc = shard_allreduce(ctx, ctx->ll_out.p, 1, true, ctx->stream))) return rc;
     CK(cudaMemcpyAsync(out, ctx->ll_out.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return PLSA_OK;
@@ -1115,6 +1126,18 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
      * and join before the next iteration.  Per-kernel profiling keeps them serial. */
     const bool two = ctx->overlap && !refit && !ctx->profiling;
     cudaStream_t s1 = ctx->stream, s2 = two ? ctx->stream2 : ctx->stream;
+    /* Document-sharded fit: the doc pass is local; the term pass leaves this shard's raw
+     * P(w|z)^T sums, which are added over the ranks (all-reduce on s2, behind the term pass,
+     * while the doc pass still runs on s1), then the column sums are taken from the complete
+     * matrix.  Every collective of this context is issued on s2, in the same order on all
+     * ranks; the log-likelihood is the sum of the shards' values, so all ranks take the
+     * same stop decision. */
+    const bool sharded = ctx->shard != nullptr; /* one rank: same path, empty collectives */
+    const int colsum_grid = 148;
+    if (sharded) {
+        CK(ctx->ll2.ensure(16));
+        CK(ctx->colpart2.ensure((size_t)colsum_grid * kp * 8));
+    }
     for (int32_t i = 0; i < n_iter; ++i) {
         const int nA = ctx->curA ^ 1, nB = ctx->curB ^ 1;
         const bool fused_now = fuse && (i == 0 || (i - 1) % n_iter_per_test == 0);
@@ -1148,11 +1171,12 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
             }
             if ((rc = launch_pass(ctx, fused_now ? MODE_DOC_LL : MODE_DOC, a, ctx->doc_items.align > 1)))
                 return rc;
-            if (fused_now) {
+            if (fused_now && !sharded) {
                 CK(cudaMemcpyAsync(&ctx->mail[0], ctx->ll_out.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
                 CK(cudaMemcpyAsync(&ctx->mail[1], ctx->flag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
                 CK(cudaEventRecord(ctx->ev_ll, ctx->stream));
             }
+            if (fused_now && sharded) CK(cudaEventRecord(ctx->ev_a, s1)); /* doc pass done */
         }
         if ((rc = run_fixup(ctx, 0, ctx->A[nA].as<float>(), s1))) return rc;
         if (!refit) {
@@ -1181,6 +1205,31 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
             }
             /* split rows: ordered sums of their chunk partials */
             if ((rc = run_fixup(ctx, 1, ctx->B[nB].as<float>(), s2))) return rc;
+            if (sharded) {
+                ProfScope ps(ctx, PLSA_PROF_NORMALIZE, s2);
+                if ((rc = shard_allreduce(ctx, ctx->B[nB].p, (size_t)c.m * ctx->strideB, false, s2)))
+                    return rc;
+                if (c.m > 0) {
+                    colsum_partial_kernel<<<colsum_grid, 256, 0, s2>>>(
+                        ctx->B[nB].as<float>(), c.m, ctx->strideB, kp, ctx->colpart2.as<double>());
+                    colsum_final_kernel<<<1, 256, 0, s2>>>(
+                        ctx->colpart2.as<double>(), colsum_grid, kp,
+                        reinterpret_cast<float *>(ctx->scale.p) + (size_t)nB * kp,
+                        ctx->colnorm.as<double>());
+                    ctx->launches += 2;
+                    CK(cudaGetLastError());
+                }
+            }
+            if (fused_now && sharded) { /* {log-likelihood, flag} summed over the shards */
+                CK(cudaStreamWaitEvent(s2, ctx->ev_a, 0));
+                pack_ll_kernel<<<1, 1, 0, s2>>>(ctx->ll_out.as<double>(), ctx->flag.as<int>(),
+                                                ctx->ll2.as<double>());
+                ctx->launches++;
+                CK(cudaGetLastError());
+                if ((rc = shard_allreduce(ctx, ctx->ll2.p, 2, true, s2))) return rc;
+                CK(cudaMemcpyAsync(ctx->mail, ctx->ll2.p, 16, cudaMemcpyDeviceToHost, s2));
+                CK(cudaEventRecord(ctx->ev_ll, s2));
+            }
             if (two) {
                 CK(cudaEventRecord(ctx->ev_b, s2));
                 CK(cudaStreamWaitEvent(s1, ctx->ev_b, 0)); /* join */
@@ -1191,7 +1240,8 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
             double v;
             int bad;
             memcpy(&v, &ctx->mail[0], 8);
-            memcpy(&bad, &ctx->mail[1], 4);
+            if (sharded) bad = ctx->mail[1] != 0.0; /* any shard's flag */
+            else memcpy(&bad, &ctx->mail[1], 4);
             if (bad && (rc = run_loglik(ctx, &v))) return rc; /* exact pass on the same factors */
             if (i == 0) { /* plsa.py:591, the value before the loop */
                 prev = v;
@@ -1387,6 +1437,7 @@ typedef int (*fn_GroupStart)(void);
 typedef int (*fn_GroupEnd)(void);
 typedef int (*fn_Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t);
 typedef int (*fn_Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t);
+typedef int (*fn_AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
 typedef const char *(*fn_GetErrorString)(int);
 struct Nccl {
     void *h = nullptr;
@@ -1398,9 +1449,12 @@ struct Nccl {
     fn_GroupEnd GroupEnd;
     fn_Send Send;
     fn_Recv Recv;
+    fn_AllReduce AllReduce;
     fn_GetErrorString GetErrorString;
 };
-const int kNcclFloat = 7; /* ncclFloat32 */
+const int kNcclFloat = 7;  /* ncclFloat32 */
+const int kNcclDouble = 8; /* ncclFloat64 */
+const int kNcclSum = 0;    /* ncclSum */
 
 static Nccl *load_nccl()
 {
@@ -1421,9 +1475,10 @@ static Nccl *load_nccl()
     n.GroupEnd = (fn_GroupEnd)dlsym(n.h, "ncclGroupEnd");
     n.Send = (fn_Send)dlsym(n.h, "ncclSend");
     n.Recv = (fn_Recv)dlsym(n.h, "ncclRecv");
+    n.AllReduce = (fn_AllReduce)dlsym(n.h, "ncclAllReduce");
     n.GetErrorString = (fn_GetErrorString)dlsym(n.h, "ncclGetErrorString");
     if (!n.GetUniqueId || !n.CommInitRank || !n.CommInitAll || !n.CommDestroy ||
-        !n.GroupStart || !n.GroupEnd || !n.Send || !n.Recv) {
+        !n.GroupStart || !n.GroupEnd || !n.Send || !n.Recv || !n.AllReduce) {
         dlclose(n.h);
         n.h = nullptr;
         return nullptr;
@@ -1596,6 +1651,34 @@ API int plsa_comm_create(int device, int32_t n_ranks, int32_t rank, const char *
         }
     }
     *out = c;
+    return PLSA_OK;
+}
+
+/* ---- document-sharded fit ------------------------------------------------------------------------- */
+/* in-place sum over the ranks of the shard communicator (float32 or float64) */
+static int shard_allreduce(plsa_ctx *ctx, void *buf, size_t count, bool f64, cudaStream_t stream)
+{
+    plsa_comm *c = ctx->shard;
+    if (!c || c->n_ranks < 2 || count == 0) return PLSA_OK;
+    Nccl *nc = load_nccl();
+    if (!nc) return ctx->fail(PLSA_ENCCL, "sharded fit: libnccl.so.2 could not be loaded");
+    const int r = nc->AllReduce(buf, buf, count, f64 ? kNcclDouble : kNcclFloat, kNcclSum, c->comm,
+                                stream);
+    ctx->launches++;
+    if (r != 0) {
+        const int rc = nccl_fail(nc, "sharded fit: ncclAllReduce", r);
+        ctx->err = g_err;
+        return rc;
+    }
+    return PLSA_OK;
+}
+
+API int plsa_set_shard(plsa_ctx *ctx, plsa_comm *comm)
+{
+    CHECK_CTX(ctx);
+    if (comm && comm->device != ctx->device)
+        return ctx->fail(PLSA_EINVAL, "set_shard: context and communicator devices differ");
+    ctx->shard = comm;
     return PLSA_OK;
 }
 

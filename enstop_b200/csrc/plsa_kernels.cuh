@@ -652,6 +652,58 @@ __global__ void __launch_bounds__(256) fixup_kernel(const FixArgs fa, const FixA
     }
 }
 
+/* ---- column sums of a whole factor (document-sharded fits) ----------------------------- */
+/* After the ranks' raw P(w|z)^T partial sums have been added (all-reduce), the per-topic
+ * normaliser (plsa.py:196-198) is the column sum of the full matrix.  Two launches, fixed
+ * summation order: each CTA adds a contiguous slice of rows in float64, one CTA adds the
+ * per-CTA values in index order.  Every rank runs it on identical input -> identical scale. */
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float *__restrict__ mat,
+                                                             int64_t rows, int stride, int kp,
+                                                             double *__restrict__ part /*[grid, kp]*/)
+{
+    __shared__ double sm[256];
+    const int64_t per = (rows + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(rows, r0 + per);
+    if (kp <= 256) { /* 256 / kp rows at a time, kp consecutive threads along a row */
+        const int nsub = 256 / kp, sub = (int)threadIdx.x / kp, z = (int)threadIdx.x - sub * kp;
+        double t = 0.0;
+        if (sub < nsub)
+            for (int64_t r = r0 + sub; r < r1; r += nsub) t += (double)mat[r * stride + z];
+        sm[threadIdx.x] = t;
+        __syncthreads();
+        if ((int)threadIdx.x < kp) {
+            double acc = 0.0;
+            for (int q = 0; q < nsub; ++q) acc += sm[q * kp + threadIdx.x];
+            part[(int64_t)blockIdx.x * kp + threadIdx.x] = acc;
+        }
+    } else {
+        for (int z = threadIdx.x; z < kp; z += 256) {
+            double t = 0.0;
+            for (int64_t r = r0; r < r1; ++r) t += (double)mat[r * stride + z];
+            part[(int64_t)blockIdx.x * kp + z] = t;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) colsum_final_kernel(const double *__restrict__ part, int n_part,
+                                                           int kp, float *__restrict__ scale_out,
+                                                           double *__restrict__ colnorm_out)
+{
+    for (int z = threadIdx.x; z < kp; z += blockDim.x) {
+        double t = 0.0;
+        for (int i = 0; i < n_part; ++i) t += part[(int64_t)i * kp + z];
+        colnorm_out[z] = t;
+        scale_out[z] = t > 0.0 ? (float)(1.0 / t) : 1.f;
+    }
+}
+
+/* {log-likelihood, flag} -> two doubles, so that one sum all-reduce carries both */
+__global__ void pack_ll_kernel(const double *ll, const int *flag, double *out2)
+{
+    out2[0] = *ll;
+    out2[1] = flag ? (double)*flag : 0.0;
+}
+
 /* ---- layout conversion between the reference's arrays and the device layout ---------- */
 /* dense [rows, k] -> padded [rows, stride] (P(z|d); also P(w|z)^T when src is [k, rows]) */
 __global__ void pack_rows_kernel(const float *__restrict__ src, float *__restrict__ dst,

@@ -145,14 +145,118 @@ class _Staging:
             self.ctx = None
 
 
+def shard_rows(indptr, n_shards):
+    """Row boundaries [b_0 = 0, ..., b_G = n] of G contiguous document shards with (nearly)
+    equal numbers of stored entries and at least one document each."""
+    indptr = np.asarray(indptr)
+    n = len(indptr) - 1
+    n_shards = int(n_shards)
+    if n_shards < 1 or n < n_shards:
+        raise ValueError("cannot cut {} documents into {} shards".format(n, n_shards))
+    targets = indptr[-1] * np.arange(1, n_shards, dtype=np.float64) / n_shards
+    cuts = np.searchsorted(indptr, targets, side="left")
+    bounds = [0]
+    for g, c in enumerate(cuts, start=1):     # strictly increasing, room left for the rest
+        bounds.append(int(min(max(c, bounds[-1] + 1), n - (n_shards - g))))
+    bounds.append(n)
+    return bounds
+
+
+def plsa_fit_shard(X_rows, k, p_z_given_d_rows, p_w_given_z, sample_weight_rows, comm, device,
+                   n_iter=100, n_iter_per_test=10, tolerance=0.001, e_step_thresh=1e-32,
+                   use_sample_weights=False, profile=False):
+    """One rank of a document-sharded fit: this rank's rows of X and of P(z|d), the full
+    P(w|z), the shard communicator (``_lib.Comm``).  Every rank calls it with the same scalar
+    arguments.  Returns (P(z|d) rows, full P(w|z), info)."""
+    ctx = _lib.Context(device)
+    try:
+        ctx.upload_csr(_as_csr(X_rows))
+        ctx.set_shard(comm)
+        ctx.set_factors(np.ascontiguousarray(p_z_given_d_rows, dtype=np.float32),
+                        np.ascontiguousarray(p_w_given_z, dtype=np.float32))
+        ctx.set_sample_weight(sample_weight_rows if use_sample_weights else None)
+        ctx.prepare(k, False)
+        if profile:
+            ctx.set_profiling(True)
+        iters, trace = ctx.em(n_iter, n_iter_per_test, tolerance, e_step_thresh, refit=False,
+                              use_sample_weights=use_sample_weights)
+        pzd, pwz = ctx.get_factors()
+        info = {"n_iter": iters, "ll_trace": trace, "em_ms": ctx.last_em_ms,
+                "launches": ctx.launches, "profile": ctx.profile() if profile else None}
+        ctx.set_shard(None)
+    finally:
+        ctx.close()
+    return pzd, pwz, info
+
+
+def _plsa_fit_sharded(X, k, sample_weight, init, n_iter, n_iter_per_test, tolerance,
+                      e_step_thresh, random_state, devices):
+    """plsa_fit over several GPUs of one box: one host thread, context and NCCL rank per
+    device, documents cut into contiguous shards of equal stored entries."""
+    X = _as_csr(X)
+    n, m = X.shape
+    rng = check_random_state(random_state)
+    fast = _random_init_f32(n, m, k, rng) if isinstance(init, str) and init == "random" else None
+    if fast is not None:
+        p_z_given_d, p_w_given_z = fast
+    else:
+        p_z_given_d, p_w_given_z = plsa_init(X, k, init=init, rng=rng)
+        p_z_given_d = p_z_given_d.astype(np.float32, order="C")
+        p_w_given_z = p_w_given_z.astype(np.float32, order="C")
+    sample_weight = np.asarray(sample_weight, dtype=np.float32)
+    use_sw = bool(np.any(sample_weight != 1.0))
+    G = len(devices)
+    bounds = shard_rows(X.indptr, G)
+    uid = _lib.Comm.unique_id()
+    results, errors = [None] * G, [None] * G
+
+    def worker(r):
+        comm = None
+        try:
+            comm = _lib.Comm(devices[r], G, r, uid)
+            lo, hi = bounds[r], bounds[r + 1]
+            results[r] = plsa_fit_shard(X[lo:hi], k, p_z_given_d[lo:hi], p_w_given_z,
+                                        sample_weight[lo:hi], comm, devices[r], n_iter,
+                                        n_iter_per_test, tolerance, e_step_thresh, use_sw)
+        except BaseException as exc:
+            errors[r] = exc
+        finally:
+            if comm is not None:
+                comm.close()
+
+    threads = [threading.Thread(target=worker, args=(r,)) for r in range(G)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for e in errors:
+        if e is not None:
+            raise e
+    iters = {res[2]["n_iter"] for res in results}
+    if len(iters) != 1:
+        raise _lib.PlsaError("sharded fit: ranks disagree on the iteration count {}".format(iters))
+    info = dict(results[0][2])
+    info["em_ms"] = max(res[2]["em_ms"] for res in results)
+    info["launches"] = sum(res[2]["launches"] for res in results)
+    info["shard_bounds"] = bounds
+    return np.concatenate([res[0] for res in results]), results[0][1], info
+
+
 def plsa_fit(X, k, sample_weight, init="random", n_iter=100, n_iter_per_test=10,
              tolerance=0.001, e_step_thresh=1e-32, random_state=None, *, device=None,
-             context=None, return_info=False):
+             context=None, return_info=False, devices=None):
     """Fit pLSA with ``k`` topics; returns ``(p_z_given_d [n,k], p_w_given_z [k,m])`` float32.
 
     Drop-in for enstop.plsa.plsa_fit (plsa.py:643-730).  ``context`` (an
     ``enstop_b200._lib.Context`` whose resident corpus is X) skips the upload — used by the
-    ensemble for its bootstrapped members."""
+    ensemble for its bootstrapped members.  ``devices`` (a list of two or more CUDA ordinals)
+    shards the documents of this one fit over those GPUs."""
+    if devices is not None and len(devices) > 1:
+        out = _plsa_fit_sharded(X, k, sample_weight, init, n_iter, n_iter_per_test, tolerance,
+                                e_step_thresh, random_state, [int(d) for d in devices])
+        return out if return_info else out[:2]
+    if devices is not None and len(devices) == 1 and device is None:
+        device = int(devices[0])
     staging = _Staging(X, k, device, context, refit=False)
     try:
         rng = check_random_state(random_state)
@@ -220,7 +324,9 @@ class PLSA(BaseEstimator, TransformerMixin):
     ``init="random"`` (``"random"``, ``"nndsvd"``, ``"nmf"`` or a tuple of arrays),
     ``n_iter=100``, ``n_iter_per_test=10``, ``tolerance=0.001``, ``e_step_thresh=1e-32``,
     ``transform_random_seed=42``, ``random_state=None``; plus ``device`` (CUDA ordinal,
-    default ``$ENSTOP_B200_DEVICE`` or 0).
+    default ``$ENSTOP_B200_DEVICE`` or 0) and ``devices`` (two or more ordinals: the
+    documents of the fit are sharded over those GPUs, P(w|z) summed over NVLink once per EM
+    iteration).
 
     Attributes: ``components_`` (P(w|z), [n_topics, n_words] float32), ``embedding_``
     (P(z|d), [n_docs, n_topics]), ``training_data_``; additionally ``n_iter_`` and
@@ -229,7 +335,7 @@ class PLSA(BaseEstimator, TransformerMixin):
 
     def __init__(self, n_components=10, init="random", n_iter=100, n_iter_per_test=10,
                  tolerance=0.001, e_step_thresh=1e-32, transform_random_seed=42,
-                 random_state=None, device=None):
+                 random_state=None, device=None, devices=None):
         self.n_components = n_components
         self.init = init
         self.n_iter = n_iter
@@ -239,6 +345,7 @@ class PLSA(BaseEstimator, TransformerMixin):
         self.transform_random_seed = transform_random_seed
         self.random_state = random_state
         self.device = device
+        self.devices = devices
 
     def fit(self, X, y=None, sample_weight=None):
         self.fit_transform(X, sample_weight=sample_weight)
@@ -272,7 +379,7 @@ class PLSA(BaseEstimator, TransformerMixin):
         U, V, info = plsa_fit(data_for_fitting, self.n_components, sample_weight, self.init,
                               self.n_iter, self.n_iter_per_test, self.tolerance,
                               self.e_step_thresh, self.random_state, device=self.device,
-                              return_info=True)
+                              return_info=True, devices=self.devices)
         if zero_rows_found:
             self.embedding_ = np.zeros((X.shape[0], self.n_components))
             self.embedding_[good_rows] = U

@@ -44,6 +44,7 @@ extern "C" {
 #define PLSA_MAX_K 1024 /* same ceiling as the incumbent GPU path (cuda_plsa.py:135) */
 
 typedef struct plsa_ctx plsa_ctx;
+typedef struct plsa_comm plsa_comm;
 
 /* ---- library / device ------------------------------------------------------------ */
 int plsa_version(void);                      /* 100 * major + minor                   */
@@ -110,7 +111,7 @@ int plsa_last_em_ms(const plsa_ctx *ctx, float *ms);
 #define PLSA_PROF_DOC_PASS 0   /* E-step + P(z|d) M-step over the doc-major copy        */
 #define PLSA_PROF_WORD_PASS 1  /* E-step + P(w|z) M-step + column sums, term-major copy */
 #define PLSA_PROF_FIXUP 2      /* ordered sums of split rows (both factors)            */
-#define PLSA_PROF_NORMALIZE 3  /* unused since the column sums moved into the word pass */
+#define PLSA_PROF_NORMALIZE 3  /* sharded fit: all-reduce of P(w|z) + its column sums   */
 #define PLSA_PROF_LOGLIK 4     /* log-likelihood pass                                  */
 #define PLSA_PROF_SLOTS 5
 int plsa_set_profiling(plsa_ctx *ctx, int32_t on);
@@ -168,13 +169,25 @@ int plsa_gather_topics(plsa_ctx **ctxs, int32_t n_ctx, const int32_t *n_slots, f
  * communicator; plsa_comm_gather_topics sends slots [0, n_per_rank[rank]) of ctx's stash to
  * `root`, which receives them in rank order into `out` (host; ignored on other ranks). */
 #define PLSA_NCCL_ID_BYTES 128
-typedef struct plsa_comm plsa_comm;
 int plsa_nccl_unique_id(char *id /*[PLSA_NCCL_ID_BYTES]*/);
 int plsa_comm_create(int device, int32_t n_ranks, int32_t rank,
                      const char *id /*[PLSA_NCCL_ID_BYTES]*/, plsa_comm **comm);
 int plsa_comm_destroy(plsa_comm *comm);
 int plsa_comm_gather_topics(plsa_comm *comm, plsa_ctx *ctx, const int32_t *n_per_rank,
                             int32_t root, float *out);
+
+/* ---- one fit over several GPUs: documents sharded by rows -------------------------------------
+ * Generalises the row blocking of enstop/block_parallel_plsa.py:156-185 and
+ * enstop/distributed_plsa.py:116-131 (per-block E-step + partial M-step sums, then a sum over
+ * the blocks).  Every rank uploads ITS rows of X as its corpus (plsa_upload_csr*), sets
+ * P(z|d) for its rows and the same full P(w|z) (plsa_set_factors), attaches the communicator
+ * and runs plsa_em with identical arguments: the doc pass is local, the term pass leaves the
+ * shard's raw P(w|z) sums, which are added over the ranks once per EM iteration (NCCL
+ * all-reduce over NVLink, issued behind the term pass so that it overlaps the doc pass); the
+ * log-likelihood is the sum of the shards' values, so every rank takes the same early-stop
+ * decision (plsa.py:630-638).  plsa_get_factors returns the rank's rows of P(z|d) and the
+ * full P(w|z).  comm == NULL detaches.  Every shard must hold at least one document. */
+int plsa_set_shard(plsa_ctx *ctx, plsa_comm *comm);
 
 #ifdef __cplusplus
 }

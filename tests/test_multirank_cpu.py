@@ -28,6 +28,36 @@ def test_two_ranks_gloo():
     assert "MULTIRANK_OK 2" in res.stdout
 
 
+def test_sharded_em_two_ranks_gloo():
+    """Document-sharded EM: local E-step + all-reduced P(w|z) sums == the unsharded oracle."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(ROOT, "tests", "_shard_worker.py")]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                         timeout=240, env=env, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-3000:]
+    assert "SHARDED_EM_OK 2" in res.stdout
+
+
+def test_shard_rows():
+    from enstop_b200.plsa import shard_rows
+    ip = np.concatenate([[0], np.cumsum(np.random.RandomState(0).randint(0, 50, size=1000))])
+    for g in (1, 2, 3, 8):
+        b = shard_rows(ip, g)
+        assert b[0] == 0 and b[-1] == 1000 and len(b) == g + 1
+        assert all(b[i] < b[i + 1] for i in range(g))
+        sizes = [ip[b[i + 1]] - ip[b[i]] for i in range(g)]
+        assert max(sizes) - min(sizes) <= 100          # within two rows of equal entries
+    assert shard_rows(np.array([0, 0, 0, 5]), 3) == [0, 1, 2, 3]   # every shard gets a row
+    assert shard_rows(np.array([0, 5, 5, 5]), 3) == [0, 1, 2, 3]
+    try:
+        shard_rows(np.array([0, 1, 2]), 3)
+        assert False
+    except ValueError:
+        pass
+
+
 def test_reference_arm_other_ranks_do_nothing():
     """bench.py --impl reference under torchrun: rank 0 alone works, the others exit 0."""
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
