@@ -151,6 +151,13 @@ class Plumbing:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return float(t[0])
 
+    def allgather(self, obj):
+        if not self.dist:
+            return [obj]
+        box = [None] * self.world
+        self.dist.all_gather_object(box, obj)
+        return box
+
     def bcast_bytes(self, payload):
         if not self.dist:
             return payload
@@ -283,6 +290,30 @@ def run_shard(args, plumb, rank, world, device):
     ctx.set_shard(comm)
     ctx.set_factors(pzd0[lo:hi].astype(np.float32), pwz0.astype(np.float32))
     ctx.set_sample_weight(None)
+
+    def exchange(c, r):
+        """peer-memory all-reduce between processes: CUDA IPC handles through the launcher"""
+        if args.no_p2p:
+            return False
+        try:
+            c.shard_p2p_prepare()
+            mine = c.shard_p2p_export()
+        except _lib.PlsaError:
+            mine = None
+        handles = plumb.allgather(mine)
+        ok = all(h is not None for h in handles)
+        if ok:
+            try:
+                for p, h in enumerate(handles):
+                    if p != r:
+                        c.shard_p2p_attach(p, -1, handle=h)
+            except _lib.PlsaError:
+                ok = False
+        ok = all(plumb.allgather(ok))
+        if not ok:
+            c.set_option("p2p", 0)
+        return ok
+    p2p = exchange(ctx, rank)
     ctx.em(args.warmup, n_iter_per_test=10, tolerance=0.0)
     sampler = ClockSampler(device)
     sampler.start()
@@ -310,7 +341,7 @@ def run_shard(args, plumb, rank, world, device):
 
     def e2e_call(n_iter):
         return plsa.plsa_fit_shard(Xs, k, pzd0[lo:hi], pwz0, sw, comm, device, n_iter=n_iter,
-                                   tolerance=0.0)
+                                   tolerance=0.0, exchange=exchange)
     e2e_call(3)
     runs = []
     for _ in range(args.e2e_repeats):
@@ -335,7 +366,9 @@ def run_shard(args, plumb, rank, world, device):
             "config": {"workload": workload_name(args.config, cfg, info), "n_docs": n, "n_terms": m,
                        "nnz": int(X.nnz), "k": k, "shard_bounds": bounds,
                        "parallelism": "ONE fit, documents sharded over %d GPUs, raw P(w|z) sums "
-                                      "all-reduced (NCCL) once per EM iteration" % world,
+                                      "all-reduced once per EM iteration (%s)"
+                                      % (world, "one kernel per rank over NVLink peer memory, fused "
+                                                "with the column sums" if p2p else "ncclAllReduce"),
                        "ll_first_last": [float(trace[0]), float(trace[-1])]},
             "roofline": {"bound": "hbm", "achieved": b_iter / (em_ms / args.steps * 1e-3) / 1e9,
                          "peak": peak * world, "unit": "GB/s",
@@ -371,6 +404,8 @@ def main():
                          "BASELINE.json multi-GPU config); 'shard' = ONE fit, documents sharded "
                          "over the GPUs, P(w|z) all-reduced per EM iteration (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-p2p", action="store_true", help="--mode shard: ncclAllReduce instead of "
+                                                          "the peer-memory all-reduce kernel")
     ap.add_argument("--cpu-iters", type=int, default=10)
     ap.add_argument("--profile-iters", type=int, default=20)
     ap.add_argument("--e2e-repeats", type=int, default=3)

@@ -77,6 +77,9 @@ SIGNATURES = {
     "plsa_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "plsa_comm_gather_topics": (ctypes.c_int, [ctypes.c_void_p, _ctx, _i32p, _i32, _f32p]),
     "plsa_set_shard": (ctypes.c_int, [_ctx, ctypes.c_void_p]),
+    "plsa_shard_p2p_prepare": (ctypes.c_int, [_ctx, ctypes.POINTER(ctypes.c_uint64), _i64p]),
+    "plsa_shard_p2p_export": (ctypes.c_int, [_ctx, ctypes.c_char_p]),
+    "plsa_shard_p2p_attach": (ctypes.c_int, [_ctx, _i32, _i32, ctypes.c_uint64, ctypes.c_char_p]),
 }
 
 _lib = None
@@ -348,6 +351,26 @@ class Context:
         log-likelihoods over it."""
         check(self._L.plsa_set_shard(self._h, comm._h if comm is not None else None), self._h)
         self._shard = comm   # keep the communicator alive while attached
+
+    def shard_p2p_prepare(self):
+        """Allocate this rank's exchange block of the peer-memory all-reduce (after set_shard
+        and set_factors).  Returns (device address, bytes)."""
+        base, nbytes = ctypes.c_uint64(), _i64()
+        check(self._L.plsa_shard_p2p_prepare(self._h, ctypes.byref(base), ctypes.byref(nbytes)),
+              self._h)
+        return int(base.value), int(nbytes.value)
+
+    def shard_p2p_export(self):
+        """CUDA IPC handle (64 bytes) of the exchange block, for peers in other processes."""
+        buf = ctypes.create_string_buffer(64)
+        check(self._L.plsa_shard_p2p_export(self._h, buf), self._h)
+        return buf.raw
+
+    def shard_p2p_attach(self, peer_rank, peer_device, base=0, handle=None):
+        """Map a peer's exchange block: ``base`` (its device address) when the peer lives in
+        this process, ``handle`` (its IPC handle) otherwise."""
+        check(self._L.plsa_shard_p2p_attach(self._h, int(peer_rank), int(peer_device), int(base),
+                                            handle), self._h)
 
     def stash_topics(self, slot, n_slots):
         check(self._L.plsa_stash_topics(self._h, int(slot), int(n_slots)), self._h)

@@ -130,6 +130,16 @@ struct plsa_ctx {
      * P(w|z) sums and log-likelihoods are added over `shard` (NCCL) inside plsa_em */
     plsa_comm *shard = nullptr;
     DevBuf ll2, colpart2;
+    /* exchange block of the peer-memory all-reduce: [partial 0 | partial 1 | signal words] */
+    struct P2P {
+        DevBuf block, err;
+        size_t part_bytes = 0;
+        void *peer_base[SHARD_MAX_RANKS] = {};
+        bool peer_ipc[SHARD_MAX_RANKS] = {};
+        int n_attached = 0;
+        unsigned int seq = 0;
+        bool enabled = true; /* option "p2p" */
+    } p2p;
 
     /* measurement */
     float last_em_ms = 0.f;
@@ -279,6 +289,9 @@ static void prof_collect(plsa_ctx *ctx)
 /* ---- document-sharded fit: collectives over the shard communicator (defined with the NCCL
  * bindings at the end of this file) ------------------------------------------------------------ */
 static int shard_allreduce(plsa_ctx *ctx, void *buf, size_t count, bool f64, cudaStream_t stream);
+static int shard_n_ranks(const plsa_ctx *ctx);
+static int shard_rank(const plsa_ctx *ctx);
+static void p2p_release(plsa_ctx *ctx);
 
 /* ---- kernel dispatch ------------------------------------------------------------------------ */
 typedef void (*pass_fn)(const PassArgs);
@@ -614,6 +627,7 @@ API int plsa_ctx_destroy(plsa_ctx *ctx)
     for (Corpus *c : {&ctx->base, &ctx->boot}) {
         c->indptr.release(); c->ent.release();
     }
+    p2p_release(ctx);
     for (DevBuf &b : ctx->scratch) b.release();
     for (DevBuf *b : {&ctx->t_ent, &ctx->t_entw, &ctx->up_cols, &ctx->up_vals, &ctx->flag,
                       &ctx->doc_items.items, &ctx->doc_items.split_rows, &ctx->doc_items.slot_begin,
@@ -1138,6 +1152,14 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
         CK(ctx->ll2.ensure(16));
         CK(ctx->colpart2.ensure((size_t)colsum_grid * kp * 8));
     }
+    /* Peer-memory path (plsa_shard_p2p_*): the term pass writes into this rank's exchange
+     * buffer and ONE kernel per rank adds the ranks' buffers over NVLink and takes the column
+     * sums (shard_reduce_kernel); otherwise NCCL all-reduce + separate column sums. */
+    const int n_ranks = sharded ? shard_n_ranks(ctx) : 1;
+    const bool p2p = sharded && !refit && ctx->p2p.enabled && ctx->p2p.block.p &&
+                     ctx->p2p.n_attached == n_ranks - 1 && n_ranks <= SHARD_MAX_RANKS &&
+                     ctx->p2p.part_bytes == (size_t)std::max<int64_t>(c.m, 1) * ctx->strideB * 4;
+    bool p2p_used = false;
     for (int32_t i = 0; i < n_iter; ++i) {
         const int nA = ctx->curA ^ 1, nB = ctx->curB ^ 1;
         const bool fused_now = fuse && (i == 0 || (i - 1) % n_iter_per_test == 0);
@@ -1189,7 +1211,11 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                 a.own_old = ctx->B[ctx->curB].as<float>();
                 a.gat_old = ctx->A[ctx->curA].as<float>();
                 a.own_scale = cur_scale(ctx);
-                a.own_new = ctx->B[nB].as<float>();
+                float *term_out = ctx->B[nB].as<float>();
+                if (p2p) /* exchange buffer (seq + 1) & 1, read by the peers */
+                    term_out = reinterpret_cast<float *>(ctx->p2p.block.as<char>() +
+                                                         ((ctx->p2p.seq + 1) & 1u) * ctx->p2p.part_bytes);
+                a.own_new = term_out;
                 a.partial = ctx->partialB.as<float>();
                 a.gat_tex = ctx->texA[ctx->curA];
                 /* plsa.py:196-198: per-topic normaliser of the new P(w|z), applied lazily */
@@ -1204,8 +1230,41 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                 if ((rc = launch_pass(ctx, MODE_TERM, a, ctx->term_items.align > 1, s2))) return rc;
             }
             /* split rows: ordered sums of their chunk partials */
-            if ((rc = run_fixup(ctx, 1, ctx->B[nB].as<float>(), s2))) return rc;
-            if (sharded) {
+            if ((rc = run_fixup(ctx, 1,
+                                p2p ? reinterpret_cast<float *>(ctx->p2p.block.as<char>() +
+                                                                ((ctx->p2p.seq + 1) & 1u) * ctx->p2p.part_bytes)
+                                    : ctx->B[nB].as<float>(), s2)))
+                return rc;
+            if (p2p && c.m > 0) {
+                ProfScope ps(ctx, PLSA_PROF_NORMALIZE, s2);
+                ctx->p2p.seq += 1;
+                p2p_used = true;
+                ShardReduceArgs ra{};
+                const int me = shard_rank(ctx);
+                char *sig0 = nullptr;
+                for (int p = 0; p < n_ranks; ++p) {
+                    char *base = (p == me) ? ctx->p2p.block.as<char>() : (char *)ctx->p2p.peer_base[p];
+                    ra.part[p] = reinterpret_cast<const float *>(base + (ctx->p2p.seq & 1u) * ctx->p2p.part_bytes);
+                    ra.peer_sig[p] = reinterpret_cast<unsigned int *>(base + 2 * ctx->p2p.part_bytes);
+                    if (p == me) sig0 = base + 2 * ctx->p2p.part_bytes;
+                }
+                ra.my_sig = reinterpret_cast<volatile unsigned int *>(sig0);
+                ra.out = ctx->B[nB].as<float>();
+                ra.colpart = ctx->colpart2.as<double>();
+                ra.err = ctx->p2p.err.as<int>();
+                ra.rows = c.m;
+                ra.stride = ctx->strideB;
+                ra.kp = kp;
+                ra.n_ranks = n_ranks;
+                ra.rank = me;
+                ra.seq = ctx->p2p.seq;
+                shard_reduce_kernel<<<colsum_grid, 256, 0, s2>>>(ra);
+                colsum_final_kernel<<<1, 256, 0, s2>>>(
+                    ctx->colpart2.as<double>(), colsum_grid, kp,
+                    reinterpret_cast<float *>(ctx->scale.p) + (size_t)nB * kp, ctx->colnorm.as<double>());
+                ctx->launches += 2;
+                CK(cudaGetLastError());
+            } else if (sharded) {
                 ProfScope ps(ctx, PLSA_PROF_NORMALIZE, s2);
                 if ((rc = shard_allreduce(ctx, ctx->B[nB].p, (size_t)c.m * ctx->strideB, false, s2)))
                     return rc;
@@ -1266,10 +1325,24 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
         if ((rc = run_loglik(ctx, &cur))) return rc;
         judge(cur);
     }
+    if (p2p_used) {
+        /* no rank may return (and perhaps free or rewrite its exchange buffer) while a peer's
+         * last reduce kernel still reads it: a one-word all-reduce is the closing barrier */
+        if ((rc = shard_allreduce(ctx, ctx->ll2.p, 1, true, ctx->stream))) return rc;
+    }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventElapsedTime(&ctx->last_em_ms, ctx->ev0, ctx->ev1));
     prof_collect(ctx);
+    if (p2p_used) {
+        int bad = 0;
+        CK(cudaMemcpy(&bad, ctx->p2p.err.p, 4, cudaMemcpyDeviceToHost));
+        if (bad) {
+            CK(cudaMemset(ctx->p2p.err.p, 0, 4));
+            return ctx->fail(PLSA_ENCCL, "sharded fit: a peer GPU did not signal within the "
+                                         "time limit (peer-memory all-reduce)");
+        }
+    }
     if (iters_run) *iters_run = done;
     if (n_ll) *n_ll = nl;
     return PLSA_OK;
@@ -1330,6 +1403,10 @@ API int plsa_set_option(plsa_ctx *ctx, const char *name, int64_t value)
     }
     if (!strcmp(name, "texture")) {
         ctx->use_texture = value != 0;
+        return PLSA_OK;
+    }
+    if (!strcmp(name, "p2p")) { /* sharded fit: 0 = NCCL all-reduce even when peers are attached */
+        ctx->p2p.enabled = value != 0;
         return PLSA_OK;
     }
     if (!strcmp(name, "vec_entries")) {
@@ -1673,12 +1750,94 @@ static int shard_allreduce(plsa_ctx *ctx, void *buf, size_t count, bool f64, cud
     return PLSA_OK;
 }
 
+static int shard_n_ranks(const plsa_ctx *ctx) { return ctx->shard ? ctx->shard->n_ranks : 1; }
+static int shard_rank(const plsa_ctx *ctx) { return ctx->shard ? ctx->shard->rank : 0; }
+
+static void p2p_release(plsa_ctx *ctx)
+{
+    for (int p = 0; p < SHARD_MAX_RANKS; ++p) {
+        if (ctx->p2p.peer_base[p] && ctx->p2p.peer_ipc[p]) cudaIpcCloseMemHandle(ctx->p2p.peer_base[p]);
+        ctx->p2p.peer_base[p] = nullptr;
+        ctx->p2p.peer_ipc[p] = false;
+    }
+    ctx->p2p.n_attached = 0;
+    ctx->p2p.block.release();
+    ctx->p2p.err.release();
+    ctx->p2p.part_bytes = 0;
+    ctx->p2p.seq = 0;
+}
+
 API int plsa_set_shard(plsa_ctx *ctx, plsa_comm *comm)
 {
     CHECK_CTX(ctx);
     if (comm && comm->device != ctx->device)
         return ctx->fail(PLSA_EINVAL, "set_shard: context and communicator devices differ");
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    p2p_release(ctx);
     ctx->shard = comm;
+    return PLSA_OK;
+}
+
+API int plsa_shard_p2p_prepare(plsa_ctx *ctx, uint64_t *base, int64_t *bytes)
+{
+    CHECK_CTX(ctx);
+    if (!ctx->shard) return ctx->fail(PLSA_EINVAL, "shard_p2p_prepare: no shard communicator attached");
+    if (!ctx->have_factors) return ctx->fail(PLSA_EINVAL, "shard_p2p_prepare: set the factors first");
+    if (ctx->shard->n_ranks > SHARD_MAX_RANKS)
+        return ctx->fail(PLSA_EINVAL, "shard_p2p_prepare: too many ranks for the peer-memory path");
+    p2p_release(ctx);
+    const size_t part = (size_t)std::max<int64_t>(ctx->cur().m, 1) * ctx->strideB * 4;
+    const size_t total = 2 * part + 256;
+    CK(ctx->p2p.block.ensure(total));
+    CK(ctx->p2p.err.ensure(4));
+    CK(cudaMemsetAsync(ctx->p2p.block.p, 0, total, ctx->stream));
+    CK(cudaMemsetAsync(ctx->p2p.err.p, 0, 4, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->p2p.part_bytes = part;
+    if (base) *base = (uint64_t)(uintptr_t)ctx->p2p.block.p;
+    if (bytes) *bytes = (int64_t)total;
+    return PLSA_OK;
+}
+
+API int plsa_shard_p2p_export(plsa_ctx *ctx, char *handle)
+{
+    CHECK_CTX(ctx);
+    if (!handle || !ctx->p2p.block.p) return ctx->fail(PLSA_EINVAL, "shard_p2p_export: nothing prepared");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->p2p.block.p));
+    static_assert(sizeof(h) == PLSA_IPC_HANDLE_BYTES, "IPC handle size");
+    memcpy(handle, &h, sizeof(h));
+    return PLSA_OK;
+}
+
+API int plsa_shard_p2p_attach(plsa_ctx *ctx, int32_t peer_rank, int32_t peer_device, uint64_t base,
+                              const char *ipc_handle)
+{
+    CHECK_CTX(ctx);
+    if (!ctx->shard || !ctx->p2p.block.p)
+        return ctx->fail(PLSA_EINVAL, "shard_p2p_attach: prepare first");
+    if (peer_rank < 0 || peer_rank >= ctx->shard->n_ranks || peer_rank == ctx->shard->rank)
+        return ctx->fail(PLSA_EINVAL, "shard_p2p_attach: bad peer rank");
+    if (ctx->p2p.peer_base[peer_rank]) return ctx->fail(PLSA_EINVAL, "shard_p2p_attach: peer attached twice");
+    void *ptr = nullptr;
+    if (ipc_handle) { /* another process: map its block (peer access is enabled lazily) */
+        cudaIpcMemHandle_t h;
+        memcpy(&h, ipc_handle, sizeof(h));
+        CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->p2p.peer_ipc[peer_rank] = true;
+    } else {          /* same process: the peer's device pointer, after enabling peer access */
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, ctx->device, peer_device));
+        if (!can) return ctx->fail(PLSA_ECUDA, "shard_p2p_attach: no peer access between the devices");
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (e != cudaSuccess)
+            return ctx->fail(PLSA_ECUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        ptr = (void *)(uintptr_t)base;
+    }
+    if (!ptr) return ctx->fail(PLSA_EINVAL, "shard_p2p_attach: null peer block");
+    ctx->p2p.peer_base[peer_rank] = ptr;
+    ctx->p2p.n_attached++;
     return PLSA_OK;
 }
 

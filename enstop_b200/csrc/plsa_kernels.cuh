@@ -697,6 +697,105 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const double *__restr
     }
 }
 
+/* ---- sharded fit: all-reduce of the raw P(w|z)^T sums over NVLink peer memory, fused with
+ * the column sums -------------------------------------------------------------------------
+ * Every rank's term pass leaves its partial sums in an exchange buffer that the other GPUs
+ * can read (peer access / CUDA IPC).  This kernel, launched behind the term pass on every
+ * rank, (1) tells the peers "my partial number `seq` is complete" by writing `seq` into the
+ * signal word it owns in each peer's memory, (2) waits until every peer has said the same,
+ * (3) reads each row from all ranks (own copy from local HBM, the others over NVLink), adds
+ * them in rank order — the same order on every rank, so all ranks hold bit-identical sums —
+ * writes the complete row into the local P(w|z)^T, and (4) accumulates the per-topic column
+ * sums of the slice in float64 (finished by colsum_final_kernel).  One pass over the data:
+ * no staging copy, no second read for the normaliser, 4*kp bytes per row and peer on the
+ * wire.  Buffer reuse: a rank rewrites exchange buffer `parity` two iterations later, after
+ * the barrier of the iteration in between, which no rank passes before all ranks have left
+ * this kernel.  The wait is bounded (about two seconds); a rank that gives up raises *err. */
+constexpr int SHARD_MAX_RANKS = 16;
+struct ShardReduceArgs {
+    const float *part[SHARD_MAX_RANKS];      /* every rank's partial, [rows, stride]; [rank] is local */
+    unsigned int *peer_sig[SHARD_MAX_RANKS]; /* rank p's signal array (word [rank] is ours to write) */
+    volatile unsigned int *my_sig;           /* our signal array: word [p] is written by rank p */
+    float *out;                              /* local complete P(w|z)^T [rows, stride] */
+    double *colpart;                         /* [grid, kp] */
+    int *err;
+    int64_t rows;
+    int32_t stride, kp, n_ranks, rank;
+    unsigned int seq;
+};
+
+__device__ __forceinline__ float4 ld_peer_f4(const float *p)
+{
+    float4 v; /* .cv: never served from this SM's L1 (peer lines are cached there only) */
+    asm volatile("ld.global.cv.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(256) shard_reduce_kernel(const ShardReduceArgs a)
+{
+    __shared__ double sm[256][4];
+    __shared__ int give_up;
+    if (threadIdx.x == 0) give_up = 0;
+    /* (1) + (2): every CTA signals nothing but waits itself; CTA 0 does the signalling, so a
+     * peer sees `seq` exactly once per iteration */
+    if (blockIdx.x == 0 && (int)threadIdx.x < a.n_ranks && (int)threadIdx.x != a.rank) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_sig[threadIdx.x] + a.rank),
+                     "r"(a.seq) : "memory");
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < a.n_ranks && (int)threadIdx.x != a.rank) {
+        const long long t0 = clock64();
+        unsigned int v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v)
+                         : "l"(const_cast<unsigned int *>(a.my_sig) + threadIdx.x) : "memory");
+            if ((int)(v - a.seq) >= 0) break;
+            if (clock64() - t0 > 4000000000LL) {
+                give_up = 1;
+                break;
+            }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    if (give_up) {
+        if (threadIdx.x == 0) *a.err = 1;
+        return;
+    }
+    /* (3) + (4): kp/4 consecutive threads along a row, 256/(kp/4) rows at a time */
+    const int nv = a.kp >> 2;
+    const int64_t per = (a.rows + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(a.rows, r0 + per);
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+    { /* kp <= 1024: nv <= 256 */
+        const int nsub = 256 / nv, sub = (int)threadIdx.x / nv, q = (int)threadIdx.x - sub * nv;
+        if (sub < nsub) {
+            for (int64_t r = r0 + sub; r < r1; r += nsub) {
+                const int64_t off = r * a.stride + 4 * q;
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int p = 0; p < a.n_ranks; ++p) {
+                    const float4 v = (p == a.rank)
+                                         ? *reinterpret_cast<const float4 *>(a.part[p] + off)
+                                         : ld_peer_f4(a.part[p] + off);
+                    t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+                }
+                *reinterpret_cast<float4 *>(a.out + off) = t;
+                c0 += (double)t.x; c1 += (double)t.y; c2 += (double)t.z; c3 += (double)t.w;
+            }
+        }
+        sm[threadIdx.x][0] = c0; sm[threadIdx.x][1] = c1;
+        sm[threadIdx.x][2] = c2; sm[threadIdx.x][3] = c3;
+        __syncthreads();
+        for (int z = threadIdx.x; z < a.kp; z += 256) { /* topic z lives in sm[sub*nv + z/4][z%4] */
+            double acc = 0.0;
+            for (int s2 = 0; s2 < nsub; ++s2) acc += sm[s2 * nv + (z >> 2)][z & 3];
+            a.colpart[(int64_t)blockIdx.x * a.kp + z] = acc;
+        }
+    }
+}
+
 /* {log-likelihood, flag} -> two doubles, so that one sum all-reduce carries both */
 __global__ void pack_ll_kernel(const double *ll, const int *flag, double *out2)
 {

@@ -162,12 +162,47 @@ def shard_rows(indptr, n_shards):
     return bounds
 
 
+class ThreadPeerExchange:
+    """Peer-memory setup between the ranks of a sharded fit that live in ONE process (one
+    host thread per GPU): every rank prepares its exchange block, the device addresses are
+    swapped through this object, every rank attaches its peers.  If any rank cannot (no
+    peer access between two of the GPUs), all ranks fall back to the NCCL all-reduce."""
+
+    def __init__(self, devices, timeout=300.0):
+        self.devices = list(devices)
+        self.barrier = threading.Barrier(len(self.devices), timeout=timeout)
+        self.base = [0] * len(self.devices)
+        self.ok = [True] * len(self.devices)
+
+    def __call__(self, ctx, rank):
+        try:
+            self.base[rank] = ctx.shard_p2p_prepare()[0]
+        except _lib.PlsaError:
+            self.ok[rank] = False
+        self.barrier.wait()
+        if all(self.ok):
+            try:
+                for p, dev in enumerate(self.devices):
+                    if p != rank:
+                        ctx.shard_p2p_attach(p, dev, base=self.base[p])
+            except _lib.PlsaError:
+                self.ok[rank] = False
+        self.barrier.wait()
+        if not all(self.ok):
+            ctx.set_option("p2p", 0)
+        return all(self.ok)
+
+    def abort(self):
+        self.barrier.abort()
+
+
 def plsa_fit_shard(X_rows, k, p_z_given_d_rows, p_w_given_z, sample_weight_rows, comm, device,
                    n_iter=100, n_iter_per_test=10, tolerance=0.001, e_step_thresh=1e-32,
-                   use_sample_weights=False, profile=False):
+                   use_sample_weights=False, profile=False, exchange=None):
     """One rank of a document-sharded fit: this rank's rows of X and of P(z|d), the full
     P(w|z), the shard communicator (``_lib.Comm``).  Every rank calls it with the same scalar
-    arguments.  Returns (P(z|d) rows, full P(w|z), info)."""
+    arguments.  ``exchange(ctx, rank)`` (optional) sets up the peer-memory all-reduce.
+    Returns (P(z|d) rows, full P(w|z), info)."""
     ctx = _lib.Context(device)
     try:
         ctx.upload_csr(_as_csr(X_rows))
@@ -175,6 +210,7 @@ def plsa_fit_shard(X_rows, k, p_z_given_d_rows, p_w_given_z, sample_weight_rows,
         ctx.set_factors(np.ascontiguousarray(p_z_given_d_rows, dtype=np.float32),
                         np.ascontiguousarray(p_w_given_z, dtype=np.float32))
         ctx.set_sample_weight(sample_weight_rows if use_sample_weights else None)
+        p2p = bool(exchange(ctx, comm.rank)) if exchange is not None else False
         ctx.prepare(k, False)
         if profile:
             ctx.set_profiling(True)
@@ -182,7 +218,8 @@ def plsa_fit_shard(X_rows, k, p_z_given_d_rows, p_w_given_z, sample_weight_rows,
                               use_sample_weights=use_sample_weights)
         pzd, pwz = ctx.get_factors()
         info = {"n_iter": iters, "ll_trace": trace, "em_ms": ctx.last_em_ms,
-                "launches": ctx.launches, "profile": ctx.profile() if profile else None}
+                "launches": ctx.launches, "profile": ctx.profile() if profile else None,
+                "p2p": p2p}
         ctx.set_shard(None)
     finally:
         ctx.close()
@@ -190,7 +227,7 @@ def plsa_fit_shard(X_rows, k, p_z_given_d_rows, p_w_given_z, sample_weight_rows,
 
 
 def _plsa_fit_sharded(X, k, sample_weight, init, n_iter, n_iter_per_test, tolerance,
-                      e_step_thresh, random_state, devices):
+                      e_step_thresh, random_state, devices, p2p=True):
     """plsa_fit over several GPUs of one box: one host thread, context and NCCL rank per
     device, documents cut into contiguous shards of equal stored entries."""
     X = _as_csr(X)
@@ -209,6 +246,7 @@ def _plsa_fit_sharded(X, k, sample_weight, init, n_iter, n_iter_per_test, tolera
     bounds = shard_rows(X.indptr, G)
     uid = _lib.Comm.unique_id()
     results, errors = [None] * G, [None] * G
+    exchange = ThreadPeerExchange(devices) if p2p else None
 
     def worker(r):
         comm = None
@@ -217,9 +255,12 @@ def _plsa_fit_sharded(X, k, sample_weight, init, n_iter, n_iter_per_test, tolera
             lo, hi = bounds[r], bounds[r + 1]
             results[r] = plsa_fit_shard(X[lo:hi], k, p_z_given_d[lo:hi], p_w_given_z,
                                         sample_weight[lo:hi], comm, devices[r], n_iter,
-                                        n_iter_per_test, tolerance, e_step_thresh, use_sw)
+                                        n_iter_per_test, tolerance, e_step_thresh, use_sw,
+                                        exchange=exchange)
         except BaseException as exc:
             errors[r] = exc
+            if exchange is not None:
+                exchange.abort()
         finally:
             if comm is not None:
                 comm.close()
@@ -253,7 +294,8 @@ def plsa_fit(X, k, sample_weight, init="random", n_iter=100, n_iter_per_test=10,
     shards the documents of this one fit over those GPUs."""
     if devices is not None and len(devices) > 1:
         out = _plsa_fit_sharded(X, k, sample_weight, init, n_iter, n_iter_per_test, tolerance,
-                                e_step_thresh, random_state, [int(d) for d in devices])
+                                e_step_thresh, random_state, [int(d) for d in devices],
+                                p2p=os.environ.get("ENSTOP_B200_P2P", "1") != "0")
         return out if return_info else out[:2]
     if devices is not None and len(devices) == 1 and device is None:
         device = int(devices[0])

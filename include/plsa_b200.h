@@ -188,6 +188,21 @@ int plsa_comm_gather_topics(plsa_comm *comm, plsa_ctx *ctx, const int32_t *n_per
  * decision (plsa.py:630-638).  plsa_get_factors returns the rank's rows of P(z|d) and the
  * full P(w|z).  comm == NULL detaches.  Every shard must hold at least one document. */
 int plsa_set_shard(plsa_ctx *ctx, plsa_comm *comm);
+/* Peer-memory all-reduce (optional; without it plsa_em uses ncclAllReduce).  After
+ * plsa_set_shard and plsa_set_factors every rank (1) prepares its exchange block — two
+ * buffers for its raw P(w|z) sums and a row of signal words, one allocation, returned as
+ * a device address — (2) hands the peers either that address (same process; the library
+ * enables peer access) or the 64-byte CUDA IPC handle from plsa_shard_p2p_export (other
+ * processes), and (3) attaches every peer's block.  Once ALL ranks have attached ALL peers
+ * (the caller's barrier), plsa_em adds the ranks' sums with one kernel per rank that reads
+ * the peers' buffers over NVLink, in rank order (bit-identical on every rank), and takes the
+ * column sums in the same pass.  Cross-GPU ordering uses signal words in peer memory with a
+ * bounded wait: a missing peer yields PLSA_ENCCL, not a hang.  Option "p2p" = 0 forces NCCL. */
+#define PLSA_IPC_HANDLE_BYTES 64
+int plsa_shard_p2p_prepare(plsa_ctx *ctx, uint64_t *device_address, int64_t *bytes);
+int plsa_shard_p2p_export(plsa_ctx *ctx, char *handle /*[PLSA_IPC_HANDLE_BYTES]*/);
+int plsa_shard_p2p_attach(plsa_ctx *ctx, int32_t peer_rank, int32_t peer_device,
+                          uint64_t device_address, const char *ipc_handle /* or NULL */);
 
 #ifdef __cplusplus
 }

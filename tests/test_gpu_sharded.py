@@ -42,7 +42,7 @@ def test_one_rank_shard_path_matches_plain_fit(corpus, k):
     comm.close()
     assert a[2] == b[2] == 25
     assert rel_l2(b[0], a[0]) < 2e-6 and rel_l2(b[1], a[1]) < 2e-6
-    assert np.allclose(a[3], b[3], rtol=1e-9)
+    assert np.allclose(a[3], b[3], rtol=1e-7)
     sw = np.ones(X.shape[0], dtype=np.float32)
     ref_pzd, ref_pwz = oracle.plsa_fit(X, k, sw, n_iter=25, tolerance=0.0, random_state=5,
                                        precision="f64")
@@ -57,12 +57,16 @@ def test_one_rank_shard_path_early_stop(corpus):
     b = _fit_ctx(X, 8, 200, 9, comm=comm, tolerance=1e-4, per_test=5)
     comm.close()
     assert a[2] == b[2] and a[2] < 200
-    assert len(a[3]) == len(b[3]) and np.allclose(a[3], b[3], rtol=1e-9)
+    assert len(a[3]) == len(b[3]) and np.allclose(a[3], b[3], rtol=1e-7)
 
 
 @pytest.mark.skipif(_lib.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("k,weighted", [(10, False), (20, True)])
-def test_two_gpu_sharded_fit_matches_oracle(corpus, k, weighted):
+@pytest.mark.parametrize("k,weighted,p2p", [(10, False, True), (20, True, True), (20, False, False),
+                                            (128, False, True)])
+def test_two_gpu_sharded_fit_matches_oracle(corpus, k, weighted, p2p, monkeypatch):
+    """p2p: the ranks' P(w|z) sums are added by shard_reduce_kernel over NVLink peer memory;
+    otherwise by ncclAllReduce."""
+    monkeypatch.setenv("ENSTOP_B200_P2P", "1" if p2p else "0")
     X = corpus
     n = X.shape[0]
     sw = np.ones(n, dtype=np.float32)
@@ -72,7 +76,7 @@ def test_two_gpu_sharded_fit_matches_oracle(corpus, k, weighted):
     pzd, pwz, info = plsa.plsa_fit(X, k, sw, devices=[0, 1], return_info=True, **kw)
     one_pzd, one_pwz = plsa.plsa_fit(X, k, sw, device=0, **kw)
     ref_pzd, ref_pwz = oracle.plsa_fit(X, k, sw, precision="f64", **kw)
-    assert info["n_iter"] == 30 and len(info["shard_bounds"]) == 3
+    assert info["n_iter"] == 30 and len(info["shard_bounds"]) == 3 and info["p2p"] == p2p
     assert pzd.shape == (n, k) and pwz.shape == (k, X.shape[1])
     assert rel_l2(pwz, ref_pwz) < 1e-5 and rel_l2(pzd, ref_pzd) < 1e-5
     assert rel_l2(pwz, one_pwz) < 5e-6 and rel_l2(pzd, one_pzd) < 5e-6
