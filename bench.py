@@ -269,6 +269,32 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def make_config_once(name, plumb, rank, world):
+    """The synthetic corpus of a config, generated by rank 0 only and handed to the other
+    ranks of the box through /dev/shm (the generator sorts up to 3e8 keys; N copies of that at
+    once would be most of the run)."""
+    from enstop_b200 import synth
+    if world == 1:
+        return synth.make_config(name, return_info=True)
+    import scipy.sparse as sp
+    path = "/dev/shm/enstop_b200_%s_%s.npz" % (name, os.environ.get("MASTER_PORT", "0"))
+    if rank == 0:
+        X, info = synth.make_config(name, return_info=True)
+        np.savez(path, data=X.data, indices=X.indices, indptr=X.indptr, shape=np.array(X.shape),
+                 info=np.array(json.dumps(info)))
+        plumb.barrier()
+        plumb.barrier()
+        os.remove(path)
+        return X, info
+    plumb.barrier()
+    with np.load(path) as z:
+        X = sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=tuple(z["shape"]))
+        info = json.loads(str(z["info"]))
+    X.has_sorted_indices = True
+    plumb.barrier()
+    return X, info
+
+
 def run_shard(args, plumb, rank, world, device):
     """--mode shard, N > 1: one fit of the whole corpus, documents sharded over the ranks
     (include/plsa_b200.h plsa_set_shard); strong scaling."""
@@ -276,7 +302,7 @@ def run_shard(args, plumb, rank, world, device):
     from enstop_b200 import _lib, plsa, synth
     cfg = synth.CONFIGS[args.config]
     k = cfg["k"]
-    X, info = synth.make_config(args.config, return_info=True)
+    X, info = make_config_once(args.config, plumb, rank, world)
     n, m = X.shape
     bounds = plsa.shard_rows(X.indptr, world)
     lo, hi = bounds[rank], bounds[rank + 1]
@@ -428,7 +454,7 @@ def main():
         return
     cfg = synth.CONFIGS[args.config]
     k = cfg["k"]
-    X, info = synth.make_config(args.config, return_info=True)
+    X, info = make_config_once(args.config, plumb, rank, world)
     n, m = X.shape
     peak, peak_src = load_peaks()
 
