@@ -397,11 +397,17 @@ static int build_items(plsa_ctx *ctx, const std::vector<int32_t> &indptr, int64_
      * walked with value 0.  Lengths below include them. */
     auto lead = [&](int64_t r) { return (int64_t)indptr[r] & (int64_t)(align - 1); };
     auto span = [&](int64_t r) { return (int64_t)indptr[r + 1] - indptr[r] + lead(r); };
+    /* A split row is cut into equal pieces (not full chunks plus a short remainder), so that
+     * the pieces of a row sort next to each other and none of them is a tiny item. */
+    auto piece = [&](int64_t len) {
+        const int64_t nc = cdiv(len, chunk);
+        return std::min(chunk, cdiv(cdiv(len, nc), (int64_t)align) * align);
+    };
     /* split rows, those with more than 32 chunks first (fixup_kernel gives them a CTA) */
     std::vector<int64_t> heavy, light;
     for (int64_t r = 0; r < rows; ++r) {
         const int64_t len = span(r);
-        if (len > chunk) (cdiv(len, chunk) > 32 ? heavy : light).push_back(r);
+        if (len > chunk) (cdiv(len, piece(len)) > 32 ? heavy : light).push_back(r);
     }
     std::vector<int32_t> split_rows, slot_begin;
     slot_begin.push_back(0);
@@ -410,7 +416,7 @@ static int build_items(plsa_ctx *ctx, const std::vector<int32_t> &indptr, int64_
     for (const std::vector<int64_t> *lst : {&heavy, &light})
         for (int64_t r : *lst) {
             first_slot[(size_t)r] = slots;
-            slots += (int32_t)cdiv(span(r), chunk);
+            slots += (int32_t)cdiv(span(r), piece(span(r)));
             split_rows.push_back((int32_t)r);
             slot_begin.push_back(slots);
         }
@@ -419,10 +425,10 @@ static int build_items(plsa_ctx *ctx, const std::vector<int32_t> &indptr, int64_
         if (len <= chunk) {
             items.push_back(Item{s, (int32_t)r, (int32_t)len, -1, (int32_t)skip});
         } else {
-            const int64_t nc = cdiv(len, chunk); /* chunk is a multiple of 32: chunks stay aligned */
+            const int64_t per = piece(len), nc = cdiv(len, per); /* per is a multiple of align */
             for (int64_t c = 0; c < nc; ++c) {
-                const int64_t b = c * chunk;
-                items.push_back(Item{s + b, (int32_t)r, (int32_t)std::min(chunk, len - b),
+                const int64_t b = c * per;
+                items.push_back(Item{s + b, (int32_t)r, (int32_t)std::min(per, len - b),
                                      first_slot[(size_t)r] + (int32_t)c,
                                      (int32_t)(c == 0 ? skip : 0)});
             }

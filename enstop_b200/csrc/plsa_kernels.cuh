@@ -98,6 +98,12 @@ __device__ __forceinline__ const char *opaque_ptr(const char *p)
     asm volatile("" : "+l"(p));
     return p;
 }
+__device__ __forceinline__ float log2_ftz(float x)
+{
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float rcp_fast(float x)
 {
     float r;
@@ -329,10 +335,11 @@ template <int G, int KV, int U, int MODE, bool TEX, bool TAIL>
 __device__ __forceinline__ void pass_block(const PassArgs &a, const int2 (&e)[U], int base, int len,
                                            const char *gat_base, const uint32_t (&lane_off)[KV],
                                            uint32_t stride_bytes, const float4 (&own)[KV],
-                                           float4 (&acc)[KV], double &ll_acc, float rw,
-                                           float thresh, int j, int gbase, bool lane_on)
+                                           float4 (&acc)[KV], double &ll_acc, float &min_norm,
+                                           float rw, float thresh, int j, int gbase, bool lane_on)
 {
     float4 g[U][KV];
+    float llt[U]; /* log-likelihood terms of the block (MODE_LOGLIK / MODE_DOC_LL) */
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         if constexpr (TEX) {
@@ -392,16 +399,18 @@ __device__ __forceinline__ void pass_block(const PassArgs &a, const int2 (&e)[U]
             part = (q == 0) ? s4 : part + s4;
         }
         const float norm = group_sum<G>(part, gbase, j);
-        if constexpr (MODE == MODE_LOGLIK) {
-            /* plsa.py:383-384; one lane per entry contributes, x == 0 marks a non-entry */
-            if (j == 0 && lane_on && x != 0.f) ll_acc += (double)(x * __logf(norm) * rw);
-        } else {
-            if constexpr (MODE == MODE_DOC_LL) {
-                if (j == 0 && lane_on && x != 0.f) {
-                    ll_acc += (double)(x * __logf(norm) * rw);
-                    if (norm < PLSA_FUSED_LL_MIN_NORM) *a.flag = 1;
-                }
-            }
+        if constexpr (MODE == MODE_LOGLIK || MODE == MODE_DOC_LL) {
+            /* plsa.py:383-384: x * log(sum) * sample_weight[d]; x == 0 marks a non-entry.
+             * Branch-free, every lane of the group carries the same term (lane 0's is used);
+             * the block's terms are added in float32, blocks in float64. */
+            float lg; /* fused pass: the sum is 0 or a normal float (thresholded products), so the
+                         flush-to-zero MUFU.LG2 needs no subnormal pre-scaling branch */
+            if constexpr (MODE == MODE_DOC_LL) lg = log2_ftz(norm) * 0.69314718f;
+            else lg = __logf(norm);
+            llt[u] = (x != 0.f) ? x * rw * lg : 0.f;
+            if constexpr (MODE == MODE_DOC_LL) min_norm = fminf(min_norm, (x != 0.f) ? norm : 1.f);
+        }
+        if constexpr (MODE != MODE_LOGLIK) {
             /* plsa.py:104: posterior = v / norm if norm > 0.  Products that survive the
              * threshold are normal floats (the host passes thresh >= FLT_MIN), so norm is 0
              * or normal; norm == 0 gives x * inf (or NaN), clamped to a finite c that
@@ -424,6 +433,12 @@ __device__ __forceinline__ void pass_block(const PassArgs &a, const int2 (&e)[U]
             }
 #endif
         }
+    }
+    if constexpr (MODE == MODE_LOGLIK || MODE == MODE_DOC_LL) {
+        float t = llt[0];
+#pragma unroll
+        for (int u = 1; u < U; ++u) t += llt[u];
+        ll_acc += (double)t;
     }
 #if PLSA_PACKED_MATH
 #pragma unroll
@@ -492,6 +507,7 @@ __global__ void __launch_bounds__(256, (KV == 1) ? 4 : (KV == 2) ? 2 : 1)
     const char *gat_base = opaque_ptr(reinterpret_cast<const char *>(a.gat_old) +
                                       (KV == 1 ? lane_off[0] : 0u));
     double ll_acc = 0.0;
+    float min_norm = 1.f; /* MODE_DOC_LL: smallest posterior normaliser of a real entry */
 
     /* Entries are fetched one block ahead (one broadcast 8-byte load per group per entry);
      * reads past an item's end land in following rows or in the array's padding and count
@@ -508,11 +524,17 @@ __global__ void __launch_bounds__(256, (KV == 1) ? 4 : (KV == 2) ? 2 : 1)
         int2 en[U];
         load_entries<U, VEC>(ent + base + U, en);
         pass_block<G, KV, U, MODE, TEX, true>(a, e, base, len, gat_base, lane_off, stride_bytes,
-                                              own, acc, ll_acc, rw, thresh, j, gbase, lane_on);
+                                              own, acc, ll_acc, min_norm, rw, thresh, j, gbase,
+                                              lane_on);
 #pragma unroll
         for (int u = 0; u < U; ++u) e[u] = en[u];
     }
 
+    if constexpr (MODE == MODE_LOGLIK || MODE == MODE_DOC_LL) {
+        if (!(j == 0 && lane_on)) ll_acc = 0.0; /* one lane per item contributes */
+        if constexpr (MODE == MODE_DOC_LL)
+            if (min_norm < PLSA_FUSED_LL_MIN_NORM) *a.flag = 1;
+    }
     if constexpr (MODE == MODE_LOGLIK) {
         finish_loglik(a, ll_acc);
     } else {
