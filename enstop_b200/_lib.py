@@ -76,6 +76,7 @@ SIGNATURES = {
                                         ctypes.POINTER(ctypes.c_void_p)]),
     "plsa_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "plsa_comm_gather_topics": (ctypes.c_int, [ctypes.c_void_p, _ctx, _i32p, _i32, _f32p]),
+    "plsa_topic_distances": (ctypes.c_int, [_i32, _f32p, _i64, _i64, _i32, _f64p]),
     "plsa_set_shard": (ctypes.c_int, [_ctx, ctypes.c_void_p]),
     "plsa_shard_p2p_prepare": (ctypes.c_int, [_ctx, ctypes.POINTER(ctypes.c_uint64), _i64p]),
     "plsa_shard_p2p_export": (ctypes.c_int, [_ctx, ctypes.c_char_p]),
@@ -423,6 +424,20 @@ def gather_topics(contexts, n_slots):
     out = np.empty((int(counts.sum()) * k, m), dtype=np.float32)
     arr = (_ctx * len(contexts))(*[c._h for c in contexts])
     check(L.plsa_gather_topics(arr, len(contexts), _ptr(counts, _i32p), _ptr(out, _f32p)))
+    return out
+
+
+def topic_distances(topics, kind, device=0):
+    """All-pairs distances between topic vectors on the GPU: kind "hellinger" or "kl"
+    (enstop_.py:234-263).  topics [N, m] -> float64 [N, N]."""
+    topics = np.ascontiguousarray(topics, dtype=np.float32)
+    if topics.ndim != 2:
+        raise ValueError("topics must be a 2-d array")
+    n, m = topics.shape
+    out = np.zeros((n, n), dtype=np.float64)
+    code = {"hellinger": 0, "kl": 1}[kind]
+    check(lib().plsa_topic_distances(int(device), _ptr(topics, _f32p), n, m, code,
+                                     _ptr(out, _f64p)))
     return out
 
 

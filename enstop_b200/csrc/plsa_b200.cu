@@ -1470,6 +1470,55 @@ API int plsa_b200_refit_inner(const int32_t *X_rows, const int32_t *X_cols, cons
                     device, iters_run);
 }
 
+/* ---- all-pairs distances between topic vectors (ensemble clustering input) ------------------------ */
+API int plsa_topic_distances(int32_t device, const float *topics, int64_t n_topics, int64_t n_terms,
+                             int32_t kind, double *out)
+{
+    if (!topics || !out || n_topics < 0 || n_terms < 0 || (kind != 0 && kind != 1) ||
+        n_topics >= ((int64_t)1 << 24)) {
+        g_err = "topic_distances: bad arguments";
+        return PLSA_EINVAL;
+    }
+    if (n_topics == 0) return PLSA_OK;
+    cudaError_t e = cudaSetDevice(device);
+    DevBuf P, A, B, l1, D;
+    cudaStream_t st = nullptr;
+    const size_t cells = (size_t)n_topics * (size_t)std::max<int64_t>(n_terms, 1);
+    auto done = [&](int rc, const char *what) {
+        if (rc != PLSA_OK) g_err = std::string("topic_distances: ") + what + ": " + cudaGetErrorString(e);
+        P.release(); A.release(); B.release(); l1.release(); D.release();
+        if (st) cudaStreamDestroy(st);
+        return rc;
+    };
+    if (e != cudaSuccess) return done(PLSA_ECUDA, "cudaSetDevice");
+    if ((e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)) != cudaSuccess)
+        return done(PLSA_ECUDA, "stream");
+    if ((e = P.ensure(cells * 4)) != cudaSuccess || (e = A.ensure(cells * 4)) != cudaSuccess ||
+        (e = B.ensure(kind == 1 ? cells * 4 : 16)) != cudaSuccess ||
+        (e = l1.ensure((size_t)n_topics * 8)) != cudaSuccess ||
+        (e = D.ensure((size_t)n_topics * n_topics * 8)) != cudaSuccess)
+        return done(PLSA_ENOMEM, "allocation");
+    if (n_terms > 0 &&
+        (e = cudaMemcpyAsync(P.p, topics, cells * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+        return done(PLSA_ECUDA, "upload");
+    topic_rowsum_kernel<<<(unsigned)n_topics, 256, 0, st>>>(P.as<float>(), n_terms, l1.as<double>());
+    if (n_terms > 0)
+        topic_prep_kernel<<<(unsigned)cdiv((int64_t)cells, 256), 256, 0, st>>>(
+            P.as<float>(), l1.as<double>(), n_topics, n_terms, kind, A.as<float>(), B.as<float>());
+    const dim3 grid((unsigned)cdiv(n_topics, 32), (unsigned)cdiv(n_topics, 32));
+    if (kind == 0)
+        topic_pairs_kernel<0><<<grid, 256, 0, st>>>(A.as<float>(), B.as<float>(), l1.as<double>(),
+                                                    (int)n_topics, n_terms, D.as<double>());
+    else
+        topic_pairs_kernel<1><<<grid, 256, 0, st>>>(A.as<float>(), B.as<float>(), l1.as<double>(),
+                                                    (int)n_topics, n_terms, D.as<double>());
+    if ((e = cudaGetLastError()) != cudaSuccess) return done(PLSA_ECUDA, "launch");
+    if ((e = cudaMemcpyAsync(out, D.p, (size_t)n_topics * n_topics * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(st)) != cudaSuccess)
+        return done(PLSA_ECUDA, "download");
+    return done(PLSA_OK, "");
+}
+
 /* ---- ensemble topic stash + gather over NCCL ------------------------------------------------------ */
 /* Each finished ensemble member leaves its P(w|z) [k, m] (reference layout) in a slot of the
  * context's device-side stash; one gather at the end moves every slot to the root

@@ -825,6 +825,111 @@ __global__ void pack_ll_kernel(const double *ll, const int *flag, double *out2)
     out2[1] = flag ? (double)*flag : 0.0;
 }
 
+/* ---- all-pairs distances between topics (enstop_.py:234-263) -------------------------------
+ * Hellinger (umap.distances.hellinger, as called at enstop_.py:253-263):
+ *     sqrt(1 - sum_w sqrt(a_w b_w) / sqrt(|a|_1 |b|_1))  =  sqrt(1/2 sum_w (r_w - s_w)^2)
+ * with r = sqrt(a / |a|_1), s = sqrt(b / |b|_1): the right-hand form has only non-negative
+ * terms, so float32 products with float64 block sums give the distance of two nearly equal
+ * topics to full relative accuracy (the 1 - inner product form cancels).
+ * KL (enstop_.py:234-250): sum over w with a_w > 0 and b_w > 0 of a_w (log2 a_w - log2 b_w).
+ * prep_kernel turns P [N, m] into the per-row operands; pairs_kernel gives one 32 x 32 tile
+ * of pairs to a CTA (each thread 2 x 2 pairs), 32 terms at a time through shared memory. */
+__global__ void topic_rowsum_kernel(const float *__restrict__ P, int64_t m, double *__restrict__ l1)
+{
+    __shared__ double sm[256];
+    const float *row = P + (int64_t)blockIdx.x * m;
+    double t = 0.0;
+    for (int64_t w = threadIdx.x; w < m; w += 256) t += (double)row[w];
+    sm[threadIdx.x] = t;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) sm[threadIdx.x] += sm[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) l1[blockIdx.x] = sm[0];
+}
+
+/* kind 0: A = sqrt(P / l1).  kind 1: A = P, B = log2(P) where P > 0, else A = 0 and B = 0
+ * (a zero A switches the term off on the a side; the b side is tested in the pair loop) */
+__global__ void topic_prep_kernel(const float *__restrict__ P, const double *__restrict__ l1,
+                                  int64_t n, int64_t m, int kind, float *__restrict__ A,
+                                  float *__restrict__ B)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * m) return;
+    const float p = P[i];
+    if (kind == 0) {
+        const double s = l1[i / m];
+        A[i] = s > 0.0 ? (float)sqrt((double)p / s) : 0.f;
+    } else {
+        A[i] = p > 0.f ? p : 0.f;
+        B[i] = p > 0.f ? log2f(p) : 0.f;
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) topic_pairs_kernel(const float *__restrict__ A,
+                                                          const float *__restrict__ B,
+                                                          const double *__restrict__ l1, int n,
+                                                          int64_t m, double *__restrict__ out)
+{
+    constexpr int T = 32, WC = 32;
+    __shared__ float ai[T][WC + 1], aj[T][WC + 1], bi[KIND ? T : 1][WC + 1], bj[KIND ? T : 1][WC + 1];
+    const int i0 = blockIdx.y * T, j0 = blockIdx.x * T;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4; /* pairs (i0+ty+16a, j0+tx+16b) */
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    for (int64_t w0 = 0; w0 < m; w0 += WC) {
+        for (int e = threadIdx.x; e < T * WC; e += 256) {
+            const int r = e / WC, c = e % WC;
+            const int64_t w = w0 + c;
+            const bool okw = w < m;
+            const int gi = i0 + r, gj = j0 + r;
+            ai[r][c] = (okw && gi < n) ? A[(int64_t)gi * m + w] : 0.f;
+            aj[r][c] = (okw && gj < n) ? A[(int64_t)gj * m + w] : 0.f;
+            if constexpr (KIND == 1) {
+                bi[r][c] = (okw && gi < n) ? B[(int64_t)gi * m + w] : 0.f;
+                bj[r][c] = (okw && gj < n) ? B[(int64_t)gj * m + w] : 0.f;
+            }
+        }
+        __syncthreads();
+        float part[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll 8
+        for (int c = 0; c < WC; ++c) {
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const float x = ai[ty + 16 * a][c], y = aj[tx + 16 * b][c];
+                    if constexpr (KIND == 0) {
+                        const float d = x - y;
+                        part[a][b] = fmaf(d, d, part[a][b]);
+                    } else { /* a_w (log2 a_w - log2 b_w) where both are positive */
+                        const float t = x * (bi[ty + 16 * a][c] - bj[tx + 16 * b][c]);
+                        part[a][b] += (y > 0.f) ? t : 0.f;
+                    }
+                }
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) acc[a][b] += (double)part[a][b];
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int gi = i0 + ty + 16 * a, gj = j0 + tx + 16 * b;
+            if (gi >= n || gj >= n) continue;
+            double v = acc[a][b];
+            if constexpr (KIND == 0) {
+                const bool zi = !(l1[gi] > 0.0), zj = !(l1[gj] > 0.0);
+                v = (gi == gj || (zi && zj)) ? 0.0 : (zi || zj) ? 1.0 : sqrt(0.5 * v);
+            }
+            out[(int64_t)gi * n + gj] = v;
+        }
+}
+
 /* ---- layout conversion between the reference's arrays and the device layout ---------- */
 /* dense [rows, k] -> padded [rows, stride] (P(z|d); also P(w|z)^T when src is [k, rows]) */
 __global__ void pack_rows_kernel(const float *__restrict__ src, float *__restrict__ dst,

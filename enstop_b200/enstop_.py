@@ -185,36 +185,18 @@ def ensemble_of_topics(X, k, model="plsa", n_jobs=4, n_runs=16, parallelism="thr
 
 
 # ---- distances between topics (enstop_.py:234-263) ------------------------------------------
-def all_pairs_kl_divergence(distributions):
-    """result[i, j] = sum_w a log2(a / b) over entries where both are > 0 (enstop_.py:234-250)."""
-    P = np.asarray(distributions, dtype=np.float64)
-    pos = P > 0
-    L = np.zeros_like(P)
-    L[pos] = np.log2(P[pos])
-    n = P.shape[0]
-    out = np.zeros((n, n))
-    for i in range(n):
-        both = pos & pos[i][None, :]
-        out[i] = np.where(both, P[i][None, :] * (L[i][None, :] - L), 0.0).sum(axis=1)
-    return out
+def all_pairs_kl_divergence(distributions, device=None):
+    """result[i, j] = sum_w a log2(a / b) over entries where both are > 0 (enstop_.py:234-250),
+    evaluated on the GPU (csrc: topic_pairs_kernel<1>); float64 [N, N]."""
+    return _lib.topic_distances(distributions, "kl", default_device() if device is None else device)
 
 
-def all_pairs_hellinger_distance(distributions):
+def all_pairs_hellinger_distance(distributions, device=None):
     """sqrt(1 - sum_w sqrt(a b) / sqrt(|a|_1 |b|_1)) (umap.distances.hellinger, as used at
-    enstop_.py:253-263) — one small dense product of sqrt(topics)."""
-    P = np.asarray(distributions, dtype=np.float64)
-    R = np.sqrt(P)
-    l1 = P.sum(axis=1)
-    inner = R @ R.T
-    denom = np.sqrt(np.outer(l1, l1))
-    with np.errstate(divide="ignore", invalid="ignore"):
-        d = np.sqrt(np.clip(1.0 - inner / denom, 0.0, None))
-    zero = l1 == 0
-    d[np.ix_(zero, ~zero)] = 1.0
-    d[np.ix_(~zero, zero)] = 1.0
-    d[np.ix_(zero, zero)] = 0.0
-    np.fill_diagonal(d, 0.0)
-    return d
+    enstop_.py:253-263), evaluated on the GPU in the cancellation-free form
+    sqrt(1/2 sum_w (sqrt(a/|a|) - sqrt(b/|b|))^2) (csrc: topic_pairs_kernel<0>)."""
+    return _lib.topic_distances(distributions, "hellinger",
+                                default_device() if device is None else device)
 
 
 def _combine(all_topics, labels, weights=None):
@@ -237,10 +219,11 @@ def _hdbscan(**kw):
     return HDBSCAN(cluster_selection_method="leaf", copy=True, **kw)
 
 
-def generate_combined_topics_kl(all_topics, min_samples=5, min_cluster_size=5):
+def generate_combined_topics_kl(all_topics, min_samples=5, min_cluster_size=5, distances=None):
     """enstop_.py:266-314: mutual reachability from the asymmetric KL matrix with the
-    min_samples-th neighbour as core divergence, single linkage, leaf clusters."""
-    div = all_pairs_kl_divergence(all_topics)
+    min_samples-th neighbour as core divergence, single linkage, leaf clusters.
+    ``distances``: a precomputed all-pairs matrix (otherwise computed on the GPU)."""
+    div = all_pairs_kl_divergence(all_topics) if distances is None else np.asarray(distances)
     core = np.sort(div, axis=1)[:, min(min_samples, div.shape[0] - 1)]
     tiled = np.tile(core, (core.shape[0], 1))
     mreach = np.dstack([div, div.T, tiled, tiled.T]).max(axis=-1)
@@ -251,9 +234,11 @@ def generate_combined_topics_kl(all_topics, min_samples=5, min_cluster_size=5):
     return _combine(all_topics, labels)
 
 
-def generate_combined_topics_hellinger(all_topics, min_samples=5, min_cluster_size=5):
-    """enstop_.py:317-351."""
-    dist = all_pairs_hellinger_distance(all_topics)
+def generate_combined_topics_hellinger(all_topics, min_samples=5, min_cluster_size=5,
+                                       distances=None):
+    """enstop_.py:317-351.  ``distances``: a precomputed all-pairs matrix (otherwise computed
+    on the GPU)."""
+    dist = all_pairs_hellinger_distance(all_topics) if distances is None else np.asarray(distances)
     labels = _hdbscan(min_samples=min_samples, min_cluster_size=min_cluster_size,
                       metric="precomputed").fit_predict(dist)
     return _combine(all_topics, labels)

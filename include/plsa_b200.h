@@ -176,6 +176,18 @@ int plsa_comm_destroy(plsa_comm *comm);
 int plsa_comm_gather_topics(plsa_comm *comm, plsa_ctx *ctx, const int32_t *n_per_rank,
                             int32_t root, float *out);
 
+/* ---- ensemble: all-pairs distances between the stacked topics (enstop_.py:234-263) ------------
+ * topics [n_topics, n_terms] float32 (the np.vstack of the members' P(w|z)); out [n_topics,
+ * n_topics] float64.  kind 0: Hellinger distance (umap.distances.hellinger as used by
+ * all_pairs_hellinger_distance, enstop_.py:253-263; rows need not sum to 1; an all-zero row is
+ * at distance 1 from every non-zero row and 0 from another all-zero row).  kind 1:
+ * all_pairs_kl_divergence (enstop_.py:234-250), out[i, j] = sum over terms where both are
+ * positive of a log2(a / b).  The reference evaluates both serially in O(N^2 m). */
+#define PLSA_DIST_HELLINGER 0
+#define PLSA_DIST_KL 1
+int plsa_topic_distances(int32_t device, const float *topics, int64_t n_topics, int64_t n_terms,
+                         int32_t kind, double *out);
+
 /* ---- one fit over several GPUs: documents sharded by rows -------------------------------------
  * Generalises the row blocking of enstop/block_parallel_plsa.py:156-185 and
  * enstop/distributed_plsa.py:116-131 (per-block E-step + partial M-step sums, then a sum over

@@ -7,12 +7,15 @@ ctypes front end to ``libplsa_oracle.so`` (the C restatement of enstop/plsa.py, 
   then float64 L1 row normalisation, utils.py:22-41)
 * ``plsa_fit``          — plsa.py:707-730
 * ``plsa_refit``        — plsa.py:975-997
+* ``all_pairs_kl_divergence`` / ``all_pairs_hellinger_distance`` — enstop_.py:234-263 (+ the
+  body of umap.distances.hellinger, which the reference file quotes at :30-46), float64 numpy
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference``
 legs of ``bench.py`` may import this module.  ``enstop_b200`` never does.
 
 Parity status: PINNED — checked against outputs of the reference itself
-(tests/golden/make_golden.py ran /root/reference/enstop/plsa.py in the build container;
+(tests/golden/make_golden.py ran /root/reference/enstop/plsa.py in the build container,
+tests/golden/make_golden_distances.py compiled the reference's own all-pairs functions;
 tests/test_oracle_golden.py compares).
 """
 import ctypes
@@ -232,3 +235,35 @@ def log_likelihood(X, pwz, pzd, sample_weight=None, precision="f64"):
                                              _p(vals, _f64p), vals.shape[0], _p(pwz, _f64p),
                                              _p(pzd, _f64p), _p(sw, _f64p), pwz.shape[1],
                                              pwz.shape[0]))
+
+
+def all_pairs_kl_divergence(distributions):
+    """enstop_.py:234-250: result[i, j] = sum_w a log2(a / b) over entries where both are > 0."""
+    P = np.asarray(distributions, dtype=np.float64)
+    pos = P > 0
+    L = np.zeros_like(P)
+    L[pos] = np.log2(P[pos])
+    n = P.shape[0]
+    out = np.zeros((n, n))
+    for i in range(n):
+        both = pos & pos[i][None, :]
+        out[i] = np.where(both, P[i][None, :] * (L[i][None, :] - L), 0.0).sum(axis=1)
+    return out
+
+
+def all_pairs_hellinger_distance(distributions):
+    """enstop_.py:253-263 with umap.distances.hellinger (quoted at enstop_.py:30-46):
+    sqrt(1 - sum_w sqrt(a b) / sqrt(|a|_1 |b|_1)); 0 for two all-zero rows, 1 when exactly
+    one row is all-zero."""
+    P = np.asarray(distributions, dtype=np.float64)
+    R = np.sqrt(P)
+    l1 = P.sum(axis=1)
+    inner = R @ R.T
+    denom = np.sqrt(np.outer(l1, l1))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        d = np.sqrt(np.clip(1.0 - inner / denom, 0.0, None))
+    zero = l1 == 0
+    d[np.ix_(zero, ~zero)] = 1.0
+    d[np.ix_(~zero, zero)] = 1.0
+    d[np.ix_(zero, zero)] = 0.0
+    return d

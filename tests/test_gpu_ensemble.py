@@ -71,3 +71,25 @@ def test_ensemble_topics_estimator(corpus):
     assert np.isfinite(model.coherence(n_words=10)) and np.isfinite(model.log_lift(n_words=10))
     with pytest.raises(ValueError, match="topic_combination"):
         EnsembleTopics(topic_combination="bogus").fit(X)
+
+
+def test_topic_distances_kernel():
+    """plsa_topic_distances (GPU) against the reference's golden values and the float64
+    oracle, including exact zeros, an all-zero row, a duplicate row and un-normalised rows."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                             "topic_distances.npz"))
+    topics = g["topics"]
+    H = enstop_.all_pairs_hellinger_distance(topics)
+    K = enstop_.all_pairs_kl_divergence(topics)
+    assert H.shape == K.shape == (25, 25) and H.dtype == np.float64
+    assert np.allclose(H ** 2, g["hellinger"] ** 2, atol=1e-6)
+    assert np.allclose(K, g["kl"], rtol=1e-5, atol=1e-5)
+    assert H[11, 0] == 1.0 and H[0, 11] == 1.0 and H[11, 11] == 0.0 and H[12, 13] == 0.0
+    # a larger, ragged case (sizes not multiples of the 32 x 32 tile or the 32-term block)
+    rng = np.random.RandomState(5)
+    big = rng.dirichlet(np.full(1013, 0.05), size=77).astype(np.float32)
+    big[big < 1e-5] = 0.0
+    Ho, Ko = oracle.all_pairs_hellinger_distance(big), oracle.all_pairs_kl_divergence(big)
+    assert np.allclose(enstop_.all_pairs_hellinger_distance(big), Ho, atol=2e-6)
+    assert np.allclose(enstop_.all_pairs_kl_divergence(big), Ko, rtol=1e-5, atol=1e-5)

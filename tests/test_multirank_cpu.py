@@ -86,21 +86,24 @@ def test_sharding_and_seeds():
 
 
 def test_topic_distances_and_combiners():
+    """The oracle's all-pairs distances against a direct evaluation, and the host-side
+    combiners on precomputed matrices (the product computes them on the GPU)."""
+    from oracle import oracle
     rng = np.random.RandomState(0)
     base = rng.dirichlet(np.full(30, 0.3), size=4)
     topics = np.vstack([b * (1 + 0.02 * rng.rand(30)) for b in base for _ in range(6)])
     topics /= topics.sum(axis=1, keepdims=True)
     topics = topics.astype(np.float32)
-    H = enstop_.all_pairs_hellinger_distance(topics)
+    H = oracle.all_pairs_hellinger_distance(topics)
     i, j = 3, 17
     direct = np.sqrt(1 - np.sum(np.sqrt(topics[i].astype(float) * topics[j]))
                      / np.sqrt(topics[i].sum(dtype=float) * topics[j].sum(dtype=float)))
-    assert np.isclose(H[i, j], direct, atol=1e-6) and np.allclose(np.diag(H), 0)
-    K = enstop_.all_pairs_kl_divergence(topics)
+    assert np.isclose(H[i, j], direct, atol=1e-6) and np.allclose(np.diag(H), 0, atol=1e-7)
+    K = oracle.all_pairs_kl_divergence(topics)
     a, b = topics[i].astype(float), topics[j].astype(float)
     ok = (a > 0) & (b > 0)
     assert np.isclose(K[i, j], np.sum(a[ok] * (np.log2(a[ok]) - np.log2(b[ok]))))
-    for name in ("hellinger", "kl_divergence"):
-        stable = enstop_._topic_combiner[name](topics, 3, 4)
+    for name, D in (("hellinger", H), ("kl_divergence", K)):
+        stable = enstop_._topic_combiner[name](topics, 3, 4, distances=D)
         assert stable.shape == (4, 30) and stable.dtype == np.float32
         assert np.allclose(stable.sum(axis=1), 1.0, atol=1e-5)

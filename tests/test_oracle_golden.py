@@ -84,3 +84,21 @@ def test_float_input(golden_small):
     pzd, pwz = oracle.plsa_fit(Xf, int(g["k"]), ones, init=(g["pzd0"], g["pwz0"]),
                                n_iter=10, tolerance=0.0)
     assert rel_l2(pwz, g["pwz_float"]) < TOL_F32 and rel_l2(pzd, g["pzd_float"]) < TOL_F32
+
+
+def test_topic_distances_against_reference():
+    """all_pairs_kl_divergence / all_pairs_hellinger_distance (enstop_.py:234-263): the
+    oracle's numpy restatement against the reference's own numba functions
+    (tests/golden/make_golden_distances.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                             "topic_distances.npz"))
+    topics = g["topics"]
+    K = oracle.all_pairs_kl_divergence(topics)
+    H = oracle.all_pairs_hellinger_distance(topics)
+    # the reference takes log2 of float32 values in float32: ~1e-7 per term
+    assert np.allclose(K, g["kl"], rtol=1e-6, atol=2e-6)
+    # the reference's 1 - inner/denominator form leaves ~1e-8 rounding under the root for
+    # identical rows: compare squared distances
+    assert np.allclose(H ** 2, g["hellinger"] ** 2, atol=1e-7)
+    assert H[11, 0] == 1.0 and H[11, 11] == 0.0 and g["hellinger"][11, 0] == 1.0
