@@ -162,6 +162,20 @@ def shard_rows(indptr, n_shards):
     return bounds
 
 
+_shard_comms = {}            # tuple(devices) -> [Comm per rank], reused by later sharded fits
+_shard_comm_lock = threading.Lock()
+
+
+def release_shard_communicators():
+    """Destroy the NCCL communicators kept for sharded fits."""
+    with _shard_comm_lock:
+        held = list(_shard_comms.values())
+        _shard_comms.clear()
+    for comms in held:
+        for c in comms:
+            c.close()
+
+
 class ThreadPeerExchange:
     """Peer-memory setup between the ranks of a sharded fit that live in ONE process (one
     host thread per GPU): every rank prepares its exchange block, the device addresses are
@@ -203,8 +217,10 @@ def plsa_fit_shard(X_rows, k, p_z_given_d_rows, p_w_given_z, sample_weight_rows,
     P(w|z), the shard communicator (``_lib.Comm``).  Every rank calls it with the same scalar
     arguments.  ``exchange(ctx, rank)`` (optional) sets up the peer-memory all-reduce.
     Returns (P(z|d) rows, full P(w|z), info)."""
-    ctx = _lib.Context(device)
+    ctx = _lib.acquire_context(device)   # pooled: device buffers survive between fits
+    ok = False
     try:
+        ctx.set_option("p2p", 1)
         ctx.upload_csr(_as_csr(X_rows))
         ctx.set_shard(comm)
         ctx.set_factors(np.ascontiguousarray(p_z_given_d_rows, dtype=np.float32),
@@ -220,9 +236,15 @@ def plsa_fit_shard(X_rows, k, p_z_given_d_rows, p_w_given_z, sample_weight_rows,
         info = {"n_iter": iters, "ll_trace": trace, "em_ms": ctx.last_em_ms,
                 "launches": ctx.launches, "profile": ctx.profile() if profile else None,
                 "p2p": p2p}
+        if profile:
+            ctx.set_profiling(False)
         ctx.set_shard(None)
+        ok = True
     finally:
-        ctx.close()
+        if ok:
+            _lib.release_context(ctx)
+        else:
+            ctx.close()
     return pzd, pwz, info
 
 
@@ -244,14 +266,19 @@ def _plsa_fit_sharded(X, k, sample_weight, init, n_iter, n_iter_per_test, tolera
     use_sw = bool(np.any(sample_weight != 1.0))
     G = len(devices)
     bounds = shard_rows(X.indptr, G)
-    uid = _lib.Comm.unique_id()
+    key = tuple(devices)
+    with _shard_comm_lock:
+        comms = _shard_comms.pop(key, None)   # communicators are kept between fits
+    uid = _lib.Comm.unique_id() if comms is None else None
+    comms = comms or [None] * G
     results, errors = [None] * G, [None] * G
     exchange = ThreadPeerExchange(devices) if p2p else None
 
     def worker(r):
-        comm = None
         try:
-            comm = _lib.Comm(devices[r], G, r, uid)
+            if comms[r] is None:
+                comms[r] = _lib.Comm(devices[r], G, r, uid)
+            comm = comms[r]
             lo, hi = bounds[r], bounds[r + 1]
             results[r] = plsa_fit_shard(X[lo:hi], k, p_z_given_d[lo:hi], p_w_given_z,
                                         sample_weight[lo:hi], comm, devices[r], n_iter,
@@ -261,18 +288,19 @@ def _plsa_fit_sharded(X, k, sample_weight, init, n_iter, n_iter_per_test, tolera
             errors[r] = exc
             if exchange is not None:
                 exchange.abort()
-        finally:
-            if comm is not None:
-                comm.close()
 
     threads = [threading.Thread(target=worker, args=(r,)) for r in range(G)]
     for t in threads:
         t.start()
     for t in threads:
         t.join()
-    for e in errors:
-        if e is not None:
-            raise e
+    if any(e is not None for e in errors):
+        for c in comms:
+            if c is not None:
+                c.close()
+        raise next(e for e in errors if e is not None)
+    with _shard_comm_lock:
+        _shard_comms[key] = comms
     iters = {res[2]["n_iter"] for res in results}
     if len(iters) != 1:
         raise _lib.PlsaError("sharded fit: ranks disagree on the iteration count {}".format(iters))
