@@ -76,6 +76,8 @@ SIGNATURES = {
                                         ctypes.POINTER(ctypes.c_void_p)]),
     "plsa_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "plsa_comm_gather_topics": (ctypes.c_int, [ctypes.c_void_p, _ctx, _i32p, _i32, _f32p]),
+    "plsa_gather_warmup": (ctypes.c_int, [_i32p, _i32]),
+    "plsa_stash_append": (ctypes.c_int, [_ctx, _ctx, _i32, _i32]),
     "plsa_topic_distances": (ctypes.c_int, [_i32, _f32p, _i64, _i64, _i32, _f64p]),
     "plsa_set_shard": (ctypes.c_int, [_ctx, ctypes.c_void_p]),
     "plsa_shard_p2p_prepare": (ctypes.c_int, [_ctx, ctypes.POINTER(ctypes.c_uint64), _i64p]),
@@ -411,6 +413,18 @@ def release_device_memory():
         _pool.clear()
     for c in ctxs:
         c.close()
+
+
+def gather_warmup(devices):
+    """Create the NCCL communicators gather_topics will need for this device list (kept by
+    the library); call it from a helper thread while the members are being fitted."""
+    devs = np.ascontiguousarray(devices, dtype=np.int32)
+    check(lib().plsa_gather_warmup(_ptr(devs, _i32p), len(devs)))
+
+
+def stash_append(dst, src, n_dst, n_src):
+    """Append src's first n_src stashed topic matrices to dst's first n_dst (same device)."""
+    check(lib().plsa_stash_append(dst._h, src._h, int(n_dst), int(n_src)), dst._h)
 
 
 def gather_topics(contexts, n_slots):

@@ -21,6 +21,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -42,11 +44,21 @@ struct DevBuf {
     cudaError_t ensure(size_t bytes)
     {
         if (bytes <= cap) return cudaSuccess;
+        /* a buffer that has to grow gets 1/16 of slack: bootstrapped ensemble members differ
+         * by a fraction of a percent in size, and cudaFree + cudaMalloc of tens of megabytes
+         * (with its device-wide synchronisation) per member costs more than the kernels */
+        const size_t want = p ? bytes + bytes / 16 : bytes;
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
-        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
-        if (e == cudaSuccess) cap = bytes;
+        cudaError_t e = cudaMalloc(&p, want ? want : 16);
+        if (e != cudaSuccess && want > bytes) {
+            cudaGetLastError();
+            e = cudaMalloc(&p, bytes);
+            if (e == cudaSuccess) cap = bytes;
+            return e;
+        }
+        if (e == cudaSuccess) cap = want;
         return e;
     }
     void release()
@@ -1626,6 +1638,77 @@ static int nccl_fail(Nccl *nc, const char *what, int r)
 }
 } // namespace
 
+/* Communicators of the single-process gather, kept per device list: ncclCommInitAll costs a
+ * few hundred milliseconds, more than a whole ensemble member; plsa_gather_warmup lets the
+ * host create them in the background while the members are being fitted. */
+namespace {
+std::mutex g_comm_mutex;
+std::map<std::vector<int>, std::vector<ncclComm_t>> g_comm_cache;
+
+static int cached_comms(Nccl *nc, const std::vector<int> &devs, std::vector<ncclComm_t> **out)
+{
+    std::lock_guard<std::mutex> lock(g_comm_mutex);
+    auto it = g_comm_cache.find(devs);
+    if (it == g_comm_cache.end()) {
+        std::vector<ncclComm_t> comms(devs.size());
+        const int r = nc->CommInitAll(comms.data(), (int)devs.size(), devs.data());
+        if (r != 0) return r;
+        it = g_comm_cache.emplace(devs, std::move(comms)).first;
+    }
+    *out = &it->second;
+    return 0;
+}
+} // namespace
+
+API int plsa_gather_warmup(const int32_t *devices, int32_t n_devices)
+{
+    if (!devices || n_devices < 1) {
+        g_err = "gather_warmup: bad arguments";
+        return PLSA_EINVAL;
+    }
+    if (n_devices == 1) return PLSA_OK;
+    Nccl *nc = load_nccl();
+    if (!nc) {
+        g_err = "gather_warmup: libnccl.so.2 could not be loaded";
+        return PLSA_ENCCL;
+    }
+    std::vector<int> devs(devices, devices + n_devices);
+    std::vector<ncclComm_t> *comms = nullptr;
+    const int r = cached_comms(nc, devs, &comms);
+    if (r != 0) return nccl_fail(nc, "gather_warmup: ncclCommInitAll", r);
+    return PLSA_OK;
+}
+
+/* Same device: append the stashed topic matrices of `src` to those of `dst` (two contexts
+ * per device keep the GPU busy while one of them prepares its next ensemble member). */
+API int plsa_stash_append(plsa_ctx *dst, plsa_ctx *src, int32_t n_dst, int32_t n_src)
+{
+    plsa_ctx *ctx = dst;
+    CHECK_CTX(ctx);
+    if (!src || src->device != dst->device) return ctx->fail(PLSA_EINVAL, "stash_append: contexts must share a device");
+    if (n_dst < 0 || n_src < 0 || (n_src > 0 && (!src->topics_dev.p || n_src > src->stash_slots)) ||
+        (n_dst > 0 && (!dst->topics_dev.p || n_dst > dst->stash_slots)))
+        return ctx->fail(PLSA_EINVAL, "stash_append: fewer stashed topic matrices than announced");
+    const size_t per = n_src > 0 ? src->stash_per : dst->stash_per;
+    if (n_dst > 0 && n_src > 0 && dst->stash_per != src->stash_per)
+        return ctx->fail(PLSA_EINVAL, "stash_append: contexts must share k and n_terms");
+    if (n_src == 0) return PLSA_OK;
+    DevBuf merged;
+    CK(merged.ensure(per * (size_t)(n_dst + n_src) * 4));
+    CK(cudaStreamSynchronize(src->stream));
+    if (n_dst > 0)
+        CK(cudaMemcpyAsync(merged.p, dst->topics_dev.p, per * (size_t)n_dst * 4,
+                           cudaMemcpyDeviceToDevice, dst->stream));
+    CK(cudaMemcpyAsync(merged.as<float>() + per * (size_t)n_dst, src->topics_dev.p,
+                       per * (size_t)n_src * 4, cudaMemcpyDeviceToDevice, dst->stream));
+    CK(cudaStreamSynchronize(dst->stream));
+    dst->topics_dev.release();
+    dst->topics_dev = merged;
+    dst->stash_slots = n_dst + n_src;
+    dst->stash_per = per;
+    return PLSA_OK;
+}
+
 /* Single process, one context per device (one host thread per GPU during the fits). */
 API int plsa_gather_topics(plsa_ctx **ctxs, int32_t n_ctx, const int32_t *n_slots, float *out)
 {
@@ -1678,12 +1761,14 @@ API int plsa_gather_topics(plsa_ctx **ctxs, int32_t n_ctx, const int32_t *n_slot
         }
         std::vector<int> devs((size_t)n_ctx);
         for (int i = 0; i < n_ctx; ++i) devs[(size_t)i] = ctxs[i]->device;
-        std::vector<ncclComm_t> comms((size_t)n_ctx);
-        int r = nc->CommInitAll(comms.data(), n_ctx, devs.data());
+        std::vector<ncclComm_t> *cached = nullptr;
+        int r = cached_comms(nc, devs, &cached);
         if (r != 0) {
             stack.release();
             return nccl_fail(nc, "gather_topics: ncclCommInitAll", r);
         }
+        std::vector<ncclComm_t> &comms = *cached;
+        std::lock_guard<std::mutex> use(g_comm_mutex); /* one gather at a time per process */
         nc->GroupStart();
         size_t off = (size_t)n_slots[0] * per;
         for (int i = 1; i < n_ctx && r == 0; ++i) {
@@ -1703,7 +1788,6 @@ API int plsa_gather_topics(plsa_ctx **ctxs, int32_t n_ctx, const int32_t *n_slot
             cudaSetDevice(ctxs[i]->device);
             cudaStreamSynchronize(ctxs[i]->stream);
         }
-        for (int i = 0; i < n_ctx; ++i) nc->CommDestroy(comms[(size_t)i]);
         if (r != 0) rc = nccl_fail(nc, "gather_topics", r);
     }
     cudaSetDevice(root->device);

@@ -88,7 +88,7 @@ def plsa_topics(X, k, **kwargs):
             tolerance=kwargs.get("tolerance", 0.001),
             e_step_thresh=kwargs.get("e_step_thresh", 1e-16),
             random_state=kwargs.get("random_state", None),
-            context=context)
+            context=context, download=kwargs.get("download", True))
     finally:
         if owned:
             context.close()
@@ -147,24 +147,34 @@ def ensemble_of_topics(X, k, model="plsa", n_jobs=4, n_runs=16, parallelism="thr
         devices = devices[:1]
     seeds = member_seeds(kwargs.get("random_state", None), n_runs)
     assign = dict(zip(devices, shard_members(n_runs, len(devices))))
+    # Two contexts ("lanes") per device, each with its own host thread and stream: while one
+    # lane's member is in its EM loop the other draws its bootstrap and seeded start on the
+    # host and rebuilds its term-major copy, so the GPU does not idle between members.
+    lanes = {d: [assign[d][0::2], assign[d][1::2]] if len(assign[d]) > 1 else [assign[d]]
+             for d in devices}
     contexts, errors = {}, []
 
-    def worker(dev):
+    def worker(dev, lane):
         try:
-            ctx = _lib.Context(dev)
-            contexts[dev] = ctx
-            ctx.upload_csr(X)
-            members = assign[dev]
+            ctx = _lib.acquire_context(dev)   # pooled: creating and destroying a context
+            contexts[(dev, lane)] = ctx       # (pinned staging, ~20 device buffers) costs more
+            ctx.upload_csr(X)                 # than several members
+            members = lanes[dev][lane]
             for slot, r in enumerate(members):
                 kw = dict(kwargs)
                 kw["random_state"] = seeds[r]
                 kw["context"] = ctx
+                kw["download"] = False        # the topics stay on the device until the gather
                 plsa_topics(X, k, **kw)
                 ctx.stash_topics(slot, len(members))
         except Exception as exc:  # surfaced after join
             errors.append(exc)
 
-    threads = [threading.Thread(target=worker, args=(d,)) for d in devices if assign[d]]
+    used = [d for d in devices if assign[d]]
+    threads = [threading.Thread(target=worker, args=(d, lane))
+               for d in used for lane in range(len(lanes[d]))]
+    if len(used) > 1:   # NCCL communicators of the final gather, created meanwhile
+        threads.append(threading.Thread(target=lambda: _lib.gather_warmup(used)))
     for t in threads:
         t.start()
     for t in threads:
@@ -172,13 +182,21 @@ def ensemble_of_topics(X, k, model="plsa", n_jobs=4, n_runs=16, parallelism="thr
     try:
         if errors:
             raise errors[0]
-        used = [d for d in devices if assign[d]]
-        stacked = _lib.gather_topics([contexts[d] for d in used],
+        for d in used:      # one stash per device: lane 0's members, then lane 1's
+            if len(lanes[d]) > 1:
+                _lib.stash_append(contexts[(d, 0)], contexts[(d, 1)], len(lanes[d][0]),
+                                  len(lanes[d][1]))
+        stacked = _lib.gather_topics([contexts[(d, 0)] for d in used],
                                      [len(assign[d]) for d in used])
     finally:
         for ctx in contexts.values():
-            ctx.close()
-    out = stack_in_member_order(stacked, [assign[d] for d in used], k)
+            if errors:
+                ctx.close()
+            else:
+                ctx.bootstrap(None)
+                _lib.release_context(ctx)
+    order = [[r for lane in lanes[d] for r in lane] for d in used]
+    out = stack_in_member_order(stacked, order, k)
     if return_seeds:
         return out, seeds
     return out

@@ -313,13 +313,14 @@ def _plsa_fit_sharded(X, k, sample_weight, init, n_iter, n_iter_per_test, tolera
 
 def plsa_fit(X, k, sample_weight, init="random", n_iter=100, n_iter_per_test=10,
              tolerance=0.001, e_step_thresh=1e-32, random_state=None, *, device=None,
-             context=None, return_info=False, devices=None):
+             context=None, return_info=False, devices=None, download=True):
     """Fit pLSA with ``k`` topics; returns ``(p_z_given_d [n,k], p_w_given_z [k,m])`` float32.
 
     Drop-in for enstop.plsa.plsa_fit (plsa.py:643-730).  ``context`` (an
     ``enstop_b200._lib.Context`` whose resident corpus is X) skips the upload — used by the
     ensemble for its bootstrapped members.  ``devices`` (a list of two or more CUDA ordinals)
-    shards the documents of this one fit over those GPUs."""
+    shards the documents of this one fit over those GPUs.  ``download=False`` leaves the
+    factors on the device (the ensemble stashes P(w|z) there) and returns (None, None)."""
     if devices is not None and len(devices) > 1:
         out = _plsa_fit_sharded(X, k, sample_weight, init, n_iter, n_iter_per_test, tolerance,
                                 e_step_thresh, random_state, [int(d) for d in devices],
@@ -345,7 +346,7 @@ def plsa_fit(X, k, sample_weight, init="random", n_iter=100, n_iter_per_test=10,
         ctx.set_sample_weight(sample_weight if use_sample_weights else None)
         iters, trace = ctx.em(n_iter, n_iter_per_test, tolerance, e_step_thresh, refit=False,
                               use_sample_weights=use_sample_weights)
-        p_z_given_d, p_w_given_z = ctx.get_factors()
+        p_z_given_d, p_w_given_z = ctx.get_factors() if download else (None, None)
         info = {"n_iter": iters, "ll_trace": trace, "em_ms": ctx.last_em_ms,
                 "launches": ctx.launches}
     finally:

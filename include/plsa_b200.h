@@ -163,6 +163,13 @@ int plsa_topics_device(plsa_ctx *ctx, void **device_ptr, int64_t *floats_per_slo
  * (host, [sum(n_slots) * k, n_terms], context order then slot order).  One context, or no
  * remote slots, never touches NCCL. */
 int plsa_gather_topics(plsa_ctx **ctxs, int32_t n_ctx, const int32_t *n_slots, float *out);
+/* Create (and keep, per device list) the communicators plsa_gather_topics will use, e.g. from
+ * a helper thread while the members are still being fitted: ncclCommInitAll takes longer
+ * than an ensemble member. */
+int plsa_gather_warmup(const int32_t *devices, int32_t n_devices);
+/* Append slots [0, n_src) of src's stash to slots [0, n_dst) of dst's (both on one device):
+ * lets several contexts share a GPU during the fits and still gather one stash per device. */
+int plsa_stash_append(plsa_ctx *dst, plsa_ctx *src, int32_t n_dst, int32_t n_src);
 
 /* One process per GPU (torchrun-style launch).  Rank 0 obtains a unique id, the caller's
  * own rendezvous hands its PLSA_NCCL_ID_BYTES bytes to every rank, each rank creates a
