@@ -552,6 +552,7 @@ def main():
         uid = plumb.bcast_bytes(_lib.Comm.unique_id() if rank == 0 else None)
         comm = _lib.Comm(device, world, rank, uid)
         ctx.stash_topics(0, 1)
+        comm.gather_topics(ctx, [1] * world, root=0)     # first use: NCCL connects its peers
         plumb.barrier()
         g0 = time.perf_counter()
         stacked = comm.gather_topics(ctx, [1] * world, root=0)
