@@ -408,7 +408,10 @@ __device__ __forceinline__ void pass_block(const PassArgs &a, const int2 (&e)[U]
             if constexpr (MODE == MODE_DOC_LL) lg = log2_ftz(norm) * 0.69314718f;
             else lg = __logf(norm);
             llt[u] = (x != 0.f) ? x * rw * lg : 0.f;
-            if constexpr (MODE == MODE_DOC_LL) min_norm = fminf(min_norm, (x != 0.f) ? norm : 1.f);
+            /* idle lanes (32 % G of them) shadow the last group with a zero owned row: their
+             * sums are not sums of an entry */
+            if constexpr (MODE == MODE_DOC_LL)
+                min_norm = fminf(min_norm, (lane_on && x != 0.f) ? norm : 1.f);
         }
         if constexpr (MODE != MODE_LOGLIK) {
             /* plsa.py:104: posterior = v / norm if norm > 0.  Products that survive the
