@@ -51,6 +51,8 @@ SIGNATURES = {
     "plsa_corpus_shape": (ctypes.c_int, [_ctx, _i64p, _i64p, _i64p]),
     "plsa_set_factors": (ctypes.c_int, [_ctx, _f32p, _f32p, _i32]),
     "plsa_set_sample_weight": (ctypes.c_int, [_ctx, _f32p]),
+    "plsa_pinned_factors": (ctypes.c_int, [_ctx, _i64, _i64, _i32, ctypes.POINTER(_f32p),
+                                           ctypes.POINTER(_f32p)]),
     "plsa_get_factors": (ctypes.c_int, [_ctx, _f32p, _f32p]),
     "plsa_stash_topics": (ctypes.c_int, [_ctx, _i32, _i32]),
     "plsa_topics_device": (ctypes.c_int, [_ctx, ctypes.POINTER(ctypes.c_void_p), _i64p]),
@@ -159,11 +161,12 @@ def check(rc, ctx=None):
         raise PlsaError("libplsa_b200: %s: %s" % (kind, msg))
 
 
-def random_rows(rng, rows, cols, want_f64=False):
+def random_rows(rng, rows, cols, want_f64=False, out=None):
     """``rng.rand(rows, cols)`` L1-row-normalised in float64 and cast to float32, computed by
     the library from the RandomState's own MT19937 state (which is advanced exactly as numpy
     would).  Returns None when ``rng`` is not a legacy MT19937 RandomState (caller falls back
-    to numpy)."""
+    to numpy).  ``out``: a C-contiguous float32 [rows, cols] array to fill (e.g. a view of the
+    context's pinned staging, Context.pinned_factors)."""
     owner = np.random if rng is np.random else rng
     get_state = getattr(owner, "get_state", None)
     if get_state is None or not (owner is np.random or isinstance(owner, np.random.RandomState)):
@@ -173,7 +176,10 @@ def random_rows(rng, rows, cols, want_f64=False):
         return None
     key = np.ascontiguousarray(state[1], dtype=np.uint32).copy()
     pos = _i32(int(state[2]))
-    out = np.empty((rows, cols), dtype=np.float32)
+    if out is None:
+        out = np.empty((rows, cols), dtype=np.float32)
+    elif out.shape != (rows, cols) or out.dtype != np.float32 or not out.flags.c_contiguous:
+        raise ValueError("random_rows: out must be a C-contiguous float32 [rows, cols] array")
     out64 = np.empty((rows, cols), dtype=np.float64) if want_f64 else None
     check(lib().plsa_host_random_rows(key.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
                                       ctypes.byref(pos), rows, cols, _ptr(out, _f32p),
@@ -284,6 +290,20 @@ class Context:
                              % (pzd.shape, pwz.shape, (n, m), k))
         check(self._L.plsa_set_factors(self._h, _ptr(pzd, _f32p), _ptr(pwz, _f32p), k), self._h)
         self.k = k
+
+    def pinned_factors(self, n_docs, n_terms, k):
+        """Two float32 numpy views ([n_docs, k], [k, n_terms]) of page-locked memory owned by
+        this context, valid until the next call or the context's end: draw the initial
+        factors into them, then set_factors.  May be called while another thread uploads
+        the corpus through this context."""
+        a, b = _f32p(), _f32p()
+        check(self._L.plsa_pinned_factors(self._h, int(n_docs), int(n_terms), int(k),
+                                          ctypes.byref(a), ctypes.byref(b)), self._h)
+        pzd = np.ctypeslib.as_array(a, shape=(int(n_docs), int(k))) if n_docs else \
+            np.empty((0, int(k)), dtype=np.float32)
+        pwz = np.ctypeslib.as_array(b, shape=(int(k), int(n_terms))) if n_terms else \
+            np.empty((int(k), 0), dtype=np.float32)
+        return pzd, pwz
 
     def set_sample_weight(self, sample_weight):
         if sample_weight is None:

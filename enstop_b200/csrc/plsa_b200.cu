@@ -126,6 +126,9 @@ struct plsa_ctx {
     cudaStream_t pin_stream[H2D_THREADS] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t pin_ev[H2D_THREADS][2] = {};
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_go = nullptr;
+    /* pinned host block the caller may draw the initial factors into (plsa_pinned_factors) */
+    char *pin_factors = nullptr;
+    size_t pin_factors_cap = 0;
     cudaTextureObject_t texA[2] = {0, 0}, texB[2] = {0, 0};
     size_t tex_max_texels = 0;
 
@@ -399,8 +402,10 @@ static int64_t choose_chunk(const plsa_ctx *ctx, int kp)
 }
 
 static int build_items(plsa_ctx *ctx, const std::vector<int32_t> &indptr, int64_t rows,
-                       ItemSet &out, const int64_t chunk_asked, int align)
+                       ItemSet &out, const int64_t chunk_asked, int align,
+                       cudaStream_t stream = nullptr)
 {
+    if (!stream) stream = ctx->stream;
     const int64_t chunk = chunk_asked / align * align; /* chunks of a split row stay aligned */
     std::vector<Item> items;
     items.reserve((size_t)rows + 1024);
@@ -464,16 +469,16 @@ static int build_items(plsa_ctx *ctx, const std::vector<int32_t> &indptr, int64_
     out.n_slots = slots;
     CK(out.items.ensure(sorted.size() * sizeof(Item)));
     CK(cudaMemcpyAsync(out.items.p, sorted.data(), sorted.size() * sizeof(Item),
-                       cudaMemcpyHostToDevice, ctx->stream));
+                       cudaMemcpyHostToDevice, stream));
     CK(out.split_rows.ensure(split_rows.size() * sizeof(int32_t)));
     CK(out.slot_begin.ensure(slot_begin.size() * sizeof(int32_t)));
     if (!split_rows.empty())
         CK(cudaMemcpyAsync(out.split_rows.p, split_rows.data(),
                            split_rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
-                           ctx->stream));
+                           stream));
     CK(cudaMemcpyAsync(out.slot_begin.p, slot_begin.data(), slot_begin.size() * sizeof(int32_t),
-                       cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream)); /* host vectors die here */
+                       cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream)); /* host vectors die here */
     out.ready = true;
     out.chunk = chunk_asked;
     out.align = align;
@@ -660,6 +665,7 @@ API int plsa_ctx_destroy(plsa_ctx *ctx)
         if (ctx->texB[i]) cudaDestroyTextureObject(ctx->texB[i]);
     }
     if (ctx->mail) cudaFreeHost(ctx->mail);
+    if (ctx->pin_factors) cudaFreeHost(ctx->pin_factors);
     for (int t = 0; t < plsa_ctx::H2D_THREADS; ++t) {
         if (ctx->pin[t]) cudaFreeHost(ctx->pin[t]);
         if (ctx->pin_stream[t]) cudaStreamDestroy(ctx->pin_stream[t]);
@@ -933,6 +939,30 @@ API int plsa_set_factors(plsa_ctx *ctx, const float *p_z_given_d, const float *p
     return PLSA_OK;
 }
 
+/* Page-locked host memory for the initial factors, owned by the context and reused by later
+ * fits: the seeded initialisation writes straight into it (no first-touch page faults on 12 MB
+ * of fresh pages) and plsa_set_factors then copies at full PCIe speed.  May be called while
+ * another thread uploads the corpus through the same context: it touches nothing else. */
+API int plsa_pinned_factors(plsa_ctx *ctx, int64_t n_docs, int64_t n_terms, int32_t k,
+                            float **p_z_given_d, float **p_w_given_z)
+{
+    CHECK_CTX(ctx);
+    if (n_docs < 0 || n_terms < 0 || k < 1 || k > PLSA_MAX_K || !p_z_given_d || !p_w_given_z)
+        return ctx->fail(PLSA_EINVAL, "pinned_factors: bad arguments");
+    const size_t a = ((size_t)n_docs * k * 4 + 255) / 256 * 256, b = (size_t)n_terms * k * 4;
+    if (a + b > ctx->pin_factors_cap) {
+        if (ctx->pin_factors) cudaFreeHost(ctx->pin_factors);
+        ctx->pin_factors = nullptr;
+        ctx->pin_factors_cap = 0;
+        const size_t want = (a + b) + (a + b) / 16 + 256;
+        CK(cudaHostAlloc((void **)&ctx->pin_factors, want, cudaHostAllocDefault));
+        ctx->pin_factors_cap = want;
+    }
+    *p_z_given_d = reinterpret_cast<float *>(ctx->pin_factors);
+    *p_w_given_z = reinterpret_cast<float *>(ctx->pin_factors + a);
+    return PLSA_OK;
+}
+
 API int plsa_set_sample_weight(plsa_ctx *ctx, const float *sample_weight)
 {
     CHECK_CTX(ctx);
@@ -990,9 +1020,26 @@ static int ensure_items(plsa_ctx *ctx, bool refit, int kp)
     const int64_t chunk = choose_chunk(ctx, kp);
     const int align = ctx->vec_entries ? pass_entry_block(kp) : 1;
     int rc;
-    if (!ctx->doc_items.ready || ctx->doc_items.chunk != chunk || ctx->doc_items.align != align)
+    const bool need_doc = !ctx->doc_items.ready || ctx->doc_items.chunk != chunk ||
+                          ctx->doc_items.align != align;
+    if (need_doc && !refit && !ctx->t_ready) {
+        /* the doc items are host work (plus one small copy on the second stream): build them on
+         * a helper thread while this one drives the term-major sort on the device */
+        int rc_doc = PLSA_OK;
+        const int device = ctx->device;
+        std::thread helper([&]() {
+            cudaSetDevice(device);
+            rc_doc = build_items(ctx, ctx->cur().h_indptr, ctx->cur().n, ctx->doc_items, chunk, align,
+                                 ctx->stream2);
+        });
+        rc = build_term_major(ctx);
+        helper.join();
+        if (rc_doc) return rc_doc;
+        if (rc) return rc;
+    } else if (need_doc) {
         if ((rc = build_items(ctx, ctx->cur().h_indptr, ctx->cur().n, ctx->doc_items, chunk, align)))
             return rc;
+    }
     if (!refit) {
         if (!ctx->t_ready && (rc = build_term_major(ctx))) return rc;
         if (!ctx->term_items.ready || ctx->term_items.chunk != chunk ||

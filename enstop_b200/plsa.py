@@ -80,16 +80,21 @@ def plsa_init(X, k, init="random", rng=np.random):
     return p_z_given_d, p_w_given_z
 
 
-def _random_init_f32(n, m, k, rng):
+def _random_init_f32(n, m, k, rng, ctx=None):
     """The "random" start of plsa_init + the float32 cast of plsa_fit (plsa.py:454-456,
     510-511, 709-710) in one pass over the RandomState's own MT19937 stream
-    (csrc/host_init.cpp): bit-identical factors, a quarter of the host time.  Returns None
-    when ``rng`` is not a legacy RandomState (then numpy does it)."""
+    (csrc/host_init.cpp): bit-identical factors, a quarter of the host time.  With ``ctx`` the
+    factors are drawn straight into the context's page-locked staging (views, valid until the
+    context's next fit).  Returns None when ``rng`` is not a legacy RandomState (then numpy
+    does it)."""
     try:
-        p_w_given_z = _lib.random_rows(rng, k, m)
+        out_pzd = out_pwz = None
+        if ctx is not None and n > 0 and m > 0:
+            out_pzd, out_pwz = ctx.pinned_factors(n, m, k)
+        p_w_given_z = _lib.random_rows(rng, k, m, out=out_pwz)
         if p_w_given_z is None:
             return None
-        p_z_given_d = _lib.random_rows(rng, n, k)
+        p_z_given_d = _lib.random_rows(rng, n, k, out=out_pzd)
     except _lib.PlsaError:
         return None
     return p_z_given_d, p_w_given_z
@@ -313,7 +318,7 @@ def _plsa_fit_sharded(X, k, sample_weight, init, n_iter, n_iter_per_test, tolera
 
 def plsa_fit(X, k, sample_weight, init="random", n_iter=100, n_iter_per_test=10,
              tolerance=0.001, e_step_thresh=1e-32, random_state=None, *, device=None,
-             context=None, return_info=False, devices=None, download=True):
+             context=None, return_info=False, devices=None, download=True, precheck=None):
     """Fit pLSA with ``k`` topics; returns ``(p_z_given_d [n,k], p_w_given_z [k,m])`` float32.
 
     Drop-in for enstop.plsa.plsa_fit (plsa.py:643-730).  ``context`` (an
@@ -322,6 +327,8 @@ def plsa_fit(X, k, sample_weight, init="random", n_iter=100, n_iter_per_test=10,
     shards the documents of this one fit over those GPUs.  ``download=False`` leaves the
     factors on the device (the ensemble stashes P(w|z) there) and returns (None, None)."""
     if devices is not None and len(devices) > 1:
+        if precheck is not None:
+            precheck()
         out = _plsa_fit_sharded(X, k, sample_weight, init, n_iter, n_iter_per_test, tolerance,
                                 e_step_thresh, random_state, [int(d) for d in devices],
                                 p2p=os.environ.get("ENSTOP_B200_P2P", "1") != "0")
@@ -331,7 +338,7 @@ def plsa_fit(X, k, sample_weight, init="random", n_iter=100, n_iter_per_test=10,
     staging = _Staging(X, k, device, context, refit=False)
     try:
         rng = check_random_state(random_state)
-        fast = _random_init_f32(X.shape[0], X.shape[1], k, rng) \
+        fast = _random_init_f32(X.shape[0], X.shape[1], k, rng, ctx=staging.ctx) \
             if isinstance(init, str) and init == "random" else None
         if fast is not None:
             p_z_given_d, p_w_given_z = fast
@@ -341,6 +348,8 @@ def plsa_fit(X, k, sample_weight, init="random", n_iter=100, n_iter_per_test=10,
             p_w_given_z = p_w_given_z.astype(np.float32, order="C")
         sample_weight = np.asarray(sample_weight, dtype=np.float32)
         use_sample_weights = bool(np.any(sample_weight != 1.0))  # plsa.py:712
+        if precheck is not None:
+            precheck()      # input validation that ran beside the staging; may raise
         ctx = staging.wait()
         ctx.set_factors(p_z_given_d, p_w_given_z)
         ctx.set_sample_weight(sample_weight if use_sample_weights else None)
@@ -388,6 +397,37 @@ def plsa_refit(X, topics, sample_weight, n_iter=50, n_iter_per_test=10, toleranc
     return p_z_given_d
 
 
+class _StoredZeros(Exception):
+    """The matrix stores explicit zeros: empty rows must be found from the row sums."""
+
+
+class _ValueCheck:
+    """min over the stored values on a helper thread (numpy releases the GIL in reductions)."""
+
+    ASYNC_FROM = 2_000_000   # stored entries; below this the check costs less than a thread
+
+    def __init__(self, X):
+        self.min = 0
+        self.thread = None
+        if X.nnz >= self.ASYNC_FROM:
+            self.thread = threading.Thread(target=self._run, args=(X.data,))
+            self.thread.start()
+        elif X.nnz:
+            self.min = X.data.min()
+
+    def _run(self, data):
+        self.min = data.min()
+
+    def result(self):
+        if self.thread is not None:
+            self.thread.join()
+            self.thread = None
+        if self.min < 0:
+            raise ValueError("PLSA is only valid for matrices with non-negative entries")
+        if self.min == 0:
+            raise _StoredZeros()
+
+
 class PLSA(BaseEstimator, TransformerMixin):
     """Probabilistic Latent Semantic Analysis, sklearn-style (mirrors plsa.py:1000-1285).
 
@@ -428,29 +468,22 @@ class PLSA(BaseEstimator, TransformerMixin):
         if not issparse(X):
             X = csr_matrix(X)
         sample_weight = _check_sample_weight(sample_weight, X, dtype=np.float32)
-        data_min = X.data.min() if X.nnz else 0
-        if data_min < 0:
-            raise ValueError("PLSA is only valid for matrices with non-negative entries")
-        if data_min > 0:
-            # every stored entry is positive: a row sums to zero iff it stores nothing
-            good_rows = np.diff(X.indptr) != 0
-        else:
+        # The sign check of plsa.py:1146-1149 reads every stored value (2 ms at 10 M entries): it
+        # runs on a helper thread while the fit stages the corpus and draws its start, and is
+        # joined before the first EM iteration.  Rows are taken as empty iff they store
+        # nothing, which is exact unless explicit zeros are stored; then the row sums of
+        # plsa.py:1151-1153 decide and the fit is redone on the stripped matrix.
+        check = _ValueCheck(X)
+        good_rows = np.diff(X.indptr) != 0
+        try:
+            if check.thread is None:      # small input: checked on the spot
+                check.result()
+                check = None
+            U, V, info, good_rows = self._fit_rows(X, sample_weight, good_rows, check)
+        except _StoredZeros:
             row_sums = np.array(X.sum(axis=1).T)[0]
-            good_rows = row_sums != 0
-        if not np.all(good_rows):
-            zero_rows_found = True
-            data_for_fitting = X[good_rows]
-            # plsa.py:1144 vs :1156-1164 leaves the weights unaligned with the stripped
-            # matrix; the weights of the kept rows are what is meant
-            sample_weight = sample_weight[good_rows]
-        else:
-            zero_rows_found = False
-            data_for_fitting = X
-
-        U, V, info = plsa_fit(data_for_fitting, self.n_components, sample_weight, self.init,
-                              self.n_iter, self.n_iter_per_test, self.tolerance,
-                              self.e_step_thresh, self.random_state, device=self.device,
-                              return_info=True, devices=self.devices)
+            U, V, info, good_rows = self._fit_rows(X, sample_weight, row_sums != 0, None)
+        zero_rows_found = not np.all(good_rows)
         if zero_rows_found:
             self.embedding_ = np.zeros((X.shape[0], self.n_components))
             self.embedding_[good_rows] = U
@@ -461,6 +494,21 @@ class PLSA(BaseEstimator, TransformerMixin):
         self.n_iter_ = info["n_iter"]
         self.log_likelihood_trace_ = info["ll_trace"]
         return self.embedding_
+
+    def _fit_rows(self, X, sample_weight, good_rows, check):
+        if not np.all(good_rows):
+            data_for_fitting = X[good_rows]
+            # plsa.py:1144 vs :1156-1164 leaves the weights unaligned with the stripped
+            # matrix; the weights of the kept rows are what is meant
+            sample_weight = sample_weight[good_rows]
+        else:
+            data_for_fitting = X
+        U, V, info = plsa_fit(data_for_fitting, self.n_components, sample_weight, self.init,
+                              self.n_iter, self.n_iter_per_test, self.tolerance,
+                              self.e_step_thresh, self.random_state, device=self.device,
+                              return_info=True, devices=self.devices,
+                              precheck=check.result if check is not None else None)
+        return U, V, info, good_rows
 
     def transform(self, X, y=None):
         X = check_array(X, accept_sparse="csr")

@@ -82,6 +82,13 @@ int plsa_corpus_shape(const plsa_ctx *ctx, int64_t *n_docs, int64_t *n_terms, in
 /* p_z_given_d [n_docs, k], p_w_given_z [k, n_terms] (plsa.py:709-710 float32 C-order). */
 int plsa_set_factors(plsa_ctx *ctx, const float *p_z_given_d, const float *p_w_given_z,
                      int32_t k);
+/* Page-locked host memory owned by the context for the two initial factors ([n_docs, k] and
+ * [k, n_terms] float32; valid until the next call with larger sizes or the context's end):
+ * a host-side initialisation that writes into it skips the page faults of fresh memory and
+ * plsa_set_factors copies from it at full PCIe speed.  Safe to call while another thread is
+ * inside plsa_upload_csr* / plsa_prepare on the same context. */
+int plsa_pinned_factors(plsa_ctx *ctx, int64_t n_docs, int64_t n_terms, int32_t k,
+                        float **p_z_given_d, float **p_w_given_z);
 /* sample_weight [n_docs] or NULL for all ones (plsa.py:1144). */
 int plsa_set_sample_weight(plsa_ctx *ctx, const float *sample_weight);
 /* Either output may be NULL. */

@@ -322,6 +322,30 @@ def test_estimator_semantics(golden_small):
         model.coherence(topic_num=k)
 
 
+def test_async_value_check(golden_small, monkeypatch):
+    """Large inputs are sign-checked on a helper thread beside the staging (PLSA.fit): same
+    error, same handling of stored zeros and empty rows as the synchronous path."""
+    g, X = golden_small
+    k = int(g["k"])
+    sync = plsa.PLSA(n_components=k, n_iter=8, tolerance=0.0, random_state=2, device=0).fit(X)
+    row7 = X[7].copy().astype(np.float64)     # row 7: every stored entry an explicit zero
+    row7.data[:] = 0.0
+    Xz = sp.vstack([X[:7].astype(np.float64), row7, X[8:].astype(np.float64)]).tocsr()
+    assert Xz.indptr[8] > Xz.indptr[7] and not Xz[7].data.any()   # stored, all zero
+    sync_z = plsa.PLSA(n_components=k, n_iter=8, tolerance=0.0, random_state=2, device=0).fit(Xz)
+    monkeypatch.setattr(plsa._ValueCheck, "ASYNC_FROM", 0)
+    a = plsa.PLSA(n_components=k, n_iter=8, tolerance=0.0, random_state=2, device=0).fit(X)
+    assert np.array_equal(a.components_, sync.components_)
+    assert np.array_equal(a.embedding_, sync.embedding_)
+    a_z = plsa.PLSA(n_components=k, n_iter=8, tolerance=0.0, random_state=2, device=0).fit(Xz)
+    assert np.array_equal(a_z.components_, sync_z.components_)
+    assert np.array_equal(a_z.embedding_, sync_z.embedding_) and not a_z.embedding_[7].any()
+    with pytest.raises(ValueError, match="non-negative"):
+        Xn = X.copy().astype(np.float64)
+        Xn.data[3] = -1.0
+        plsa.PLSA(n_components=k, device=0).fit(Xn)
+
+
 def test_errors_are_codes_not_aborts():
     L = _lib.lib()
     with _lib.Context(0) as ctx:
