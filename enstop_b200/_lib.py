@@ -77,6 +77,7 @@ SIGNATURES = {
     "plsa_comm_create": (ctypes.c_int, [ctypes.c_int, _i32, _i32, ctypes.c_char_p,
                                         ctypes.POINTER(ctypes.c_void_p)]),
     "plsa_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "plsa_comm_abort": (ctypes.c_int, [ctypes.c_void_p]),
     "plsa_comm_gather_topics": (ctypes.c_int, [ctypes.c_void_p, _ctx, _i32p, _i32, _f32p]),
     "plsa_gather_warmup": (ctypes.c_int, [_i32p, _i32]),
     "plsa_stash_append": (ctypes.c_int, [_ctx, _ctx, _i32, _i32]),
@@ -499,6 +500,11 @@ class Comm:
         check(self._L.plsa_comm_gather_topics(self._h, ctx._h, _ptr(counts, _i32p), int(root),
                                               _ptr(out, _f32p)), ctx._h)
         return out
+
+    def abort(self):
+        """Cancel outstanding collectives so that peers blocked on this communicator return."""
+        if self._h:
+            self._L.plsa_comm_abort(self._h)
 
     def close(self):
         if self._h:

@@ -1624,6 +1624,7 @@ typedef int (*fn_GetUniqueId)(NcclId *);
 typedef int (*fn_CommInitRank)(ncclComm_t *, int, NcclId, int);
 typedef int (*fn_CommInitAll)(ncclComm_t *, int, const int *);
 typedef int (*fn_CommDestroy)(ncclComm_t);
+typedef int (*fn_CommAbort)(ncclComm_t);
 typedef int (*fn_GroupStart)(void);
 typedef int (*fn_GroupEnd)(void);
 typedef int (*fn_Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t);
@@ -1636,6 +1637,7 @@ struct Nccl {
     fn_CommInitRank CommInitRank;
     fn_CommInitAll CommInitAll;
     fn_CommDestroy CommDestroy;
+    fn_CommAbort CommAbort; /* optional */
     fn_GroupStart GroupStart;
     fn_GroupEnd GroupEnd;
     fn_Send Send;
@@ -1662,6 +1664,7 @@ static Nccl *load_nccl()
     n.CommInitRank = (fn_CommInitRank)dlsym(n.h, "ncclCommInitRank");
     n.CommInitAll = (fn_CommInitAll)dlsym(n.h, "ncclCommInitAll");
     n.CommDestroy = (fn_CommDestroy)dlsym(n.h, "ncclCommDestroy");
+    n.CommAbort = (fn_CommAbort)dlsym(n.h, "ncclCommAbort");
     n.GroupStart = (fn_GroupStart)dlsym(n.h, "ncclGroupStart");
     n.GroupEnd = (fn_GroupEnd)dlsym(n.h, "ncclGroupEnd");
     n.Send = (fn_Send)dlsym(n.h, "ncclSend");
@@ -2024,6 +2027,22 @@ API int plsa_shard_p2p_attach(plsa_ctx *ctx, int32_t peer_rank, int32_t peer_dev
     if (!ptr) return ctx->fail(PLSA_EINVAL, "shard_p2p_attach: null peer block");
     ctx->p2p.peer_base[peer_rank] = ptr;
     ctx->p2p.n_attached++;
+    return PLSA_OK;
+}
+
+/* Tear the communicator down without waiting for outstanding collectives (ncclCommAbort):
+ * called for every rank of a sharded fit when one of them failed, so that the others do not
+ * wait for it forever.  The handle stays valid for plsa_comm_destroy. */
+API int plsa_comm_abort(plsa_comm *c)
+{
+    if (!c) return PLSA_OK;
+    cudaSetDevice(c->device);
+    if (c->comm) {
+        Nccl *nc = load_nccl();
+        if (nc && nc->CommAbort) nc->CommAbort(c->comm);
+        else if (nc) nc->CommDestroy(c->comm);
+        c->comm = nullptr;
+    }
     return PLSA_OK;
 }
 

@@ -293,6 +293,9 @@ def _plsa_fit_sharded(X, k, sample_weight, init, n_iter, n_iter_per_test, tolera
             errors[r] = exc
             if exchange is not None:
                 exchange.abort()
+            for c in comms:          # peers blocked in a collective with this rank return
+                if c is not None:
+                    c.abort()
 
     threads = [threading.Thread(target=worker, args=(r,)) for r in range(G)]
     for t in threads:

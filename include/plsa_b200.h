@@ -187,6 +187,9 @@ int plsa_nccl_unique_id(char *id /*[PLSA_NCCL_ID_BYTES]*/);
 int plsa_comm_create(int device, int32_t n_ranks, int32_t rank,
                      const char *id /*[PLSA_NCCL_ID_BYTES]*/, plsa_comm **comm);
 int plsa_comm_destroy(plsa_comm *comm);
+/* Abort outstanding collectives (ncclCommAbort): lets the surviving ranks of a failed sharded
+ * fit return an error instead of waiting.  plsa_comm_destroy must still follow. */
+int plsa_comm_abort(plsa_comm *comm);
 int plsa_comm_gather_topics(plsa_comm *comm, plsa_ctx *ctx, const int32_t *n_per_rank,
                             int32_t root, float *out);
 
