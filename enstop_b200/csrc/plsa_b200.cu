@@ -375,6 +375,20 @@ static int launch_pass(plsa_ctx *ctx, int mode, const PassArgs &a, bool vec,
 {
     if (a.n_items == 0) return PLSA_OK;
     pass_fn fn = pick_kernel(a.kp, mode, ctx->use_texture && a.gat_tex != 0, vec);
+    {   /* The pass lives on L1 hits of the gathered factor rows and uses next to no shared
+         * memory (the term pass 5 KB per CTA for its column sums): ask for the smallest
+         * shared-memory carve-out that still holds the resident CTAs (ncu showed 64 KB being
+         * set aside for the term pass by default). */
+        static std::mutex mu;
+        static std::map<pass_fn, bool> configured;
+        std::lock_guard<std::mutex> lock(mu);
+        if (!configured[fn]) {
+            cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 mode == MODE_TERM ? 15 : 5);
+            cudaGetLastError(); /* a hint: failure is not an error */
+            configured[fn] = true;
+        }
+    }
     fn<<<(unsigned)pass_grid(a.n_items, a.kp), 256, 0, stream ? stream : ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
