@@ -317,8 +317,17 @@ def run_shard(args, plumb, rank, world, device):
     ctx.set_factors(pzd0[lo:hi].astype(np.float32), pwz0.astype(np.float32))
     ctx.set_sample_weight(None)
 
-    def exchange(c, r):
+    class Exchange:
         """peer-memory all-reduce between processes: CUDA IPC handles through the launcher"""
+
+        def __call__(self, c, r):
+            return exchange_setup(c, r)
+
+        def finish(self, c):     # importers unmap before any exporter frees its block
+            c.shard_p2p_detach()
+            plumb.barrier()
+
+    def exchange_setup(c, r):
         if args.no_p2p:
             return False
         try:
@@ -339,6 +348,7 @@ def run_shard(args, plumb, rank, world, device):
         if not ok:
             c.set_option("p2p", 0)
         return ok
+    exchange = Exchange()
     p2p = exchange(ctx, rank)
     ctx.em(args.warmup, n_iter_per_test=10, tolerance=0.0)
     sampler = ClockSampler(device)
@@ -378,6 +388,8 @@ def run_shard(args, plumb, rank, world, device):
         plumb.barrier()
         runs.append(plumb.max(dt))
     e2e_s = statistics.median(runs)
+    if p2p:
+        exchange.finish(ctx)
     ctx.set_shard(None)
     ctx.close()
     comm.close()

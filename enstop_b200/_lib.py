@@ -86,6 +86,7 @@ SIGNATURES = {
     "plsa_shard_p2p_prepare": (ctypes.c_int, [_ctx, ctypes.POINTER(ctypes.c_uint64), _i64p]),
     "plsa_shard_p2p_export": (ctypes.c_int, [_ctx, ctypes.c_char_p]),
     "plsa_shard_p2p_attach": (ctypes.c_int, [_ctx, _i32, _i32, ctypes.c_uint64, ctypes.c_char_p]),
+    "plsa_shard_p2p_detach": (ctypes.c_int, [_ctx]),
 }
 
 _lib = None
@@ -395,6 +396,10 @@ class Context:
         this process, ``handle`` (its IPC handle) otherwise."""
         check(self._L.plsa_shard_p2p_attach(self._h, int(peer_rank), int(peer_device), int(base),
                                             handle), self._h)
+
+    def shard_p2p_detach(self):
+        """Unmap the peers' exchange blocks (before any rank frees its own)."""
+        check(self._L.plsa_shard_p2p_detach(self._h), self._h)
 
     def stash_topics(self, slot, n_slots):
         check(self._L.plsa_stash_topics(self._h, int(slot), int(n_slots)), self._h)

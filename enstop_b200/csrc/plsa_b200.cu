@@ -1956,7 +1956,7 @@ static int shard_allreduce(plsa_ctx *ctx, void *buf, size_t count, bool f64, cud
 static int shard_n_ranks(const plsa_ctx *ctx) { return ctx->shard ? ctx->shard->n_ranks : 1; }
 static int shard_rank(const plsa_ctx *ctx) { return ctx->shard ? ctx->shard->rank : 0; }
 
-static void p2p_release(plsa_ctx *ctx)
+static void p2p_detach_peers(plsa_ctx *ctx)
 {
     for (int p = 0; p < SHARD_MAX_RANKS; ++p) {
         if (ctx->p2p.peer_base[p] && ctx->p2p.peer_ipc[p]) cudaIpcCloseMemHandle(ctx->p2p.peer_base[p]);
@@ -1964,6 +1964,11 @@ static void p2p_release(plsa_ctx *ctx)
         ctx->p2p.peer_ipc[p] = false;
     }
     ctx->p2p.n_attached = 0;
+}
+
+static void p2p_release(plsa_ctx *ctx)
+{
+    p2p_detach_peers(ctx);
     ctx->p2p.block.release();
     ctx->p2p.err.release();
     ctx->p2p.part_bytes = 0;
@@ -1999,6 +2004,17 @@ API int plsa_shard_p2p_prepare(plsa_ctx *ctx, uint64_t *base, int64_t *bytes)
     ctx->p2p.part_bytes = part;
     if (base) *base = (uint64_t)(uintptr_t)ctx->p2p.block.p;
     if (bytes) *bytes = (int64_t)total;
+    return PLSA_OK;
+}
+
+/* Unmap the peers' exchange blocks (this rank's own block stays).  Between processes an
+ * exported block must outlive its importers' mappings: every rank detaches, the caller's
+ * barrier follows, and only then plsa_set_shard(ctx, NULL) / plsa_ctx_destroy free the blocks. */
+API int plsa_shard_p2p_detach(plsa_ctx *ctx)
+{
+    CHECK_CTX(ctx);
+    if (ctx->stream) CK(cudaStreamSynchronize(ctx->stream));
+    p2p_detach_peers(ctx);
     return PLSA_OK;
 }
 

@@ -211,6 +211,11 @@ class ThreadPeerExchange:
             ctx.set_option("p2p", 0)
         return all(self.ok)
 
+    def finish(self, ctx):
+        """Every rank unmaps its peers' blocks before any rank frees its own."""
+        ctx.shard_p2p_detach()
+        self.barrier.wait()
+
     def abort(self):
         self.barrier.abort()
 
@@ -243,6 +248,8 @@ def plsa_fit_shard(X_rows, k, p_z_given_d_rows, p_w_given_z, sample_weight_rows,
                 "p2p": p2p}
         if profile:
             ctx.set_profiling(False)
+        if p2p and hasattr(exchange, "finish"):
+            exchange.finish(ctx)
         ctx.set_shard(None)
         ok = True
     finally:

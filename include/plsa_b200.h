@@ -232,6 +232,9 @@ int plsa_shard_p2p_prepare(plsa_ctx *ctx, uint64_t *device_address, int64_t *byt
 int plsa_shard_p2p_export(plsa_ctx *ctx, char *handle /*[PLSA_IPC_HANDLE_BYTES]*/);
 int plsa_shard_p2p_attach(plsa_ctx *ctx, int32_t peer_rank, int32_t peer_device,
                           uint64_t device_address, const char *ipc_handle /* or NULL */);
+/* Unmap the peers' blocks; call on every rank, then a barrier, before any rank frees its own
+ * block (plsa_set_shard(ctx, NULL) or plsa_ctx_destroy). */
+int plsa_shard_p2p_detach(plsa_ctx *ctx);
 
 #ifdef __cplusplus
 }
