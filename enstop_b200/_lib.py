@@ -65,6 +65,8 @@ SIGNATURES = {
     "plsa_get_profile": (ctypes.c_int, [_ctx, _f64p, _i64p]),
     "plsa_launch_count": (ctypes.c_int, [_ctx, _i64p]),
     "plsa_set_option": (ctypes.c_int, [_ctx, ctypes.c_char_p, _i64]),
+    "plsa_plan_items": (ctypes.c_int, [_i32p, _i64, _i64, _i32, _i32, _i64, _i64p, _i32p, _i32p,
+                                       _i32p, _i32p, _i64p, _i32p, _i32p]),
     "plsa_host_random_rows": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint32), _i32p, _i64, _i64, _f32p,
                                              _f64p]),
     "plsa_b200_fit_inner": (ctypes.c_int, [_i32p, _i32p, _f32p, _i64, _f32p, _f32p, _f32p, _i64,
@@ -190,6 +192,30 @@ def random_rows(rng, rows, cols, want_f64=False, out=None):
     return (out, out64) if want_f64 else out
 
 
+def plan_items(indptr, chunk, align=4, order=0):
+    """Host-only: the work items a row pass over a CSR with these row pointers launches, in
+    launch order (plsa_plan_items).  Returns a dict of arrays start/row/len/slot/skip plus
+    n_split and n_slots."""
+    indptr = _as(indptr, np.int32)
+    rows = indptr.shape[0] - 1
+    n = _i64(0)
+    ns, nl = _i32(0), _i32(0)
+    L = lib()
+    check(L.plsa_plan_items(_ptr(indptr, _i32p), rows, int(chunk), int(align), int(order), 0,
+                            None, None, None, None, None, ctypes.byref(n), ctypes.byref(ns),
+                            ctypes.byref(nl)))
+    out = dict(start=np.empty(n.value, np.int64), row=np.empty(n.value, np.int32),
+               len=np.empty(n.value, np.int32), slot=np.empty(n.value, np.int32),
+               skip=np.empty(n.value, np.int32))
+    check(L.plsa_plan_items(_ptr(indptr, _i32p), rows, int(chunk), int(align), int(order), n.value,
+                            _ptr(out["start"], _i64p), _ptr(out["row"], _i32p),
+                            _ptr(out["len"], _i32p), _ptr(out["slot"], _i32p),
+                            _ptr(out["skip"], _i32p), ctypes.byref(n), ctypes.byref(ns),
+                            ctypes.byref(nl)))
+    out["n_split"], out["n_slots"] = ns.value, nl.value
+    return out
+
+
 def device_count():
     n = ctypes.c_int(0)
     rc = lib().plsa_device_count(ctypes.byref(n))
@@ -220,6 +246,8 @@ class Context:
             self.set_option("texture", int(os.environ["ENSTOP_B200_TEXTURE"]))
         if os.environ.get("ENSTOP_B200_VEC"):       # 0: unaligned items, one 8-byte load per entry
             self.set_option("vec_entries", int(os.environ["ENSTOP_B200_VEC"]))
+        if os.environ.get("ENSTOP_B200_ITEM_ORDER"):  # 1: same-window chunks adjacent (L1 reuse)
+            self.set_option("item_order", int(os.environ["ENSTOP_B200_ITEM_ORDER"]))
 
     def close(self):
         if self._h:

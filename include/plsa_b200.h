@@ -129,8 +129,20 @@ int plsa_launch_count(const plsa_ctx *ctx, int64_t *launches);
 /* Tunables: "chunk" (max stored entries per work item, 32..4096, 0 = automatic; longer rows
  * are split),
  * "texture" (1: gather factor rows through the texture pipe when they fit, 0: plain loads),
- * "fuse_ll" (1: the periodic log-likelihood rides on the next doc pass, 0: separate pass). */
+ * "fuse_ll" (1: the periodic log-likelihood rides on the next doc pass, 0: separate pass),
+ * "item_order" (launch order of same-length work items: 0 = chunks of a split row adjacent,
+ * 1 = chunks that cover the same window of gathered rows adjacent, for L1 reuse inside a CTA;
+ * the sums are the same in both orders). */
 int plsa_set_option(plsa_ctx *ctx, const char *name, int64_t value);
+/* Host-only (no device): the work items a pass over a CSR with these row pointers would launch,
+ * in launch order.  A row longer than `chunk` entries is cut into equal chunks that write
+ * partial sums into consecutive slots; with `align` > 1 an item starts on a multiple of
+ * `align` entries and its first `skip` entries belong to the row before.  Writes at most
+ * `cap` items into the optional arrays; *n_items is the full count. */
+int plsa_plan_items(const int32_t *indptr, int64_t rows, int64_t chunk, int32_t align,
+                    int32_t order, int64_t cap, int64_t *start, int32_t *row, int32_t *len,
+                    int32_t *slot, int32_t *skip, int64_t *n_items, int32_t *n_split,
+                    int32_t *n_slots);
 
 /* ---- host helper: the reference's seeded random initialisation, faster ------------------------ */
 /* plsa.py:454-456 + :510-511 + :709-710: draw rows*cols doubles from a numpy legacy

@@ -184,3 +184,78 @@ def test_synth_recipe():
     assert info["sum_counts"] == info["tokens"]
     Y = synth.make_corpus(2000, 5000, 200_000, seed=1)
     assert (X != Y).nnz == 0
+
+
+def _ragged_indptr(rng, rows, long_rows):
+    """Row pointers with empty rows, short rows and a few rows far longer than a chunk."""
+    lens = rng.integers(0, 40, size=rows)
+    lens[rng.random(rows) < 0.2] = 0
+    for r in rng.choice(rows, size=long_rows, replace=False):
+        lens[r] = int(rng.integers(300, 20_000))
+    indptr = np.zeros(rows + 1, dtype=np.int32)
+    np.cumsum(lens, out=indptr[1:])
+    return indptr
+
+
+@pytest.mark.parametrize("chunk,align", [(256, 4), (32, 4), (64, 1), (2048, 2), (100, 4)])
+@pytest.mark.parametrize("order", [0, 1])
+def test_work_item_plan_covers_every_entry_once(chunk, align, order):
+    """plan_items (host side of the row pass, csrc/plsa_b200.cu): in either launch order the
+    items tile the stored entries exactly, chunks of a split row own consecutive slots, items
+    start on entry-block boundaries and are sorted longest first."""
+    rng = np.random.default_rng(chunk * 7 + align + order)
+    indptr = _ragged_indptr(rng, 3000, 12)
+    p = _lib.plan_items(indptr, chunk, align=align, order=order)
+    start, row, ln, slot, skip = p["start"], p["row"], p["len"], p["slot"], p["skip"]
+    eff = chunk // align * align
+    assert np.all(ln <= eff) and np.all(ln >= 0) and np.all(skip >= 0) and np.all(skip < align)
+    assert np.all(start % align == 0)
+    assert np.all(np.diff(ln) <= 0), "items must be sorted by length, longest first"
+    # every stored entry is covered by exactly one item of its own row
+    cover = np.zeros(int(indptr[-1]), dtype=np.int32)
+    owner = np.full(int(indptr[-1]), -1, dtype=np.int64)
+    for s, r, l, k in zip(start, row, ln, skip):
+        cover[s + k:s + l] += 1
+        owner[s + k:s + l] = r
+        assert indptr[r] <= s + k and s + l <= indptr[r + 1]
+    assert np.all(cover == 1)
+    assert np.array_equal(owner, np.repeat(np.arange(indptr.shape[0] - 1), np.diff(indptr)))
+    # one item per unsplit row (empty rows included: their result is a zero row)
+    whole = slot < 0
+    n_rows = indptr.shape[0] - 1
+    split_rows = np.unique(row[~whole])
+    assert np.array_equal(np.sort(np.concatenate([row[whole], split_rows])), np.arange(n_rows))
+    assert p["n_split"] == split_rows.shape[0]
+    # slots: a permutation of 0..n_slots-1; within a row consecutive and in entry order
+    assert np.array_equal(np.sort(slot[~whole]), np.arange(p["n_slots"]))
+    for r in split_rows:
+        sel = np.flatnonzero(row == r)
+        by_start = sel[np.argsort(start[sel])]
+        assert np.array_equal(slot[by_start], slot[by_start][0] + np.arange(sel.shape[0]))
+        assert np.all(skip[by_start][1:] == 0)
+
+
+def test_work_item_orders_hold_the_same_items():
+    """The window order only permutes same-length items; and it does put chunks that sit at the
+    same position of their rows next to each other."""
+    rng = np.random.default_rng(11)
+    indptr = _ragged_indptr(rng, 2000, 40)
+    a = _lib.plan_items(indptr, 256, align=4, order=0)
+    b = _lib.plan_items(indptr, 256, align=4, order=1)
+    key = lambda p: sorted(zip(p["start"].tolist(), p["row"].tolist(), p["len"].tolist(),
+                               p["slot"].tolist(), p["skip"].tolist()))
+    assert key(a) == key(b)
+    assert a["n_slots"] == b["n_slots"] and a["n_split"] == b["n_split"]
+    assert np.array_equal(a["len"], b["len"])
+    # relative position of a chunk inside its row, for runs of equal-length chunks
+    def positions(p):
+        span = (indptr[p["row"] + 1] - (indptr[p["row"]] & ~3)).astype(np.float64)
+        return (p["start"] - (indptr[p["row"]] & ~3)) / np.maximum(span, 1.0)
+    chunks_b = b["slot"] >= 0
+    pos_b, len_b = positions(b)[chunks_b], b["len"][chunks_b]
+    same = len_b[1:] == len_b[:-1]
+    assert np.all(np.diff(pos_b)[same] >= -1.0 / 4096 - 1e-12)
+    with pytest.raises(_lib.PlsaError):
+        _lib.plan_items(indptr, 256, align=3, order=0)
+    with pytest.raises(_lib.PlsaError):
+        _lib.plan_items(indptr, 256, align=4, order=2)
