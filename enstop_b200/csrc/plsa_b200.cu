@@ -781,8 +781,17 @@ static int upload_csr_impl(plsa_ctx *ctx, const int32_t *indptr, const int32_t *
     for (int64_t r = 0; r < n; ++r)
         if (indptr[r + 1] < indptr[r]) return ctx->fail(PLSA_EINVAL, "upload: indptr decreases");
     Corpus &c = ctx->base;
+    /* a failed upload leaves the context without a corpus, not with half of one */
+    ctx->use_boot = false;
+    corpus_changed(ctx);
+    c.h_indptr.clear();
     c.n = n; c.m = m; c.nnz = nnz;
-    c.h_indptr.assign(indptr, indptr + n + 1);
+    std::vector<int32_t> h_indptr;
+    try { /* no C++ exception crosses the C ABI */
+        h_indptr.assign(indptr, indptr + n + 1);
+    } catch (const std::bad_alloc &) {
+        return ctx->fail(PLSA_ENOMEM, "upload: out of host memory");
+    }
     CK(c.indptr.ensure((size_t)(n + 1) * 4));
     CK(c.ent.ensure(ent_bytes(nnz)));
     CK(ctx->flag.ensure(4));
@@ -810,12 +819,8 @@ static int upload_csr_impl(plsa_ctx *ctx, const int32_t *indptr, const int32_t *
         CK(cudaMemcpyAsync(&bad, ctx->flag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->use_boot = false;
-    corpus_changed(ctx);
-    if (bad) {
-        c.h_indptr.clear();
-        return ctx->fail(PLSA_EINVAL, "upload: column index out of range");
-    }
+    if (bad) return ctx->fail(PLSA_EINVAL, "upload: column index out of range");
+    c.h_indptr.swap(h_indptr);
     return PLSA_OK;
 }
 
@@ -840,7 +845,12 @@ API int plsa_upload_coo(plsa_ctx *ctx, const int32_t *rows, const int32_t *cols,
     CHECK_CTX(ctx);
     if (n_docs < 0 || nnz < 0 || (nnz > 0 && !rows))
         return ctx->fail(PLSA_EINVAL, "upload_coo: null pointer or negative size");
-    std::vector<int32_t> indptr((size_t)n_docs + 1, 0);
+    std::vector<int32_t> indptr;
+    try {
+        indptr.assign((size_t)n_docs + 1, 0);
+    } catch (const std::bad_alloc &) {
+        return ctx->fail(PLSA_ENOMEM, "upload_coo: out of host memory");
+    }
     for (int64_t i = 0; i < nnz; ++i) {
         if ((uint32_t)rows[i] >= (uint32_t)n_docs)
             return ctx->fail(PLSA_EINVAL, "upload_coo: row index out of range");
@@ -865,7 +875,14 @@ API int plsa_bootstrap(plsa_ctx *ctx, const int32_t *row_idx, int64_t n_rows)
     if (n_rows < 0) return ctx->fail(PLSA_EINVAL, "bootstrap: negative row count");
     const Corpus &b = ctx->base;
     Corpus &c = ctx->boot;
-    c.h_indptr.assign((size_t)n_rows + 1, 0);
+    /* the row pointers are checked and built aside: a rejected call leaves the context on the
+     * corpus it had; a call that fails later leaves it on the base corpus */
+    std::vector<int32_t> h_indptr;
+    try {
+        h_indptr.assign((size_t)n_rows + 1, 0);
+    } catch (const std::bad_alloc &) {
+        return ctx->fail(PLSA_ENOMEM, "bootstrap: out of host memory");
+    }
     int64_t run = 0;
     for (int64_t i = 0; i < n_rows; ++i) {
         if ((uint32_t)row_idx[i] >= (uint32_t)b.n)
@@ -873,8 +890,11 @@ API int plsa_bootstrap(plsa_ctx *ctx, const int32_t *row_idx, int64_t n_rows)
         run += b.h_indptr[(size_t)row_idx[i] + 1] - b.h_indptr[(size_t)row_idx[i]];
         if (run >= ((int64_t)1 << 31))
             return ctx->fail(PLSA_EINVAL, "bootstrap: resampled corpus exceeds int32 entries");
-        c.h_indptr[(size_t)i + 1] = (int32_t)run;
+        h_indptr[(size_t)i + 1] = (int32_t)run;
     }
+    ctx->use_boot = false;
+    corpus_changed(ctx);
+    c.h_indptr.swap(h_indptr);
     c.n = n_rows; c.m = b.m; c.nnz = run;
     CK(c.indptr.ensure((size_t)(n_rows + 1) * 4));
     CK(c.ent.ensure(ent_bytes(run)));
@@ -1761,35 +1781,36 @@ const int kNcclFloat = 7;  /* ncclFloat32 */
 const int kNcclDouble = 8; /* ncclFloat64 */
 const int kNcclSum = 0;    /* ncclSum */
 
+/* Resolved once per process; the ensemble's helper thread (plsa_gather_warmup) and its worker
+ * threads may ask at the same time, so the one-time work sits behind std::call_once. */
 static Nccl *load_nccl()
 {
     static Nccl n;
-    static bool tried = false;
-    if (tried) return n.h ? &n : nullptr;
-    tried = true;
-    for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
-        n.h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
-        if (n.h) break;
-    }
-    if (!n.h) return nullptr;
-    n.GetUniqueId = (fn_GetUniqueId)dlsym(n.h, "ncclGetUniqueId");
-    n.CommInitRank = (fn_CommInitRank)dlsym(n.h, "ncclCommInitRank");
-    n.CommInitAll = (fn_CommInitAll)dlsym(n.h, "ncclCommInitAll");
-    n.CommDestroy = (fn_CommDestroy)dlsym(n.h, "ncclCommDestroy");
-    n.CommAbort = (fn_CommAbort)dlsym(n.h, "ncclCommAbort");
-    n.GroupStart = (fn_GroupStart)dlsym(n.h, "ncclGroupStart");
-    n.GroupEnd = (fn_GroupEnd)dlsym(n.h, "ncclGroupEnd");
-    n.Send = (fn_Send)dlsym(n.h, "ncclSend");
-    n.Recv = (fn_Recv)dlsym(n.h, "ncclRecv");
-    n.AllReduce = (fn_AllReduce)dlsym(n.h, "ncclAllReduce");
-    n.GetErrorString = (fn_GetErrorString)dlsym(n.h, "ncclGetErrorString");
-    if (!n.GetUniqueId || !n.CommInitRank || !n.CommInitAll || !n.CommDestroy ||
-        !n.GroupStart || !n.GroupEnd || !n.Send || !n.Recv || !n.AllReduce) {
-        dlclose(n.h);
-        n.h = nullptr;
-        return nullptr;
-    }
-    return &n;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            n.h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+            if (n.h) break;
+        }
+        if (!n.h) return;
+        n.GetUniqueId = (fn_GetUniqueId)dlsym(n.h, "ncclGetUniqueId");
+        n.CommInitRank = (fn_CommInitRank)dlsym(n.h, "ncclCommInitRank");
+        n.CommInitAll = (fn_CommInitAll)dlsym(n.h, "ncclCommInitAll");
+        n.CommDestroy = (fn_CommDestroy)dlsym(n.h, "ncclCommDestroy");
+        n.CommAbort = (fn_CommAbort)dlsym(n.h, "ncclCommAbort");
+        n.GroupStart = (fn_GroupStart)dlsym(n.h, "ncclGroupStart");
+        n.GroupEnd = (fn_GroupEnd)dlsym(n.h, "ncclGroupEnd");
+        n.Send = (fn_Send)dlsym(n.h, "ncclSend");
+        n.Recv = (fn_Recv)dlsym(n.h, "ncclRecv");
+        n.AllReduce = (fn_AllReduce)dlsym(n.h, "ncclAllReduce");
+        n.GetErrorString = (fn_GetErrorString)dlsym(n.h, "ncclGetErrorString");
+        if (!n.GetUniqueId || !n.CommInitRank || !n.CommInitAll || !n.CommDestroy ||
+            !n.GroupStart || !n.GroupEnd || !n.Send || !n.Recv || !n.AllReduce) {
+            dlclose(n.h);
+            n.h = nullptr;
+        }
+    });
+    return n.h ? &n : nullptr;
 }
 
 static int nccl_fail(Nccl *nc, const char *what, int r)
