@@ -68,6 +68,31 @@ def test_reference_arm_other_ranks_do_nothing():
     assert res.returncode == 0 and res.stdout.strip() == ""
 
 
+def test_reference_arm_json_contract():
+    """bench.py --impl reference on rank 0: one JSON line with the keys the driver reads (same
+    metric / unit / config as the GPU arm, `impl`, a cpu_baseline describing this run, an e2e
+    object with zero copy bytes) — run here on C1, the reference's own CPU-sized case."""
+    import json
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                          "--steps", "2", "--warmup", "1", "--config", "C1"],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300,
+                         env=env, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "nnz*k/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("EM iters/sec") and d["steps"] == 2 and d["n_gpus"] == 1
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None
+    assert d["config"]["workload"].startswith("C1:") and d["config"]["k"] == 10
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0
+
+
 def test_sharding_and_seeds():
     assert enstop_.shard_members(16, 8)[3] == [3, 11]
     assert enstop_.shard_members(5, 2) == [[0, 2, 4], [1, 3]]
