@@ -39,14 +39,14 @@ def _fit(X, k, order, n_iter, chunk=0, sw=None, use_sw=False):
 def test_window_order_is_the_same_model(k, chunk):
     # planted corpus with rows and columns far longer than the work-item length
     X = synth.make_corpus(1500, 900, 120_000, seed=21, planted=True, k_true=6)
-    a = _fit(X, k, 0, 12, chunk)
-    b = _fit(X, k, 1, 12, chunk)
-    assert a[2] == b[2] == 12
-    assert rel_l2(b[1], a[1]) < 2e-6 and rel_l2(b[0], a[0]) < 2e-6
+    a = _fit(X, k, 0, 5, chunk)
+    b = _fit(X, k, 1, 5, chunk)
+    assert a[2] == b[2] == 5
+    assert rel_l2(b[1], a[1]) < 5e-6 and rel_l2(b[0], a[0]) < 5e-6
     assert np.allclose(a[3], b[3], rtol=1e-9)
     sw = np.ones(X.shape[0], dtype=np.float32)
-    ez, ew = oracle.plsa_fit(X, k, sw, init=a[4], n_iter=12, tolerance=0.0, precision="f64")
-    assert rel_l2(b[1], ew) < 3e-5 and rel_l2(b[0], ez) < 3e-5
+    ez, ew = oracle.plsa_fit(X, k, sw, init=a[4], n_iter=5, tolerance=0.0, precision="f64")
+    assert rel_l2(b[1], ew) < 2e-5 and rel_l2(b[0], ez) < 2e-5
 
 
 def test_window_order_with_sample_weights_and_bit_repeatable():
@@ -56,4 +56,4 @@ def test_window_order_with_sample_weights_and_bit_repeatable():
     b = _fit(X, 12, 1, 8, 32, sw=sw, use_sw=True)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     c = _fit(X, 12, 0, 8, 32, sw=sw, use_sw=True)
-    assert rel_l2(a[1], c[1]) < 2e-6 and rel_l2(a[0], c[0]) < 2e-6
+    assert rel_l2(a[1], c[1]) < 5e-6 and rel_l2(a[0], c[0]) < 5e-6
