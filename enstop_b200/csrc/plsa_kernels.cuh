@@ -140,6 +140,26 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+/* Experiment (build with -DPLSA_EXP_FTZ_THRESH=1, off by default): the threshold of
+ * plsa.py:98-102 without compare/select instructions.  The owned row is scaled by a power of
+ * two S <= FLT_MIN / thresh, so a product at or below the threshold becomes subnormal and the
+ * flush-to-zero multiply drops it; the posterior v / sum(v) and the M-step sums do not see
+ * the common factor, the log-likelihood subtracts log2(S).  Exact scaling; the products that
+ * are dropped are those below T = FLT_MIN / S, thresh <= T < 2 thresh (the reference drops
+ * v <= thresh).  8 of the 33 instructions per stored entry go away. */
+#ifndef PLSA_EXP_FTZ_THRESH
+#define PLSA_EXP_FTZ_THRESH 0
+#endif
+__device__ __forceinline__ f32x2 mul2_ftz(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float ftz_thresh_scale(float thresh)
+{   /* largest power of two <= FLT_MIN / thresh (thresh >= FLT_MIN: at most 1) */
+    return __int_as_float(__float_as_int(1.17549435e-38f / thresh) & 0x7f800000);
+}
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
 {
     f32x2 r;
@@ -336,7 +356,8 @@ __device__ __forceinline__ void pass_block(const PassArgs &a, const int2 (&e)[U]
                                            const char *gat_base, const uint32_t (&lane_off)[KV],
                                            uint32_t stride_bytes, const float4 (&own)[KV],
                                            float4 (&acc)[KV], double &ll_acc, float &min_norm,
-                                           float rw, float thresh, int j, int gbase, bool lane_on)
+                                           float rw, float thresh, int j, int gbase, bool lane_on,
+                                           float ll_shift = 0.f /* log2(S), FTZ experiment */)
 {
     float4 g[U][KV];
     float llt[U]; /* log-likelihood terms of the block (MODE_LOGLIK / MODE_DOC_LL) */
@@ -373,7 +394,15 @@ __device__ __forceinline__ void pass_block(const PassArgs &a, const int2 (&e)[U]
 #pragma unroll
         for (int q = 0; q < KV; ++q) {
             float4 v;
-#if PLSA_PACKED_MATH
+#if PLSA_PACKED_MATH && PLSA_EXP_FTZ_THRESH
+            if constexpr (MODE != MODE_LOGLIK) { /* the owned row carries S: see above */
+                upk2(mul2_ftz(pk2(g[u][q].x, g[u][q].y), own2[q][0]), v.x, v.y);
+                upk2(mul2_ftz(pk2(g[u][q].z, g[u][q].w), own2[q][1]), v.z, v.w);
+            } else {
+                upk2(mul2(pk2(g[u][q].x, g[u][q].y), own2[q][0]), v.x, v.y);
+                upk2(mul2(pk2(g[u][q].z, g[u][q].w), own2[q][1]), v.z, v.w);
+            }
+#elif PLSA_PACKED_MATH
             upk2(mul2(pk2(g[u][q].x, g[u][q].y), own2[q][0]), v.x, v.y);
             upk2(mul2(pk2(g[u][q].z, g[u][q].w), own2[q][1]), v.z, v.w);
 #else
@@ -382,7 +411,7 @@ __device__ __forceinline__ void pass_block(const PassArgs &a, const int2 (&e)[U]
             v.z = g[u][q].z * own[q].z;
             v.w = g[u][q].w * own[q].w;
 #endif
-            if constexpr (MODE != MODE_LOGLIK) { /* plsa.py:98-102 */
+            if constexpr (MODE != MODE_LOGLIK && !(PLSA_PACKED_MATH && PLSA_EXP_FTZ_THRESH)) { /* plsa.py:98-102 */
                 v.x = v.x > thresh ? v.x : 0.f;
                 v.y = v.y > thresh ? v.y : 0.f;
                 v.z = v.z > thresh ? v.z : 0.f;
@@ -405,7 +434,11 @@ __device__ __forceinline__ void pass_block(const PassArgs &a, const int2 (&e)[U]
              * the block's terms are added in float32, blocks in float64. */
             float lg; /* fused pass: the sum is 0 or a normal float (thresholded products), so the
                          flush-to-zero MUFU.LG2 needs no subnormal pre-scaling branch */
+#if PLSA_PACKED_MATH && PLSA_EXP_FTZ_THRESH
+            if constexpr (MODE == MODE_DOC_LL) lg = (log2_ftz(norm) - ll_shift) * 0.69314718f;
+#else
             if constexpr (MODE == MODE_DOC_LL) lg = log2_ftz(norm) * 0.69314718f;
+#endif
             else lg = __logf(norm);
             llt[u] = (x != 0.f) ? x * rw * lg : 0.f;
             /* idle lanes (32 % G of them) shadow the last group with a zero owned row: their
@@ -502,6 +535,17 @@ __global__ void __launch_bounds__(256, (KV == 1) ? 4 : (KV == 2) ? 2 : 1)
     }
     float rw = 1.f;
     if constexpr (MODE == MODE_LOGLIK || MODE == MODE_DOC_LL) rw = has ? a.row_weight[it.row] : 0.f;
+    float ll_shift = 0.f, norm_scale = 1.f;
+#if PLSA_PACKED_MATH && PLSA_EXP_FTZ_THRESH
+    if constexpr (MODE != MODE_LOGLIK) {
+        norm_scale = ftz_thresh_scale(a.thresh);
+        ll_shift = log2_ftz(norm_scale); /* exact: a power of two */
+#pragma unroll
+        for (int q = 0; q < KV; ++q)
+            own[q] = make_float4(own[q].x * norm_scale, own[q].y * norm_scale,
+                                 own[q].z * norm_scale, own[q].w * norm_scale);
+    }
+#endif
 
     const int2 *ent = a.ent + it.start;
     const int len = it.len;
@@ -528,7 +572,7 @@ __global__ void __launch_bounds__(256, (KV == 1) ? 4 : (KV == 2) ? 2 : 1)
         load_entries<U, VEC>(ent + base + U, en);
         pass_block<G, KV, U, MODE, TEX, true>(a, e, base, len, gat_base, lane_off, stride_bytes,
                                               own, acc, ll_acc, min_norm, rw, thresh, j, gbase,
-                                              lane_on);
+                                              lane_on, ll_shift);
 #pragma unroll
         for (int u = 0; u < U; ++u) e[u] = en[u];
     }
@@ -536,7 +580,7 @@ __global__ void __launch_bounds__(256, (KV == 1) ? 4 : (KV == 2) ? 2 : 1)
     if constexpr (MODE == MODE_LOGLIK || MODE == MODE_DOC_LL) {
         if (!(j == 0 && lane_on)) ll_acc = 0.0; /* one lane per item contributes */
         if constexpr (MODE == MODE_DOC_LL)
-            if (min_norm < PLSA_FUSED_LL_MIN_NORM) *a.flag = 1;
+            if (min_norm < PLSA_FUSED_LL_MIN_NORM * norm_scale) *a.flag = 1;
     }
     if constexpr (MODE == MODE_LOGLIK) {
         finish_loglik(a, ll_acc);
