@@ -259,3 +259,65 @@ def test_work_item_orders_hold_the_same_items():
         _lib.plan_items(indptr, 256, align=3, order=0)
     with pytest.raises(_lib.PlsaError):
         _lib.plan_items(indptr, 256, align=4, order=2)
+
+
+def _emulate_pass(indptr, idx, val, own, gat, plan, thresh, normalise):
+    """What row_pass_kernel + fixup_kernel compute from a work-item plan (float64, numpy):
+    per item the E-step posterior of plsa.py:95-104 folded into the M-step sums of
+    plsa.py:189-194; whole rows are written directly, chunks into their partial-sum slot, and
+    the slots of a split row are added in slot order."""
+    k = own.shape[1]
+    own_new = np.zeros_like(own)
+    partial = np.zeros((max(plan["n_slots"], 1), k))
+    for s, r, l, slot, skip in zip(plan["start"], plan["row"], plan["len"], plan["slot"],
+                                   plan["skip"]):
+        e = slice(s + skip, s + l)
+        v = own[r][None, :] * gat[idx[e]]
+        v[v <= thresh] = 0.0
+        norm = v.sum(axis=1)
+        c = np.divide(val[e], norm, out=np.zeros_like(norm), where=norm > 0)
+        acc = (c[:, None] * v).sum(axis=0)
+        if slot < 0:
+            own_new[r] = acc
+        else:
+            partial[slot] = acc
+    chunks = np.flatnonzero(plan["slot"] >= 0)
+    for r in np.unique(plan["row"][chunks]):
+        sl = np.sort(plan["slot"][chunks][plan["row"][chunks] == r])
+        assert np.array_equal(sl, np.arange(sl[0], sl[0] + sl.shape[0]))
+        own_new[r] = partial[sl].sum(axis=0)
+    if normalise:  # plsa.py:199-202
+        tot = own_new.sum(axis=1, keepdims=True)
+        np.divide(own_new, tot, out=own_new, where=tot > 0)
+    return own_new
+
+
+@pytest.mark.parametrize("order", [0, 1])
+def test_planned_passes_are_one_em_iteration(order):
+    """Host-side plan semantics end to end on the CPU: a doc pass and a term pass carried out
+    item by item from plsa_plan_items (both launch orders, aligned items, split rows), with
+    the lazily normalised P(w|z), equal one EM iteration of the oracle's float64
+    restatement of plsa_fit_inner."""
+    X = synth.make_corpus(400, 300, 14_000, seed=9, planted=True, k_true=4).astype(np.float64)
+    n, m = X.shape
+    k = 6
+    rng = np.random.RandomState(5)
+    pzd, pwz = oracle.plsa_init_random(n, m, k, rng)
+    Xt = X.T.tocsr()
+    Xt.sort_indices()
+    thresh = 1e-32
+    plan_d = _lib.plan_items(X.indptr, 32, align=4, order=order)
+    plan_t = _lib.plan_items(Xt.indptr, 32, align=4, order=order)
+    assert plan_d["n_split"] > 0 and plan_t["n_split"] > 0
+    new_pzd = _emulate_pass(X.indptr, X.indices, X.data, pzd, pwz.T.copy(), plan_d, thresh, True)
+    raw = _emulate_pass(Xt.indptr, Xt.indices, Xt.data, pwz.T.copy(), pzd, plan_t, thresh, False)
+    col = raw.sum(axis=0)                                   # plsa.py:196-198
+    new_pwz = (raw / np.where(col > 0, col, 1.0)).T
+    A = X.tocoo()
+    e_pwz, e_pzd = pwz.copy(), pzd.copy()
+    iters, _ = oracle.fit_inner(A.row.astype(np.int32), A.col.astype(np.int32),
+                                A.data.astype(np.float64), e_pwz, e_pzd, np.ones(n), n_iter=1,
+                                tolerance=0.0, e_step_thresh=thresh, precision="f64")
+    assert iters == 1
+    assert np.allclose(new_pzd, e_pzd, rtol=1e-10, atol=1e-15)
+    assert np.allclose(new_pwz, e_pwz, rtol=1e-10, atol=1e-15)
