@@ -104,7 +104,26 @@ struct Stream {
             int64_t pairs = (MT_N - pos) / 2;
             if (pairs > n) pairs = n;
             const uint32_t *src = out + pos;
-            for (int64_t i = 0; i < pairs; ++i) dst[i] = make(src[2 * i], src[2 * i + 1]);
+            int64_t i = 0;
+#if defined(__AVX2__)
+            /* four doubles from eight words; a >> 5 and b >> 6 are below 2^27, so the signed
+             * conversion is exact, and so are a * 2^26 + b (< 2^53) and the scaling by 2^-53:
+             * bit-identical to make() in any evaluation order */
+            const __m256i even = _mm256_setr_epi32(0, 2, 4, 6, 0, 2, 4, 6),
+                          odd = _mm256_setr_epi32(1, 3, 5, 7, 1, 3, 5, 7);
+            const __m256d hi = _mm256_set1_pd(67108864.0), scale = _mm256_set1_pd(1.0 / 9007199254740992.0);
+            for (; i + 4 <= pairs; i += 4) {
+                const __m256i w = _mm256_loadu_si256((const __m256i *)(src + 2 * i));
+                const __m128i a = _mm256_castsi256_si128(
+                    _mm256_permutevar8x32_epi32(_mm256_srli_epi32(w, 5), even));
+                const __m128i b = _mm256_castsi256_si128(
+                    _mm256_permutevar8x32_epi32(_mm256_srli_epi32(w, 6), odd));
+                const __m256d v = _mm256_add_pd(_mm256_mul_pd(_mm256_cvtepi32_pd(a), hi),
+                                                _mm256_cvtepi32_pd(b));
+                _mm256_storeu_pd(dst + i, _mm256_mul_pd(v, scale));
+            }
+#endif
+            for (; i < pairs; ++i) dst[i] = make(src[2 * i], src[2 * i + 1]);
             dst += pairs;
             n -= pairs;
             pos += (int)(2 * pairs);
