@@ -370,7 +370,7 @@ static pass_fn pick_kernel(int kp, int mode, bool tex, bool vec)
 
 static int64_t pass_grid(int64_t n_items, int kp)
 {
-    return cdiv(n_items, (int64_t)8 * (32 / pass_group_lanes(kp))); /* 8 warps per CTA */
+    return cdiv(n_items, (int64_t)(PLSA_PASS_THREADS / 32) * (32 / pass_group_lanes(kp))); /* 8 warps per CTA */
 }
 
 static int launch_pass(plsa_ctx *ctx, int mode, const PassArgs &a, bool vec,
@@ -386,13 +386,18 @@ static int launch_pass(plsa_ctx *ctx, int mode, const PassArgs &a, bool vec,
         static std::map<pass_fn, bool> configured;
         std::lock_guard<std::mutex> lock(mu);
         if (!configured[fn]) {
+#if PLSA_PASS_THREADS == 256
             cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  mode == MODE_TERM ? 15 : 5);
+#else /* occupancy experiments: more, smaller CTAs need a larger share for the same kernels */
+            cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 mode == MODE_TERM ? 30 : 12);
+#endif
             cudaGetLastError(); /* a hint: failure is not an error */
             configured[fn] = true;
         }
     }
-    fn<<<(unsigned)pass_grid(a.n_items, a.kp), 256, 0, stream ? stream : ctx->stream>>>(a);
+    fn<<<(unsigned)pass_grid(a.n_items, a.kp), PLSA_PASS_THREADS, 0, stream ? stream : ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
     return PLSA_OK;

@@ -488,8 +488,21 @@ __device__ __forceinline__ void pass_block(const PassArgs &a, const int2 (&e)[U]
 /* entries of an item in flight = the entry block aligned items start on */
 __host__ __device__ constexpr int pass_block_entries(int KV) { return (KV >= 4) ? 1 : (KV == 2) ? 2 : 4; }
 
+/* CTA shape of the row pass: 8 warps, 4 CTAs per SM at 64 registers (KV == 1).  The macros
+ * exist for occupancy experiments (scripts/build_variants.sh); the host side launches with
+ * PLSA_PASS_THREADS and sizes the grid from it. */
+#ifndef PLSA_PASS_THREADS
+#define PLSA_PASS_THREADS 256
+#endif
+#ifndef PLSA_PASS_MIN_CTAS
+#define PLSA_PASS_MIN_CTAS 4
+#endif
+static_assert(PLSA_PASS_THREADS == 256 || PLSA_PASS_THREADS == 128, "row pass: 4 or 8 warps per CTA");
+
 template <int G, int KV, int MODE, bool TEX, bool VEC>
-__global__ void __launch_bounds__(256, (KV == 1) ? 4 : (KV == 2) ? 2 : 1)
+__global__ void __launch_bounds__(PLSA_PASS_THREADS,
+                                  (KV == 1) ? PLSA_PASS_MIN_CTAS
+                                            : ((KV == 2) ? 2 : 1) * (256 / PLSA_PASS_THREADS))
     row_pass_kernel(const PassArgs a)
 {
     constexpr int NG = 32 / G;

@@ -16,6 +16,13 @@ if [ -f build/libplsa_ftz.so ]; then
     bash scripts/gpu_ab.sh $CFG "ftz 1 0 1 0" "ftz 1 0 1 1" "d 1 0 1 0"
   done
 fi
+for L in ftz128_9 d128_9; do
+  if [ -f build/libplsa_$L.so ]; then
+    ENSTOP_B200_LIB=$PWD/build/libplsa_$L.so timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -5 > gpurun_out/pytest_$L.log
+    tail -2 gpurun_out/pytest_$L.log
+    bash scripts/gpu_ab.sh C2 "$L 1 0 1 0" "$L 1 0 1 1" "d 1 0 1 0"
+  fi
+done
 for ORD in 0 1; do
   ENSTOP_B200_ITEM_ORDER=$ORD timeout 600 ncu --clock-control none -k regex:row_pass -s 9 -c 2 --csv \
     --metrics gpu__time_duration.sum,l1tex__t_sector_hit_rate.pct,lts__t_sectors_srcunit_tex_op_read.sum,lts__t_sector_hit_rate.pct,dram__bytes_read.sum \
