@@ -435,8 +435,12 @@ static int64_t choose_chunk(const plsa_ctx *ctx, int kp)
  * carries then cover the SAME window — the gathers of one chunk hit L1 lines another chunk
  * of the CTA pulled in.  Modelled on the C2 corpus (scripts/sim_item_locality.py): share of
  * the term pass's gathers whose line another item of the same CTA also touches 4 % -> 37 %,
- * hit rate of a 1400-line LRU shared by four resident CTAs 3 % -> 12-14 %.  Item lengths, the
- * slot of every chunk and hence every sum are the same in both orders. */
+ * hit rate of a 1400-line LRU shared by four resident CTAs 3 % -> 12-14 %.
+ * order 2 ("band"): all chunks first, in 32 bands of positions; inside a band longest first,
+ * then by position; the whole rows follow, longest first.  The chunks in flight on the whole
+ * GPU at one time then cover a narrow band of gathered rows — meant for corpora whose
+ * gathered factor does not fit the L2 (C5: P(z|d) is 128 MB).
+ * Item lengths, the slot of every chunk and hence every sum are the same in all orders. */
 struct ItemPlan {
     std::vector<Item> sorted;
     std::vector<int32_t> split_rows, slot_begin;
@@ -447,7 +451,7 @@ static void plan_items(const int32_t *indptr, int64_t rows, const int64_t chunk_
                        int order, ItemPlan &plan)
 {
     const int64_t chunk = std::max<int64_t>(align, chunk_asked / align * align); /* chunks of a split row stay aligned */
-    std::vector<Item> items, pieces;
+    std::vector<Item> items;
     items.reserve((size_t)rows + 1024);
     /* align > 1: an item starts on a multiple of `align` entries at or before its first
      * entry; the entries in between (Item::skip of them, they belong to the row before) are
@@ -479,9 +483,10 @@ static void plan_items(const int32_t *indptr, int64_t rows, const int64_t chunk_
             split_rows.push_back((int32_t)r);
             slot_begin.push_back(slots);
         }
-    /* order 1: the chunks are kept apart and binned by their position inside the row */
-    constexpr int POS_BINS = 4096;
-    std::vector<int32_t> pos_bin;
+    /* orders 1 and 2: the chunks are kept apart and binned by their position inside the row */
+    constexpr int POS_BINS = 4096, BANDS = 32;
+    struct Piece { Item it; int32_t pos; };
+    std::vector<Piece> pieces;
     for (int64_t r = 0; r < rows; ++r) {
         const int64_t skip = lead(r), s = indptr[r] - skip, len = span(r);
         if (len <= chunk) {
@@ -492,23 +497,23 @@ static void plan_items(const int32_t *indptr, int64_t rows, const int64_t chunk_
                 const int64_t b = c * per;
                 const Item it{s + b, (int32_t)r, (int32_t)std::min(per, len - b),
                               first_slot[(size_t)r] + (int32_t)c, (int32_t)(c == 0 ? skip : 0)};
-                if (order == 1) {
-                    pieces.push_back(it);
-                    pos_bin.push_back((int32_t)(b * POS_BINS / len));
-                } else {
-                    items.push_back(it);
-                }
+                if (order != 0) pieces.push_back(Piece{it, (int32_t)(b * POS_BINS / len)});
+                else items.push_back(it);
             }
         }
     }
-    if (order == 1 && !pieces.empty()) { /* stable counting sort of the chunks by position bin */
-        std::vector<int64_t> at((size_t)POS_BINS + 1, 0);
-        for (int32_t b : pos_bin) at[(size_t)b + 1]++;
-        for (int b = 0; b < POS_BINS; ++b) at[(size_t)b + 1] += at[(size_t)b];
-        const size_t whole = items.size();
-        items.resize(whole + pieces.size());
-        for (size_t i = 0; i < pieces.size(); ++i) items[whole + (size_t)at[(size_t)pos_bin[i]]++] = pieces[i];
-    }
+    /* stable counting sort of the chunks by key(piece) in [0, n_keys) */
+    auto bucket = [&](int64_t n_keys, auto key) {
+        std::vector<int64_t> at((size_t)n_keys + 1, 0);
+        for (const Piece &p : pieces) at[(size_t)key(p) + 1]++;
+        for (int64_t b = 0; b < n_keys; ++b) at[(size_t)b + 1] += at[(size_t)b];
+        std::vector<Piece> out(pieces.size());
+        for (const Piece &p : pieces) out[(size_t)at[(size_t)key(p)]++] = p;
+        pieces.swap(out);
+    };
+    if (!pieces.empty()) bucket(POS_BINS, [](const Piece &p) { return (int64_t)p.pos; });
+    if (order == 1)
+        for (const Piece &p : pieces) items.push_back(p.it); /* behind the whole rows */
     /* counting sort by length, descending, stable */
     std::vector<int64_t> cnt((size_t)chunk + 2, 0);
     for (const Item &it : items) cnt[(size_t)(chunk - it.len)]++;
@@ -519,8 +524,15 @@ static void plan_items(const int32_t *indptr, int64_t rows, const int64_t chunk_
         run += t;
     }
     std::vector<Item> &sorted = plan.sorted;
-    sorted.resize(items.size());
-    for (const Item &it : items) sorted[(size_t)cnt[(size_t)(chunk - it.len)]++] = it;
+    const size_t lead_items = order == 2 ? pieces.size() : 0; /* order 2: the chunks go first */
+    sorted.resize(items.size() + lead_items);
+    for (const Item &it : items) sorted[lead_items + (size_t)cnt[(size_t)(chunk - it.len)]++] = it;
+    if (order == 2 && !pieces.empty()) {
+        /* band-major: BANDS bands of positions; inside a band longest first, then by position */
+        bucket(chunk + 1, [&](const Piece &p) { return chunk - (int64_t)p.it.len; });
+        bucket(BANDS, [](const Piece &p) { return (int64_t)p.pos / (POS_BINS / BANDS); });
+        for (size_t i = 0; i < pieces.size(); ++i) sorted[i] = pieces[i].it;
+    }
     plan.n_heavy = (int32_t)heavy.size();
     plan.slots = slots;
 }
@@ -1576,8 +1588,8 @@ API int plsa_set_option(plsa_ctx *ctx, const char *name, int64_t value)
         ctx->vec_entries = value != 0; /* item sets are rebuilt on the next prepare / em */
         return PLSA_OK;
     }
-    if (!strcmp(name, "item_order")) { /* 0 row, 1 window: see plan_items */
-        if (value != 0 && value != 1) return ctx->fail(PLSA_EINVAL, "item_order: 0 or 1");
+    if (!strcmp(name, "item_order")) { /* 0 row, 1 window, 2 band: see plan_items */
+        if (value < 0 || value > 2) return ctx->fail(PLSA_EINVAL, "item_order: 0, 1 or 2");
         ctx->item_order = (int)value; /* item sets are rebuilt on the next prepare / em */
         return PLSA_OK;
     }
@@ -1592,7 +1604,7 @@ API int plsa_plan_items(const int32_t *indptr, int64_t rows, int64_t chunk, int3
                         int32_t *n_slots)
 {
     if (!indptr || rows < 0 || chunk < 1 || align < 1 || (align & (align - 1)) || chunk < align ||
-        (order != 0 && order != 1) || !n_items) {
+        order < 0 || order > 2 || !n_items) {
         g_err = "plan_items: bad argument";
         return PLSA_EINVAL;
     }

@@ -131,8 +131,9 @@ int plsa_launch_count(const plsa_ctx *ctx, int64_t *launches);
  * "texture" (1: gather factor rows through the texture pipe when they fit, 0: plain loads),
  * "fuse_ll" (1: the periodic log-likelihood rides on the next doc pass, 0: separate pass),
  * "item_order" (launch order of same-length work items: 0 = chunks of a split row adjacent,
- * 1 = chunks that cover the same window of gathered rows adjacent, for L1 reuse inside a CTA;
- * the sums are the same in both orders). */
+ * 1 = chunks that cover the same window of gathered rows adjacent, for L1 reuse inside a CTA,
+ * 2 = all chunks first in bands of positions, for L2 reuse when the gathered factor exceeds
+ * the L2; the sums are the same in all orders). */
 int plsa_set_option(plsa_ctx *ctx, const char *name, int64_t value);
 /* Host-only (no device): the work items a pass over a CSR with these row pointers would launch,
  * in launch order.  A row longer than `chunk` entries is cut into equal chunks that write

@@ -7,8 +7,9 @@
 #   bash scripts/build_variants.sh && gpurun --timeout 2400 -- 'bash scripts/gpu_item_order.sh'
 mkdir -p gpurun_out
 for CFG in C2 C3; do
-  bash scripts/gpu_ab.sh $CFG "d 1 0 1 0" "d 1 0 1 1" "d 1 0 1 0" "d 1 0 1 1"
+  bash scripts/gpu_ab.sh $CFG "d 1 0 1 0" "d 1 0 1 1" "d 1 0 1 2" "d 1 0 1 0" "d 1 0 1 1" "d 1 0 1 2"
 done
+bash scripts/gpu_ab.sh C5 "d 1 0 1 0" "d 1 0 1 1" "d 1 0 1 2"   # order 2 is meant for this size
 if [ -f build/libplsa_ftz.so ]; then
   ENSTOP_B200_LIB=$PWD/build/libplsa_ftz.so timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q 2>&1 | tail -15 > gpurun_out/pytest_ftz.log
   tail -3 gpurun_out/pytest_ftz.log
@@ -23,7 +24,7 @@ for L in ftz128_9 d128_9; do
     bash scripts/gpu_ab.sh C2 "$L 1 0 1 0" "$L 1 0 1 1" "d 1 0 1 0"
   fi
 done
-for ORD in 0 1; do
+for ORD in 0 1 2; do
   ENSTOP_B200_ITEM_ORDER=$ORD timeout 600 ncu --clock-control none -k regex:row_pass -s 9 -c 2 --csv \
     --metrics gpu__time_duration.sum,l1tex__t_sector_hit_rate.pct,lts__t_sectors_srcunit_tex_op_read.sum,lts__t_sector_hit_rate.pct,dram__bytes_read.sum \
     --log-file gpurun_out/item_order_${ORD}_ncu.csv \

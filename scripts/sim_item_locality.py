@@ -124,6 +124,21 @@ def lru_hit_rate(items, order, gat, items_per_cta, items_per_warp, lines=1400, s
 
 
 
+def inflight_working_set(items, gat, items_per_cta, ctas_in_flight=592, row_bytes=128):
+    """Distinct gathered rows of every run of `ctas_in_flight` consecutive CTAs (what the whole
+    GPU has in flight at one time) x 128 bytes: the L2 footprint of the gathered factor."""
+    start, length, skip = items["start"], items["len"], items["skip"]
+    real = length - skip
+    n_items = start.shape[0]
+    win = (np.arange(n_items) // items_per_cta) // ctas_in_flight
+    offs = np.repeat(start + skip - (np.cumsum(real) - real), real) + np.arange(real.sum())
+    key = np.repeat(win, real).astype(np.int64) * (int(gat.max()) + 1) + gat[offs]
+    uniq = np.unique(key)
+    per_win = np.bincount((uniq // (int(gat.max()) + 1)).astype(np.int64))
+    tot_win = np.bincount(np.repeat(win, real))
+    return per_win * row_bytes / 1e6, tot_win
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("config", nargs="?", default="C2")
@@ -146,7 +161,8 @@ def main():
     for name, M in (("term pass", X.T.tocsr()), ("doc pass", X)):
         M.sort_indices()
         gat = M.indices
-        for order, label in ((0, "row (library, order 0)"), (1, "window (library, order 1)")):
+        for order, label in ((0, "row (library, order 0)"), (1, "window (library, order 1)"),
+                             (2, "band (library, order 2)")):
             p = _lib.plan_items(M.indptr, args.chunk, align=args.align, order=order)
             it = dict(start=p["start"], len=p["len"].astype(np.int64), skip=p["skip"].astype(np.int64),
                       split=p["slot"] >= 0, row=p["row"])
@@ -155,6 +171,9 @@ def main():
                 print("--", name, "(%d items, %d of them chunks of split rows)"
                       % (ident.shape[0], int(it["split"].sum())))
             evaluate(it, ident, gat, ipc, ipw, label)
+            ws, tw = inflight_working_set(it, gat, ipc)
+            print("      gathered rows in flight per 592 CTAs: %s MB (gathers per run: %s k)"
+                  % (" ".join("%.1f" % w for w in ws), " ".join("%d" % (t // 1000) for t in tw)))
             for lines in [int(x) for x in args.lru_lines.split(",")]:
                 h, tot = lru_hit_rate(it, ident, gat, ipc, ipw, lines=lines)
                 print("      LRU of %4d lines per SM (4 resident CTAs, 4 SMs sampled): gather hit "

@@ -1,6 +1,6 @@
 """GPU: the work-item launch orders of the row pass (plsa_set_option "item_order").
 
-Order 1 ("window") only permutes same-length work items (tests/test_host_cpu.py checks the
+Orders 1 ("window") and 2 ("band") only permute the work items (tests/test_host_cpu.py checks the
 plan on the CPU); every per-row sum is taken over the same entries in the same order, so the
 factors must agree with order 0 to float rounding of the column sums / log-likelihood (whose
 per-CTA partial sums are grouped differently) and with the float64 oracle at the parity
@@ -41,7 +41,9 @@ def test_window_order_is_the_same_model(k, chunk):
     X = synth.make_corpus(1500, 900, 120_000, seed=21, planted=True, k_true=6)
     a = _fit(X, k, 0, 5, chunk)
     b = _fit(X, k, 1, 5, chunk)
-    assert a[2] == b[2] == 5
+    c = _fit(X, k, 2, 5, chunk)
+    assert a[2] == b[2] == c[2] == 5
+    assert rel_l2(c[1], a[1]) < 5e-6 and rel_l2(c[0], a[0]) < 5e-6
     assert rel_l2(b[1], a[1]) < 5e-6 and rel_l2(b[0], a[0]) < 5e-6
     assert np.allclose(a[3], b[3], rtol=1e-9)
     sw = np.ones(X.shape[0], dtype=np.float32)

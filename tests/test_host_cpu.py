@@ -198,7 +198,7 @@ def _ragged_indptr(rng, rows, long_rows):
 
 
 @pytest.mark.parametrize("chunk,align", [(256, 4), (32, 4), (64, 1), (2048, 2), (100, 4)])
-@pytest.mark.parametrize("order", [0, 1])
+@pytest.mark.parametrize("order", [0, 1, 2])
 def test_work_item_plan_covers_every_entry_once(chunk, align, order):
     """plan_items (host side of the row pass, csrc/plsa_b200.cu): in either launch order the
     items tile the stored entries exactly, chunks of a split row own consecutive slots, items
@@ -210,7 +210,12 @@ def test_work_item_plan_covers_every_entry_once(chunk, align, order):
     eff = chunk // align * align
     assert np.all(ln <= eff) and np.all(ln >= 0) and np.all(skip >= 0) and np.all(skip < align)
     assert np.all(start % align == 0)
-    assert np.all(np.diff(ln) <= 0), "items must be sorted by length, longest first"
+    if order < 2:
+        assert np.all(np.diff(ln) <= 0), "items must be sorted by length, longest first"
+    else:   # band order: every chunk ahead of every whole row, whole rows longest first
+        n_chunks = int(np.sum(slot >= 0))
+        assert np.all(slot[:n_chunks] >= 0) and np.all(slot[n_chunks:] < 0)
+        assert np.all(np.diff(ln[n_chunks:]) <= 0)
     # every stored entry is covered by exactly one item of its own row
     cover = np.zeros(int(indptr[-1]), dtype=np.int32)
     owner = np.full(int(indptr[-1]), -1, dtype=np.int64)
@@ -257,8 +262,17 @@ def test_work_item_orders_hold_the_same_items():
     assert np.all(np.diff(pos_b)[same] >= -1.0 / 4096 - 1e-12)
     with pytest.raises(_lib.PlsaError):
         _lib.plan_items(indptr, 256, align=3, order=0)
+    # band order: the same items again; the band (1/32 of the row) never decreases along the
+    # chunks, and inside a band the lengths never increase
+    c = _lib.plan_items(indptr, 256, align=4, order=2)
+    assert key(c) == key(a)
+    chunks_c = c["slot"] >= 0
+    band = np.floor(positions(c)[chunks_c] * 4096).astype(np.int64) // 128
+    assert np.all(np.diff(band) >= 0)
+    same_band = band[1:] == band[:-1]
+    assert np.all(np.diff(c["len"][chunks_c])[same_band] <= 0)
     with pytest.raises(_lib.PlsaError):
-        _lib.plan_items(indptr, 256, align=4, order=2)
+        _lib.plan_items(indptr, 256, align=4, order=3)
 
 
 def _emulate_pass(indptr, idx, val, own, gat, plan, thresh, normalise):
@@ -292,7 +306,7 @@ def _emulate_pass(indptr, idx, val, own, gat, plan, thresh, normalise):
     return own_new
 
 
-@pytest.mark.parametrize("order", [0, 1])
+@pytest.mark.parametrize("order", [0, 1, 2])
 def test_planned_passes_are_one_em_iteration(order):
     """Host-side plan semantics end to end on the CPU: a doc pass and a term pass carried out
     item by item from plsa_plan_items (both launch orders, aligned items, split rows), with
