@@ -274,9 +274,22 @@ def make_config_once(name, plumb, rank, world):
     ranks of the box through /dev/shm (the generator sorts up to 3e8 keys; N copies of that at
     once would be most of the run)."""
     from enstop_b200 import synth
+    import scipy.sparse as sp
+    cache = os.environ.get("ENSTOP_B200_CORPUS_CACHE")   # A/B scripts: reuse a generated corpus
+    if world == 1 and cache:
+        path = os.path.join(cache, "enstop_b200_%s.npz" % name)
+        if os.path.exists(path):
+            with np.load(path) as z:
+                X = sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=tuple(z["shape"]))
+                info = json.loads(str(z["info"]))
+            X.has_sorted_indices = True
+            return X, info
+        X, info = synth.make_config(name, return_info=True)
+        np.savez(path, data=X.data, indices=X.indices, indptr=X.indptr, shape=np.array(X.shape),
+                 info=np.array(json.dumps(info)))
+        return X, info
     if world == 1:
         return synth.make_config(name, return_info=True)
-    import scipy.sparse as sp
     path = "/dev/shm/enstop_b200_%s_%s.npz" % (name, os.environ.get("MASTER_PORT", "0"))
     if rank == 0:
         X, info = synth.make_config(name, return_info=True)
