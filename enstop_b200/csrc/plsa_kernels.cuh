@@ -146,7 +146,10 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
  * flush-to-zero multiply drops it; the posterior v / sum(v) and the M-step sums do not see
  * the common factor, the log-likelihood subtracts log2(S).  Exact scaling; the products that
  * are dropped are those below T = FLT_MIN / S, thresh <= T < 2 thresh (the reference drops
- * v <= thresh).  8 of the 33 instructions per stored entry go away. */
+ * v <= thresh).  8 of the 33 instructions per stored entry go away.  Known edge: a surviving
+ * normaliser can be as small as FLT_MIN, so x / norm overflows (and is clamped) for an entry
+ * with count x > 4 whose true normaliser lies in [T, T x / 4) — entries the reference keeps at
+ * full weight although they sit a hair above its own cut-off. */
 #ifndef PLSA_EXP_FTZ_THRESH
 #define PLSA_EXP_FTZ_THRESH 0
 #endif
