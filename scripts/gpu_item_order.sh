@@ -9,6 +9,7 @@ mkdir -p gpurun_out
 for CFG in C2 C3; do
   bash scripts/gpu_ab.sh $CFG "d 1 0 1 0" "d 1 0 1 1" "d 1 0 1 2" "d 1 0 1 0" "d 1 0 1 1" "d 1 0 1 2"
 done
+bash scripts/gpu_ab.sh C2 "d 1 192 1 2" "d 1 320 1 2" "d 1 192 1 1" "d 1 320 1 1"   # item length x order
 AB_TIMEOUT=1500 bash scripts/gpu_ab.sh C5 "d 1 0 1 0" "d 1 0 1 1" "d 1 0 1 2"   # order 2 is meant for this size
 if [ -f build/libplsa_ftz.so ]; then
   ENSTOP_B200_LIB=$PWD/build/libplsa_ftz.so timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q 2>&1 | tail -15 > gpurun_out/pytest_ftz.log
