@@ -59,3 +59,31 @@ def test_window_order_with_sample_weights_and_bit_repeatable():
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     c = _fit(X, 12, 0, 8, 32, sw=sw, use_sw=True)
     assert rel_l2(a[1], c[1]) < 5e-6 and rel_l2(a[0], c[0]) < 5e-6
+
+
+def test_failed_calls_leave_a_consistent_context():
+    """A rejected bootstrap keeps the corpus and model the context had; a failed upload leaves
+    the context without a corpus (not with half of one)."""
+    import types
+    X = synth.make_corpus(300, 200, 6_000, seed=4, planted=True, k_true=3)
+    n, m = X.shape
+    pzd0, pwz0 = plsa.plsa_init(X, 4, "random", np.random.RandomState(1))
+    with _lib.Context(0) as ctx:
+        ctx.upload_csr(X)
+        ctx.set_factors(pzd0.astype(np.float32), pwz0.astype(np.float32))
+        with pytest.raises(_lib.PlsaError, match="row index out of range"):
+            ctx.bootstrap(np.array([0, n + 5, 2], dtype=np.int32))
+        assert ctx.shape == (n, m, X.nnz)
+        iters, _ = ctx.em(2, tolerance=0.0)              # corpus and factors are still there
+        assert iters == 2
+        ctx.bootstrap(np.arange(n - 1, -1, -1, dtype=np.int32))
+        assert ctx.shape == (n, m, X.nnz)
+        bad = types.SimpleNamespace(indptr=X.indptr, indices=np.where(
+            np.arange(X.nnz) == 17, m + 3, X.indices).astype(np.int32), data=X.data, shape=X.shape)
+        with pytest.raises(_lib.PlsaError, match="column index out of range"):
+            ctx.upload_csr(bad)
+        with pytest.raises(_lib.PlsaError, match="no corpus uploaded"):
+            ctx.set_factors(pzd0.astype(np.float32), pwz0.astype(np.float32))
+        ctx.upload_csr(X)                                 # and the context is reusable
+        ctx.set_factors(pzd0.astype(np.float32), pwz0.astype(np.float32))
+        assert ctx.em(1, tolerance=0.0)[0] == 1
