@@ -59,6 +59,12 @@ def traffic(rep, config, out_json):
             'dram_bytes_write': val(r, 'dram__bytes_write.sum'),
             'duration_us_under_ncu': float(r[hdr.index('gpu__time_duration.sum')]),
             'source': os.path.basename(rep)}
+        if 'lts__t_sectors_srcunit_tex_op_read.sum' in hdr:   # 32-byte sectors L2 -> SMs
+            entry[names.get(mode, mode)]['lts_sectors_read_from_sm'] = float(
+                r[hdr.index('lts__t_sectors_srcunit_tex_op_read.sum')])
+        if 'l1tex__t_sector_hit_rate.pct' in hdr:
+            entry[names.get(mode, mode)]['l1_sector_hit_rate_pct'] = float(
+                r[hdr.index('l1tex__t_sector_hit_rate.pct')])
     json.dump(data, open(out_json, 'w'), indent=1, sort_keys=True)
     print(json.dumps(entry, indent=1))
 
