@@ -170,6 +170,209 @@ class Plumbing:
             self.dist.destroy_process_group()
 
 
+class IpcExchange:
+    """Peer-memory all-reduce of a document-sharded fit between PROCESSES (one rank per GPU):
+    every rank exports the CUDA IPC handle of its exchange block through the launcher's
+    rendezvous and maps its peers'.  Falls back to ncclAllReduce on every rank if any rank
+    cannot."""
+
+    def __init__(self, plumb, no_p2p=False):
+        self.plumb, self.no_p2p = plumb, no_p2p
+
+    def __call__(self, c, r):
+        from enstop_b200 import _lib
+        if self.no_p2p:
+            return False
+        try:
+            c.shard_p2p_prepare()
+            mine = c.shard_p2p_export()
+        except _lib.PlsaError:
+            mine = None
+        handles = self.plumb.allgather(mine)
+        ok = all(h is not None for h in handles)
+        if ok:
+            try:
+                for p, h in enumerate(handles):
+                    if p != r:
+                        c.shard_p2p_attach(p, -1, handle=h)
+            except _lib.PlsaError:
+                ok = False
+        ok = all(self.plumb.allgather(ok))
+        if not ok:
+            c.set_option("p2p", 0)
+        return ok
+
+    def finish(self, c):     # importers unmap before any exporter frees its block
+        c.shard_p2p_detach()
+        self.plumb.barrier()
+
+
+def _rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+TOL_SHARD_VS_SINGLE = 5e-6      # tests/test_gpu_sharded.py
+TOL_VS_REFERENCE = 3e-4         # tests/test_gpu_parity.py TOL_REF_50 (the reference's own drift)
+
+
+def sharded_fit_checks(plumb, rank, world, device):
+    """N > 1, before anything is timed: ONE fit of the committed C1 golden corpus with its
+    documents sharded over all N ranks — through the peer-memory reduce kernel and through
+    ncclAllReduce — against the same fit on one GPU and against the reference's own output
+    (tests/golden/c1_planted.npz, made by tests/golden/make_golden.py from enstop/plsa.py).
+    Returns the list of check records (rank 0; every rank learns the verdict)."""
+    import scipy.sparse as sp
+    from enstop_b200 import _lib, plsa
+    g = np.load(os.path.join(ROOT, "tests", "golden", "c1_planted.npz"))
+    X = sp.csr_matrix((g["data"], g["indices"], g["indptr"]), shape=tuple(g["shape"]))
+    k, n = int(g["k"]), X.shape[0]
+    n_iter = 10
+    sw = np.ones(n, dtype=np.float32)
+    bounds = plsa.shard_rows(X.indptr, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    single = None
+    if rank == 0:
+        single = plsa.plsa_fit(X, k, sw, init=(g["pzd0"], g["pwz0"]), n_iter=n_iter, tolerance=0.0,
+                               device=device)
+    uid = plumb.bcast_bytes(_lib.Comm.unique_id() if rank == 0 else None)
+    comm = _lib.Comm(device, world, rank, uid)
+    checks = []
+    for path in ("peer-memory kernel", "ncclAllReduce"):
+        ex = IpcExchange(plumb, no_p2p=(path == "ncclAllReduce"))
+        pzd_rows, pwz, info = plsa.plsa_fit_shard(X[lo:hi], k, g["pzd0"][lo:hi], g["pwz0"], sw[lo:hi],
+                                                  comm, device, n_iter=n_iter, tolerance=0.0,
+                                                  exchange=ex)
+        parts = plumb.allgather(pzd_rows)
+        pwzs = plumb.allgather(pwz if rank in (0, world - 1) else None)
+        used = plumb.allgather(bool(info["p2p"]))
+        if rank == 0:
+            pzd = np.concatenate(parts)
+            rec = {"check": "doc-sharded fit of C1 golden over %d ranks, %s" % (world, path),
+                   "exchange_used": "peer-memory kernel" if all(used) else "ncclAllReduce",
+                   "iters": int(info["n_iter"]),
+                   "components_vs_single_gpu": _rel_l2(pwz, single[1]),
+                   "embedding_vs_single_gpu": _rel_l2(pzd, single[0]),
+                   "components_vs_reference_golden": _rel_l2(pwz, g["pwz_%d" % n_iter]),
+                   "embedding_vs_reference_golden": _rel_l2(pzd, g["pzd_%d" % n_iter]),
+                   "ranks_agree_bitwise": bool(np.array_equal(pwzs[0], pwzs[world - 1]))}
+            rec["ok"] = bool(rec["iters"] == n_iter and rec["ranks_agree_bitwise"]
+                             and rec["components_vs_single_gpu"] < TOL_SHARD_VS_SINGLE
+                             and rec["embedding_vs_single_gpu"] < TOL_SHARD_VS_SINGLE
+                             and rec["components_vs_reference_golden"] < TOL_VS_REFERENCE
+                             and rec["embedding_vs_reference_golden"] < TOL_VS_REFERENCE)
+            checks.append(rec)
+    comm.close()
+    return checks
+
+
+C4_KW = dict(init="random", n_iter=80, n_iter_per_test=10, tolerance=0.001, e_step_thresh=1e-32,
+             bootstrap=True)   # EnsembleTopics' constructor defaults (enstop_.py:709-730)
+
+
+def run_c4(plumb, rank, world, device, X, k, n_starts=16, seed=42):
+    """BASELINE.json config 4: the fan-out of EnsembleTopics(n_components=k, n_starts=16) over
+    the N ranks — member r on rank r mod N (enstop_.py:209-217), two lanes per GPU, topics left
+    on the device — and the gather of the stacked topic matrices to rank 0 over NCCL
+    (enstop_.py:231).  Strong scaling: the 16 members are fixed.  Members 0 and n_starts-1 are
+    then fitted alone on rank 0 and must equal their rows of the gathered stack bit for bit."""
+    from enstop_b200 import _lib, enstop_
+    seeds = enstop_.member_seeds(seed, n_starts)
+    shards = enstop_.shard_members(n_starts, world)
+    counts = [len(m) for m in shards]
+    comm = None
+    if world > 1:
+        uid = plumb.bcast_bytes(_lib.Comm.unique_id() if rank == 0 else None)
+        comm = _lib.Comm(device, world, rank, uid)
+
+    def once():
+        plumb.barrier()
+        t0 = time.perf_counter()
+        ctx, order, used = enstop_.fit_members_on_device(X, k, device, shards[rank], seeds, **C4_KW)
+        t_fit = time.perf_counter() - t0
+        if comm is not None:
+            stacked = comm.gather_topics(ctx, counts, root=0)
+        else:
+            stacked = _lib.gather_topics([ctx], counts)
+        dt = time.perf_counter() - t0
+        enstop_.release_member_contexts(used)
+        plumb.barrier()
+        return stacked, order, plumb.max(dt), plumb.max(t_fit)
+
+    once()          # warm-up: NCCL connects its peers, contexts and pinned staging are created
+    stacked, order, wall, fit_wall = once()
+    orders = plumb.allgather(order)
+    if comm is not None:
+        comm.close()
+    out = None
+    if rank == 0:
+        all_topics = enstop_.stack_in_member_order(stacked, orders, k)
+        checks = []
+        for r in (0, n_starts - 1):
+            alone = enstop_.plsa_topics(X, k, random_state=seeds[r], device=device, **C4_KW)
+            mine = all_topics[r * k:(r + 1) * k]
+            checks.append({"check": "C4 member %d (fitted on rank %d, gathered) == the same member "
+                                    "fitted alone" % (r, r % world),
+                           "bit_equal": bool(np.array_equal(alone, mine)),
+                           "rel_l2": _rel_l2(mine, alone),
+                           "ok": bool(np.array_equal(alone, mine))})
+        rows_ok = bool(np.allclose(all_topics.sum(axis=1), 1.0, atol=1e-4))
+        checks.append({"check": "C4 stack is [%d, %d], rows sum to 1" % all_topics.shape,
+                       "ok": bool(all_topics.shape == (n_starts * k, X.shape[1]) and rows_ok)})
+        out = {"c4_wall_s": wall, "c4_fit_wall_s": fit_wall, "c4_gather_s": wall - fit_wall,
+               "c4": {"workload": "EnsembleTopics(n_components=%d, n_starts=%d) fan-out + gather on "
+                                  "the C2 corpus, members %s per rank, two lanes per GPU"
+                                  % (k, n_starts, counts),
+                      "scaling": "strong", "member_seeds_from": seed, "kwargs": C4_KW},
+               "checks": checks}
+    return out
+
+
+def c1_parity(device):
+    """BASELINE.json config 1 from the committed goldens (no reference, no oracle at run time):
+    50 EM iterations from the goldens' start through the C ABI; relative L2 of components_
+    (P(w|z)) and embedding_ (P(z|d)) between the engine, the reference's own output
+    (tests/golden/c1_*.npz, made from enstop/plsa.py by make_golden.py) and the float64-exact
+    EM (tests/golden/c1_exact.npz, make_exact.py)."""
+    import scipy.sparse as sp
+    from enstop_b200 import plsa
+    out = {}
+    try:
+        ex = np.load(os.path.join(ROOT, "tests", "golden", "c1_exact.npz"))
+        for tag in ("c1_planted", "c1_zipf"):
+            g = np.load(os.path.join(ROOT, "tests", "golden", tag + ".npz"))
+            X = sp.csr_matrix((g["data"], g["indices"], g["indptr"]), shape=tuple(g["shape"]))
+            sw = np.ones(X.shape[0], dtype=np.float32)
+            pzd, pwz = plsa.plsa_fit(X, int(g["k"]), sw, init=(g["pzd0"], g["pwz0"]), n_iter=50,
+                                     tolerance=0.0, device=device)
+            out[tag] = {
+                "components_engine_vs_reference": _rel_l2(pwz, g["pwz_50"]),
+                "components_engine_vs_f64_exact": _rel_l2(pwz, ex[tag + "_pwz_50"]),
+                "components_reference_vs_f64_exact": _rel_l2(g["pwz_50"], ex[tag + "_pwz_50"]),
+                "embedding_engine_vs_reference": _rel_l2(pzd, g["pzd_50"]),
+                "embedding_engine_vs_f64_exact": _rel_l2(pzd, ex[tag + "_pzd_50"]),
+                "embedding_reference_vs_f64_exact": _rel_l2(g["pzd_50"], ex[tag + "_pzd_50"]),
+            }
+        out["note"] = ("relative L2 after 50 EM iterations from the same float32 start, k=10, "
+                       "2000 x 5000; the reference's serial float32 accumulators put IT ~1e-4 from "
+                       "exact arithmetic, which bounds engine_vs_reference from below")
+    except Exception as exc:   # a report, never a reason to lose the bench line
+        out["error"] = repr(exc)
+    return out
+
+
+def finish_checks(plumb, rank, checks):
+    """Every rank learns whether all checks passed; a failure ends the run non-zero."""
+    ok = all(c.get("ok", False) for c in checks) if rank == 0 else True
+    ok = all(plumb.allgather(ok))
+    if not ok:
+        if rank == 0:
+            print(json.dumps({"parity_checks": checks, "error": "parity check failed"}), file=sys.stderr)
+        plumb.close()
+        sys.exit(3)
+
+
 def measured_traffic(config):
     """DRAM bytes per launch of the doc pass from the committed `ncu --set full` capture of
     this same command (profiles/traffic.json, written by scripts/ncu_summary.py --traffic)."""
@@ -349,38 +552,7 @@ def run_shard(args, plumb, rank, world, device):
     ctx.set_factors(pzd0[lo:hi].astype(np.float32), pwz0.astype(np.float32))
     ctx.set_sample_weight(None)
 
-    class Exchange:
-        """peer-memory all-reduce between processes: CUDA IPC handles through the launcher"""
-
-        def __call__(self, c, r):
-            return exchange_setup(c, r)
-
-        def finish(self, c):     # importers unmap before any exporter frees its block
-            c.shard_p2p_detach()
-            plumb.barrier()
-
-    def exchange_setup(c, r):
-        if args.no_p2p:
-            return False
-        try:
-            c.shard_p2p_prepare()
-            mine = c.shard_p2p_export()
-        except _lib.PlsaError:
-            mine = None
-        handles = plumb.allgather(mine)
-        ok = all(h is not None for h in handles)
-        if ok:
-            try:
-                for p, h in enumerate(handles):
-                    if p != r:
-                        c.shard_p2p_attach(p, -1, handle=h)
-            except _lib.PlsaError:
-                ok = False
-        ok = all(plumb.allgather(ok))
-        if not ok:
-            c.set_option("p2p", 0)
-        return ok
-    exchange = Exchange()
+    exchange = IpcExchange(plumb, args.no_p2p)
     p2p = exchange(ctx, rank)
     ctx.em(args.warmup, n_iter_per_test=10, tolerance=0.0)
     sampler = ClockSampler(device)
@@ -476,6 +648,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-p2p", action="store_true", help="--mode shard: ncclAllReduce instead of "
                                                           "the peer-memory all-reduce kernel")
+    ap.add_argument("--no-checks", action="store_true", help="N > 1: skip the sharded-fit parity checks")
+    ap.add_argument("--no-c4", action="store_true", help="skip the 16-member ensemble (config 4) leg")
     ap.add_argument("--cpu-iters", type=int, default=10)
     ap.add_argument("--profile-iters", type=int, default=20)
     ap.add_argument("--e2e-repeats", type=int, default=3)
@@ -498,6 +672,11 @@ def main():
         return
     cfg = synth.CONFIGS[args.config]
     k = cfg["k"]
+    # ---- N > 1: parity of the multi-GPU paths, before anything is timed ---------------------
+    parity_checks = []
+    if world > 1 and not args.no_checks:
+        parity_checks += sharded_fit_checks(plumb, rank, world, device) or []
+        finish_checks(plumb, rank, parity_checks)
     X, info = make_config_once(args.config, plumb, rank, world)
     n, m = X.shape
     peak, peak_src = load_peaks()
@@ -623,6 +802,15 @@ def main():
                          "enstop/plsa.py:182)" % (args.cpu_iters, args.config)}
 
     ctx.close()
+    _lib.release_device_memory()
+
+    # ---- BASELINE.json config 4: the 16-member ensemble over the N ranks (strong scaling) ---
+    c4 = None
+    if args.config == "C2" and not args.no_c4:
+        c4 = run_c4(plumb, rank, world, device, X, k)
+        if rank == 0:
+            parity_checks += c4.pop("checks")
+        finish_checks(plumb, rank, parity_checks)
     if rank == 0:
         line = {
             "metric": METRIC % k, "value": value, "unit": UNIT, "n_gpus": world,
@@ -647,6 +835,11 @@ def main():
         }
         if gather_ms is not None:
             line["ensemble_gather_ms"] = gather_ms
+        if c4 is not None:
+            line.update(c4)
+        line["parity_checks"] = parity_checks
+        if world == 1:
+            line["parity"] = c1_parity(device)
         print(json.dumps(line))
     plumb.close()
 

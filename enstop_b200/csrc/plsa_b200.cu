@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -30,6 +31,7 @@
 
 #include "../../include/plsa_b200.h"
 #include "plsa_kernels.cuh"
+#include "plsa_tile.cuh"
 
 using namespace plsa;
 
@@ -92,6 +94,30 @@ struct ItemSet {
     int order = 0; /* plan_items order the set was built with */
 };
 
+/* Tiled doc pass (plsa_tile.cuh): the doc-major corpus split into a "head" CSR whose columns
+ * are slots of the shared-memory tile (the most frequent terms) and a "tail" CSR with the
+ * rest, which stays with the group-per-row kernel. */
+struct TileSet {
+    bool ready = false;
+    int32_t kp = 0, tile_rows = 0, pitch_f = 0;
+    int64_t n = 0, head_slots = 0, tail_nnz = 0;
+    DevBuf col_count, col_ids, col_count_sorted, col_sorted, slot_of, head_len, tail_len,
+        head_indptr, tail_indptr, head_ent, tail_ent, order, order_keys, row_ids, cub_tmp, head_sum,
+        img[2], scale_raw, ll_part, ll_head, ll_ticket;
+    std::vector<int32_t> h_tail_indptr;
+    ItemSet tail_items;
+    void release()
+    {
+        for (DevBuf *b : {&col_count, &col_ids, &col_count_sorted, &col_sorted, &slot_of, &head_len,
+                          &tail_len, &head_indptr, &tail_indptr, &head_ent, &tail_ent, &order,
+                          &order_keys, &row_ids, &cub_tmp, &head_sum, &img[0], &img[1], &scale_raw,
+                          &ll_part, &ll_head, &ll_ticket, &tail_items.items, &tail_items.split_rows,
+                          &tail_items.slot_begin})
+            b->release();
+        ready = false;
+    }
+};
+
 } // namespace
 
 struct plsa_ctx {
@@ -111,6 +137,11 @@ struct plsa_ctx {
     bool t_ready = false, t_weighted_ready = false;
 
     ItemSet doc_items, term_items;
+    TileSet tiles;
+    int tiled_opt = -1;                 /* option "tiled": -1 auto, 0 off, 1 on where possible */
+    int64_t tile_bytes = 200 * 1024;    /* option "tile_kb": shared memory of the tile        */
+    bool b_norm[2] = {false, false};    /* B[i] is column-normalised in place, tiles.img[i] holds its tile rows */
+    int n_sms = 0;
     int64_t chunk_user = 0;  /* option "chunk": 0 = chosen per corpus size and k */
     int64_t chunk_built = 0; /* work-item length the item sets were built with */
     int32_t k_hint = 0;      /* plsa_prepare: k the items should be sized for */
@@ -157,6 +188,7 @@ struct plsa_ctx {
         int n_attached = 0;
         unsigned int seq = 0;
         bool enabled = true; /* option "p2p" */
+        int64_t timeout_ms = 30000; /* option "p2p_timeout_ms": wait for a peer's signal */
     } p2p;
 
     /* measurement */
@@ -383,9 +415,9 @@ static int launch_pass(plsa_ctx *ctx, int mode, const PassArgs &a, bool vec,
          * shared-memory carve-out that still holds the resident CTAs (ncu showed 64 KB being
          * set aside for the term pass by default). */
         static std::mutex mu;
-        static std::map<pass_fn, bool> configured;
+        static std::map<std::pair<int, pass_fn>, bool> configured; /* function attributes are per device */
         std::lock_guard<std::mutex> lock(mu);
-        if (!configured[fn]) {
+        if (!configured[std::make_pair(ctx->device, fn)]) {
 #if PLSA_PASS_THREADS == 256
             cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  mode == MODE_TERM ? 15 : 5);
@@ -394,7 +426,7 @@ static int launch_pass(plsa_ctx *ctx, int mode, const PassArgs &a, bool vec,
                                  mode == MODE_TERM ? 30 : 12);
 #endif
             cudaGetLastError(); /* a hint: failure is not an error */
-            configured[fn] = true;
+            configured[std::make_pair(ctx->device, fn)] = true;
         }
     }
     fn<<<(unsigned)pass_grid(a.n_items, a.kp), PLSA_PASS_THREADS, 0, stream ? stream : ctx->stream>>>(a);
@@ -496,7 +528,8 @@ static void plan_items(const int32_t *indptr, int64_t rows, const int64_t chunk_
             for (int64_t c = 0; c < nc; ++c) {
                 const int64_t b = c * per;
                 const Item it{s + b, (int32_t)r, (int32_t)std::min(per, len - b),
-                              first_slot[(size_t)r] + (int32_t)c, (int32_t)(c == 0 ? skip : 0)};
+                              first_slot[(size_t)r] + (int32_t)c,
+                              (int32_t)(c == 0 ? (skip | ITEM_FIRST) : 0)};
                 if (order != 0) pieces.push_back(Piece{it, (int32_t)(b * POS_BINS / len)});
                 else items.push_back(it);
             }
@@ -663,8 +696,175 @@ static int ensure_weighted_vals(plsa_ctx *ctx)
     return PLSA_OK;
 }
 
+/* ---- tiled doc pass: head / tail split of the doc-major corpus (plsa_tile.cuh) --------------- */
+static bool tiled_possible(const plsa_ctx *ctx, int kp)
+{
+    const Corpus &c = ctx->cur();
+    return ctx->tiled_opt != 0 && ctx->shard == nullptr && kp >= 4 && kp <= 24 && c.n > 0 && c.m > 0 &&
+           c.nnz > 0 && c.nnz < ((int64_t)1 << 28); /* padded head slots (< 8 nnz) stay int32 */
+}
+
+static bool tiled_wanted(const plsa_ctx *ctx, int kp)
+{
+    if (!tiled_possible(ctx, kp)) return false;
+    if (ctx->tiled_opt > 0) return true;
+    return ctx->cur().nnz >= 2'000'000; /* below this the tile load and two launches do not pay */
+}
+
+typedef void (*tile_fn)(const TileArgs);
+template <int KC> static tile_fn pick_tile_ll(bool ll)
+{
+    return ll ? tile_pass_kernel<KC, true> : tile_pass_kernel<KC, false>;
+}
+static tile_fn pick_tile_kernel(int kp, bool ll)
+{
+    switch (kp / 4) {
+    case 1: return pick_tile_ll<1>(ll);
+    case 2: return pick_tile_ll<2>(ll);
+    case 3: return pick_tile_ll<3>(ll);
+    case 4: return pick_tile_ll<4>(ll);
+    case 5: return pick_tile_ll<5>(ll);
+    default: return pick_tile_ll<6>(ll);
+    }
+}
+
+static int ensure_tiles(plsa_ctx *ctx, int kp)
+{
+    TileSet &t = ctx->tiles;
+    const Corpus &c = ctx->cur();
+    const int64_t n = c.n, m = c.m, nnz = c.nnz;
+    const int pc = tile_pitch_chunks(kp / 4);
+    const int32_t cap = (int32_t)std::max<int64_t>(TILE_MIN_ROWS, ctx->tile_bytes / (pc * 16));
+    const int32_t tile_rows = (int32_t)std::min<int64_t>(m, cap);
+    const int64_t chunk = choose_chunk(ctx, kp);
+    const int align = ctx->vec_entries ? pass_entry_block(kp) : 1;
+    if (t.ready && t.kp == kp && t.tile_rows == tile_rows && t.n == n && t.tail_items.ready &&
+        t.tail_items.chunk == chunk && t.tail_items.align == align && t.tail_items.order == ctx->item_order)
+        return PLSA_OK;
+    cudaStream_t s = ctx->stream;
+    const int T = 256;
+    t.ready = false;
+    t.kp = kp;
+    t.tile_rows = tile_rows;
+    t.pitch_f = pc * 4;
+    t.n = n;
+    /* the most frequent columns: count, sort by count (descending, stable: ties by index) */
+    CK(t.col_count.ensure((size_t)m * 4));
+    CK(t.col_ids.ensure((size_t)m * 4));
+    CK(t.col_count_sorted.ensure((size_t)m * 4));
+    CK(t.col_sorted.ensure((size_t)m * 4));
+    CK(t.slot_of.ensure((size_t)m * 4));
+    CK(cudaMemsetAsync(t.col_count.p, 0, (size_t)m * 4, s));
+    CK(cudaMemsetAsync(t.slot_of.p, 0xff, (size_t)m * 4, s));
+    col_count_kernel<<<(unsigned)cdiv(nnz, T), T, 0, s>>>(c.ent.as<int2>(), nnz, t.col_count.as<int32_t>());
+    iota_kernel<<<(unsigned)cdiv(m, T), T, 0, s>>>(t.col_ids.as<int32_t>(), m);
+    size_t tmp_a = 0, tmp_b = 0, tmp_c = 0;
+    CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_a, t.col_count.as<int32_t>(),
+                                                 t.col_count_sorted.as<int32_t>(), t.col_ids.as<int32_t>(),
+                                                 t.col_sorted.as<int32_t>(), (int)m, 0, 32, s));
+    CK(t.head_len.ensure((size_t)(n + 1) * 4));
+    CK(t.tail_len.ensure((size_t)(n + 1) * 4));
+    CK(t.head_indptr.ensure((size_t)(n + 1) * 4));
+    CK(t.tail_indptr.ensure((size_t)(n + 1) * 4));
+    CK(t.order.ensure((size_t)n * 4));
+    CK(t.order_keys.ensure((size_t)n * 4));
+    CK(t.row_ids.ensure((size_t)n * 4));
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_b, t.head_len.as<int32_t>(), t.head_indptr.as<int32_t>(),
+                                     (int)(n + 1), s));
+    CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_c, t.head_len.as<int32_t>(),
+                                                 t.order_keys.as<int32_t>(), t.row_ids.as<int32_t>(),
+                                                 t.order.as<int32_t>(), (int)n, 0, 32, s));
+    CK(t.cub_tmp.ensure(std::max(tmp_a, std::max(tmp_b, tmp_c))));
+    size_t tmp = t.cub_tmp.cap;
+    CK(cub::DeviceRadixSort::SortPairsDescending(t.cub_tmp.p, tmp, t.col_count.as<int32_t>(),
+                                                 t.col_count_sorted.as<int32_t>(), t.col_ids.as<int32_t>(),
+                                                 t.col_sorted.as<int32_t>(), (int)m, 0, 32, s));
+    tile_slot_kernel<<<(unsigned)cdiv(tile_rows, T), T, 0, s>>>(t.col_sorted.as<int32_t>(), tile_rows,
+                                                              t.slot_of.as<int32_t>());
+    /* per row: padded head length and tail length, then the two row-pointer arrays */
+    CK(cudaMemsetAsync(t.head_len.as<int32_t>() + n, 0, 4, s));
+    CK(cudaMemsetAsync(t.tail_len.as<int32_t>() + n, 0, 4, s));
+    tile_count_kernel<<<(unsigned)cdiv(n * 32, T), T, 0, s>>>(c.indptr.as<int32_t>(), n, c.ent.as<int2>(),
+                                                            t.slot_of.as<int32_t>(), t.head_len.as<int32_t>(),
+                                                            t.tail_len.as<int32_t>());
+    tmp = t.cub_tmp.cap;
+    CK(cub::DeviceScan::ExclusiveSum(t.cub_tmp.p, tmp, t.head_len.as<int32_t>(), t.head_indptr.as<int32_t>(),
+                                     (int)(n + 1), s));
+    tmp = t.cub_tmp.cap;
+    CK(cub::DeviceScan::ExclusiveSum(t.cub_tmp.p, tmp, t.tail_len.as<int32_t>(), t.tail_indptr.as<int32_t>(),
+                                     (int)(n + 1), s));
+    /* rows by padded head length, longest first: the four items of a warp are equally long and
+     * every warp's share of the work is the same to within its last item */
+    iota_kernel<<<(unsigned)cdiv(n, T), T, 0, s>>>(t.row_ids.as<int32_t>(), n);
+    tmp = t.cub_tmp.cap;
+    CK(cub::DeviceRadixSort::SortPairsDescending(t.cub_tmp.p, tmp, t.head_len.as<int32_t>(),
+                                                 t.order_keys.as<int32_t>(), t.row_ids.as<int32_t>(),
+                                                 t.order.as<int32_t>(), (int)n, 0, 32, s));
+    ctx->launches += 6;
+    CK(cudaGetLastError());
+    try {
+        t.h_tail_indptr.resize((size_t)n + 1);
+    } catch (const std::bad_alloc &) {
+        return ctx->fail(PLSA_ENOMEM, "tiles: out of host memory");
+    }
+    int32_t head_total = 0;
+    CK(cudaMemcpyAsync(t.h_tail_indptr.data(), t.tail_indptr.p, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&head_total, t.head_indptr.as<int32_t>() + n, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    t.head_slots = head_total;
+    t.tail_nnz = t.h_tail_indptr[(size_t)n];
+    if (t.head_slots < 0 || t.tail_nnz < 0 || t.tail_nnz > nnz)
+        return ctx->fail(PLSA_ECUDA, "tiles: inconsistent head / tail split");
+    CK(t.head_ent.ensure((size_t)std::max<int64_t>(t.head_slots, 1) * sizeof(int2)));
+    CK(t.tail_ent.ensure(ent_bytes(t.tail_nnz)));
+    CK(cudaMemsetAsync(t.tail_ent.as<int2>() + t.tail_nnz, 0, ENT_PAD * sizeof(int2), s));
+    tile_place_kernel<<<(unsigned)cdiv(n * 32, T), T, 0, s>>>(
+        c.indptr.as<int32_t>(), n, c.ent.as<int2>(), t.slot_of.as<int32_t>(), t.head_indptr.as<int32_t>(),
+        t.tail_indptr.as<int32_t>(), t.head_ent.as<int2>(), t.tail_ent.as<int2>());
+    ctx->launches++;
+    CK(cudaGetLastError());
+    /* compact images of the tile rows (ping-pong like B), zero beyond the last row */
+    const size_t img_bytes = (size_t)std::max<int32_t>(tile_rows, TILE_MIN_ROWS) * t.pitch_f * 4;
+    for (int i = 0; i < 2; ++i) {
+        CK(t.img[i].ensure(img_bytes));
+        CK(cudaMemsetAsync(t.img[i].p, 0, img_bytes, s));
+    }
+    ctx->b_norm[0] = ctx->b_norm[1] = false; /* the images are empty */
+    CK(t.head_sum.ensure((size_t)n * kp * 4));
+    CK(t.scale_raw.ensure((size_t)kp * 4 * 2));
+    CK(t.ll_part.ensure((size_t)ctx->n_sms * 8));
+    CK(t.ll_head.ensure(8));
+    CK(t.ll_ticket.ensure(4));
+    CK(cudaMemsetAsync(t.ll_ticket.p, 0, 4, s));
+    int rc = build_items(ctx, t.h_tail_indptr, n, t.tail_items, chunk, align);
+    if (rc) return rc;
+    /* opt in to the tile's dynamic shared memory once per kernel and device */
+    for (int ll = 0; ll < 2; ++ll)
+        CK(cudaFuncSetAttribute(pick_tile_kernel(kp, ll != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)img_bytes));
+    t.ready = true;
+    return PLSA_OK;
+}
+
+/* B[which] times its pending column scale, in place, plus its tile image (tiled mode keeps
+ * P(w|z) normalised in memory: the flush-to-zero threshold needs gathered values <= 1) */
+static int normalise_b(plsa_ctx *ctx, int which, const float *scale, cudaStream_t stream)
+{
+    TileSet &t = ctx->tiles;
+    const int64_t m = ctx->cur().m;
+    const int64_t threads = m * (ctx->kp / 4);
+    normalise_rows_kernel<<<(unsigned)cdiv(threads, 256), 256, 0, stream>>>(
+        ctx->B[which].as<float>(), m, ctx->strideB, ctx->kp, scale, t.slot_of.as<int32_t>(),
+        t.img[which].as<float>(), t.pitch_f);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return PLSA_OK;
+}
+
 static void corpus_changed(plsa_ctx *ctx)
 {
+    ctx->tiles.ready = false;
+    ctx->tiles.tail_items.ready = false;
     ctx->t_ready = false;
     ctx->t_weighted_ready = false;
     ctx->doc_items.ready = false;
@@ -726,6 +926,12 @@ API int plsa_ctx_create(int device, plsa_ctx **out)
     if (cudaDeviceGetAttribute(&max_lin, cudaDevAttrMaxTexture1DLinearWidth, device) == cudaSuccess &&
         max_lin > 0)
         ctx->tex_max_texels = (size_t)max_lin;
+    cudaDeviceGetAttribute(&ctx->n_sms, cudaDevAttrMultiProcessorCount, device);
+    if (ctx->n_sms <= 0) ctx->n_sms = 148;
+    /* every context of the process, the one-shot entry points' included (A/B runs, tests) */
+    if (const char *e = getenv("ENSTOP_B200_TILED")) ctx->tiled_opt = std::max(-1, std::min(1, atoi(e)));
+    if (const char *e = getenv("ENSTOP_B200_TILE_KB"))
+        ctx->tile_bytes = (int64_t)std::max(1, std::min(220, atoi(e))) * 1024;
     *out = ctx;
     return PLSA_OK;
 }
@@ -741,6 +947,7 @@ API int plsa_ctx_destroy(plsa_ctx *ctx)
         c->indptr.release(); c->ent.release();
     }
     p2p_release(ctx);
+    ctx->tiles.release();
     for (DevBuf &b : ctx->scratch) b.release();
     for (DevBuf *b : {&ctx->t_ent, &ctx->t_entw, &ctx->up_cols, &ctx->up_vals, &ctx->flag,
                       &ctx->doc_items.items, &ctx->doc_items.split_rows, &ctx->doc_items.slot_begin,
@@ -1045,6 +1252,7 @@ API int plsa_set_factors(plsa_ctx *ctx, const float *p_z_given_d, const float *p
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->curA = ctx->curB = 0;
+    ctx->b_norm[0] = ctx->b_norm[1] = false;
     ctx->have_factors = true;
     return PLSA_OK;
 }
@@ -1125,13 +1333,16 @@ API int plsa_get_factors(plsa_ctx *ctx, float *p_z_given_d, float *p_w_given_z)
 
 /* ---- EM ------------------------------------------------------------------------------------------ */
 /* work items of the doc pass (and of the term pass for a full fit), sized for kp */
-static int ensure_items(plsa_ctx *ctx, bool refit, int kp)
+static int ensure_items(plsa_ctx *ctx, bool refit, int kp, bool want_doc = true)
 {
     const int64_t chunk = choose_chunk(ctx, kp);
     const int align = ctx->vec_entries ? pass_entry_block(kp) : 1;
     int rc;
-    const bool need_doc = !ctx->doc_items.ready || ctx->doc_items.chunk != chunk ||
-                          ctx->doc_items.align != align || ctx->doc_items.order != ctx->item_order;
+    /* tiled mode: the doc items of the whole corpus serve only the exact log-likelihood pass
+     * and are built when that pass first runs */
+    const bool need_doc = want_doc &&
+                          (!ctx->doc_items.ready || ctx->doc_items.chunk != chunk ||
+                           ctx->doc_items.align != align || ctx->doc_items.order != ctx->item_order);
     if (need_doc && !refit && !ctx->t_ready) {
         /* the doc items are host work (plus one small copy on the second stream): build them on
          * a helper thread while this one drives the term-major sort on the device */
@@ -1205,7 +1416,11 @@ API int plsa_prepare(plsa_ctx *ctx, int32_t refit, int32_t k)
     CHECK_CTX(ctx);
     if (ctx->cur().h_indptr.empty()) return ctx->fail(PLSA_EINVAL, "prepare: no corpus uploaded");
     if (k < 1 || k > PLSA_MAX_K) return ctx->fail(PLSA_EINVAL, "prepare: k out of range");
-    return ensure_items(ctx, refit != 0, (k + 3) / 4 * 4);
+    const int kp = (k + 3) / 4 * 4;
+    const bool tiled = tiled_wanted(ctx, kp);
+    int rc = ensure_items(ctx, refit != 0, kp, !tiled);
+    if (rc == PLSA_OK && tiled) rc = ensure_tiles(ctx, kp);
+    return rc;
 }
 
 API int plsa_log_likelihood(plsa_ctx *ctx, double *ll)
@@ -1217,9 +1432,10 @@ API int plsa_log_likelihood(plsa_ctx *ctx, double *ll)
 }
 
 /* split rows of one factor (which = 0: P(z|d), normalised; 1: P(w|z)^T) on `stream` */
-static int run_fixup(plsa_ctx *ctx, int which, float *own_new, cudaStream_t stream)
+static int run_fixup(plsa_ctx *ctx, int which, float *own_new, cudaStream_t stream,
+                     const ItemSet *doc_set = nullptr)
 {
-    const ItemSet &is = which ? ctx->term_items : ctx->doc_items;
+    const ItemSet &is = which ? ctx->term_items : (doc_set ? *doc_set : ctx->doc_items);
     if (is.n_split == 0) return PLSA_OK;
     ProfScope ps(ctx, PLSA_PROF_FIXUP, stream);
     FixArgs f{}, none{};
@@ -1251,14 +1467,28 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
         return ctx->fail(PLSA_EINVAL, "em: n_iter < 0 or n_iter_per_test < 1");
     Corpus &c = ctx->cur();
     int rc;
-    if ((rc = ensure_items(ctx, refit != 0, ctx->kp))) return rc;
+    const int kp = ctx->kp;
+    /* tiled doc pass (plsa_tile.cuh): head entries from a shared-memory tile, tail entries
+     * through the texture path; P(w|z) is then kept normalised in memory */
+    const bool tiled = tiled_wanted(ctx, kp);
+    if ((rc = ensure_items(ctx, refit != 0, kp, !tiled))) return rc;
+    if (tiled && (rc = ensure_tiles(ctx, kp))) return rc;
     if (!ctx->have_sw && (rc = plsa_set_sample_weight(ctx, nullptr))) return rc;
     if (!refit && use_sample_weights && (rc = ensure_weighted_vals(ctx))) return rc;
-    const int kp = ctx->kp;
+    const ItemSet &doc_set = tiled ? ctx->tiles.tail_items : ctx->doc_items;
     /* products at or below the threshold are dropped (plsa.py:98-102); subnormal products
      * are dropped as well so that a surviving posterior normaliser is never subnormal */
     e_step_thresh = std::max(e_step_thresh, 1.17549435e-38f);
-    CK(ctx->partialA.ensure((size_t)std::max(ctx->doc_items.n_slots, 1) * kp * 4));
+    CK(ctx->partialA.ensure((size_t)std::max(doc_set.n_slots, 1) * kp * 4));
+    if (tiled && !ctx->b_norm[ctx->curB]) {
+        /* fold the pending column scale into B and build its tile image; from here on the
+         * scale vectors are all ones */
+        if ((rc = normalise_b(ctx, ctx->curB, cur_scale(ctx), ctx->stream))) return rc;
+        if ((rc = fill(ctx, ctx->scale.as<float>(), 2 * kp, 1.f))) return rc;
+        ctx->b_norm[ctx->curB] = true;
+    }
+    /* the flush-to-zero scale of the tiled pass: S = FLT_MIN / thresh (>= thresh is kept) */
+    const float ftz_scale = (float)(1.17549435e-38 / (double)e_step_thresh);
     if (!refit) CK(ctx->partialB.ensure((size_t)std::max(ctx->term_items.n_slots, 1) * kp * 4));
 
     /* plsa.py:913 — the refit loop's early stop is guarded by LL > 0, which a
@@ -1271,9 +1501,9 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
      * not adopted — the returned model is exactly the reference's (plsa.py:630-638). */
     const bool fuse = want_ll && !refit && ctx->fuse_ll && e_step_thresh <= PLSA_FUSED_LL_MAX_THRESH;
     if (fuse) {
-        if (!ctx->mail) CK(cudaHostAlloc((void **)&ctx->mail, 16, cudaHostAllocDefault));
+        if (!ctx->mail) CK(cudaHostAlloc((void **)&ctx->mail, 32, cudaHostAllocDefault));
         CK(ctx->flag.ensure(4));
-        CK(ctx->ll_part.ensure((size_t)std::max<int64_t>(pass_grid(ctx->doc_items.n_items, kp), 1) * 8));
+        CK(ctx->ll_part.ensure((size_t)std::max<int64_t>(pass_grid(doc_set.n_items, kp), 1) * 8));
     }
     if (!refit) { /* per-CTA column sums of the term pass and its last-arrival tickets */
         const int64_t tgrid = pass_grid(ctx->term_items.n_items, kp);
@@ -1335,6 +1565,11 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                      ctx->p2p.n_attached == n_ranks - 1 && n_ranks <= SHARD_MAX_RANKS &&
                      ctx->p2p.part_bytes == (size_t)std::max<int64_t>(c.m, 1) * ctx->strideB * 4;
     bool p2p_used = false;
+    if (p2p && n_iter > 0) {
+        /* the ranks reach this point unsynchronised (corpus preparation, lazy module loads):
+         * a one-word all-reduce on the exchange stream lines them up before the first peer wait */
+        if ((rc = shard_allreduce(ctx, ctx->ll2.p, 1, true, s2))) return rc;
+    }
     for (int32_t i = 0; i < n_iter; ++i) {
         const int nA = ctx->curA ^ 1, nB = ctx->curB ^ 1;
         const bool fused_now = fuse && (i == 0 || (i - 1) % n_iter_per_test == 0);
@@ -1344,10 +1579,39 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
         }
         {   /* E-step + M-step of P(z|d): plsa.py:91-105, :189-194 (P(z|d) part), :199-202 */
             ProfScope ps(ctx, PLSA_PROF_DOC_PASS);
+            if (tiled) { /* head entries: shared-memory tile, TMA-staged, lane per entry */
+                TileSet &t = ctx->tiles;
+                TileArgs h{};
+                h.order = t.order.as<int32_t>();
+                h.indptr = t.head_indptr.as<int32_t>();
+                h.ent = t.head_ent.as<int2>();
+                h.own_old = ctx->A[ctx->curA].as<float>();
+                h.tile_src = t.img[ctx->curB].as<float>();
+                h.partial_out = t.head_sum.as<float>();
+                h.n_rows = c.n;
+                h.tile_rows = t.tile_rows;
+                h.stride_own = ctx->strideA;
+                h.kp = kp;
+                h.ftz_scale = ftz_scale;
+                h.inv_ftz_scale = 1.f / ftz_scale;
+                if (fused_now) {
+                    h.row_weight = ctx->sw.as<float>();
+                    h.cta_partial = t.ll_part.as<double>();
+                    h.ticket = t.ll_ticket.as<unsigned int>();
+                    h.ll_out = t.ll_head.as<double>();
+                    h.flag = ctx->flag.as<int>();
+                    CK(cudaMemsetAsync(ctx->flag.p, 0, 4, ctx->stream));
+                }
+                const size_t smem = (size_t)std::max<int32_t>(t.tile_rows, TILE_MIN_ROWS) * t.pitch_f * 4;
+                pick_tile_kernel(kp, fused_now)<<<ctx->n_sms, TILE_THREADS, smem, ctx->stream>>>(h);
+                ctx->launches++;
+                CK(cudaGetLastError());
+            }
             PassArgs a{};
-            a.items = ctx->doc_items.items.as<Item>();
-            a.n_items = ctx->doc_items.n_items;
-            a.ent = c.ent.as<int2>();
+            a.items = doc_set.items.as<Item>();
+            a.n_items = doc_set.n_items;
+            a.ent = tiled ? ctx->tiles.tail_ent.as<int2>() : c.ent.as<int2>();
+            a.add_partial = tiled ? ctx->tiles.head_sum.as<float>() : nullptr;
             a.own_old = ctx->A[ctx->curA].as<float>();
             a.gat_old = ctx->B[ctx->curB].as<float>();
             a.own_scale = cur_scale(ctx);
@@ -1364,18 +1628,21 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                 a.ticket = ctx->tickets.as<unsigned int>();
                 a.ll_out = ctx->ll_out.as<double>();
                 a.flag = ctx->flag.as<int>();
-                CK(cudaMemsetAsync(ctx->flag.p, 0, 4, ctx->stream));
+                if (!tiled) CK(cudaMemsetAsync(ctx->flag.p, 0, 4, ctx->stream));
             }
-            if ((rc = launch_pass(ctx, fused_now ? MODE_DOC_LL : MODE_DOC, a, ctx->doc_items.align > 1)))
+            if ((rc = launch_pass(ctx, fused_now ? MODE_DOC_LL : MODE_DOC, a, doc_set.align > 1)))
                 return rc;
             if (fused_now && !sharded) {
                 CK(cudaMemcpyAsync(&ctx->mail[0], ctx->ll_out.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
                 CK(cudaMemcpyAsync(&ctx->mail[1], ctx->flag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+                if (tiled)
+                    CK(cudaMemcpyAsync(&ctx->mail[2], ctx->tiles.ll_head.p, 8, cudaMemcpyDeviceToHost,
+                                       ctx->stream));
                 CK(cudaEventRecord(ctx->ev_ll, ctx->stream));
             }
             if (fused_now && sharded) CK(cudaEventRecord(ctx->ev_a, s1)); /* doc pass done */
         }
-        if ((rc = run_fixup(ctx, 0, ctx->A[nA].as<float>(), s1))) return rc;
+        if ((rc = run_fixup(ctx, 0, ctx->A[nA].as<float>(), s1, &doc_set))) return rc;
         if (!refit) {
             {   /* E-step + M-step of P(w|z): plsa.py:91-105, :189-193 (P(w|z) part) */
                 ProfScope ps(ctx, PLSA_PROF_WORD_PASS, s2);
@@ -1396,7 +1663,8 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                 /* plsa.py:196-198: per-topic normaliser of the new P(w|z), applied lazily */
                 a.cta_partial = ctx->colpart.as<double>();
                 a.ticket = ctx->tickets.as<unsigned int>() + 1; /* [0] is the log-likelihood's */
-                a.scale_out = reinterpret_cast<float *>(ctx->scale.p) + (size_t)nB * kp;
+                a.scale_out = tiled ? ctx->tiles.scale_raw.as<float>() + (size_t)nB * kp
+                                    : reinterpret_cast<float *>(ctx->scale.p) + (size_t)nB * kp;
                 a.colnorm_out = ctx->colnorm.as<double>();
                 a.stride_own = ctx->strideB;
                 a.stride_gat = ctx->strideA;
@@ -1410,6 +1678,11 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                                                                 ((ctx->p2p.seq + 1) & 1u) * ctx->p2p.part_bytes)
                                     : ctx->B[nB].as<float>(), s2)))
                 return rc;
+            if (tiled) { /* plsa.py:196-198 applied now, not lazily: B[nB] *= scale, + tile image */
+                ProfScope ps(ctx, PLSA_PROF_NORMALIZE, s2);
+                if ((rc = normalise_b(ctx, nB, ctx->tiles.scale_raw.as<float>() + (size_t)nB * kp, s2)))
+                    return rc;
+            }
             if (p2p && c.m > 0) {
                 ProfScope ps(ctx, PLSA_PROF_NORMALIZE, s2);
                 ctx->p2p.seq += 1;
@@ -1433,6 +1706,7 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                 ra.n_ranks = n_ranks;
                 ra.rank = me;
                 ra.seq = ctx->p2p.seq;
+                ra.timeout_clocks = (long long)ctx->p2p.timeout_ms * 2000000LL; /* ~2 GHz SM clock */
                 shard_reduce_kernel<<<colsum_grid, 256, 0, s2>>>(ra);
                 colsum_final_kernel<<<1, 256, 0, s2>>>(
                     ctx->colpart2.as<double>(), colsum_grid, kp,
@@ -1476,6 +1750,7 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
             memcpy(&v, &ctx->mail[0], 8);
             if (sharded) bad = ctx->mail[1] != 0.0; /* any shard's flag */
             else memcpy(&bad, &ctx->mail[1], 4);
+            if (tiled) v += ctx->mail[2]; /* tail entries + head entries */
             if (bad && (rc = run_loglik(ctx, &v))) return rc; /* exact pass on the same factors */
             if (i == 0) { /* plsa.py:591, the value before the loop */
                 prev = v;
@@ -1486,7 +1761,10 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                 break;
             }
         }
-        if (!refit) ctx->curB = nB;
+        if (!refit) {
+            ctx->curB = nB;
+            ctx->b_norm[nB] = tiled;
+        }
         ctx->curA = nA;
         done = i + 1;
         if (want_ll && !fuse && i % n_iter_per_test == 0) { /* plsa.py:630-638 / :909-918 */
@@ -1584,8 +1862,24 @@ API int plsa_set_option(plsa_ctx *ctx, const char *name, int64_t value)
         ctx->p2p.enabled = value != 0;
         return PLSA_OK;
     }
+    if (!strcmp(name, "p2p_timeout_ms")) { /* sharded fit: how long a rank waits for a peer's partial sums */
+        if (value < 1 || value > 3600000) return ctx->fail(PLSA_EINVAL, "p2p_timeout_ms: 1..3600000");
+        ctx->p2p.timeout_ms = value;
+        return PLSA_OK;
+    }
     if (!strcmp(name, "vec_entries")) {
         ctx->vec_entries = value != 0; /* item sets are rebuilt on the next prepare / em */
+        return PLSA_OK;
+    }
+    if (!strcmp(name, "tiled")) { /* -1 auto (by corpus size), 0 never, 1 wherever possible */
+        if (value < -1 || value > 1) return ctx->fail(PLSA_EINVAL, "tiled: -1, 0 or 1");
+        ctx->tiled_opt = (int)value;
+        return PLSA_OK;
+    }
+    if (!strcmp(name, "tile_kb")) { /* shared memory of the tile, per CTA */
+        if (value < 1 || value > 220) return ctx->fail(PLSA_EINVAL, "tile_kb: 1..220");
+        ctx->tile_bytes = value * 1024;
+        ctx->tiles.ready = false;
         return PLSA_OK;
     }
     if (!strcmp(name, "item_order")) { /* 0 row, 1 window, 2 band: see plan_items */
@@ -1625,7 +1919,7 @@ API int plsa_plan_items(const int32_t *indptr, int64_t rows, int64_t chunk, int3
         if (row) row[i] = it.row;
         if (len) len[i] = it.len;
         if (slot) slot[i] = it.slot;
-        if (skip) skip[i] = it.skip;
+        if (skip) skip[i] = it.skip & 0xffff;
     }
     return PLSA_OK;
 }

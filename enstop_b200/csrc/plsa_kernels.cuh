@@ -46,8 +46,10 @@ struct Item {          /* one unit of group work: a row, or a chunk of a long ro
     int32_t slot;      /* < 0: whole row, result goes to own_new; else partial-sum slot */
     int32_t skip;      /* aligned items: `start` is rounded down to a multiple of the entry
                           block, the first `skip` entries (< block) belong to the row before
-                          and count as value 0; `len` includes them                        */
+                          and count as value 0; `len` includes them.  ITEM_FIRST is or-ed in
+                          for the first chunk of a split row                                */
 };
+constexpr int32_t ITEM_FIRST = 0x10000;
 
 enum { MODE_DOC = 0, MODE_TERM = 1, MODE_LOGLIK = 2,
        MODE_DOC_LL = 3 /* doc pass that also returns the log-likelihood of the factors it reads */ };
@@ -77,6 +79,8 @@ struct PassArgs {
     float *scale_out;        /* MODE_TERM: [kp] 1 / column sum of the new P(w|z)         */
     double *colnorm_out;     /* MODE_TERM: [kp] the column sums                          */
     cudaTextureObject_t gat_tex; /* gat_old as a linear float4 texture (TEX kernels)     */
+    const float *add_partial;    /* tiled doc pass: [rows, kp] sums of the row's head entries
+                                    (plsa_tile.cuh), added to the row's first item           */
     int32_t stride_own, stride_gat, kp;
     float thresh;
 };
@@ -581,7 +585,7 @@ __global__ void __launch_bounds__(PLSA_PASS_THREADS,
     load_entries<U, VEC>(ent, e);
     if constexpr (VEC && U > 1) { /* entries before the row's first one: value 0 */
 #pragma unroll
-        for (int u = 0; u < U - 1; ++u) e[u].y = (u < it.skip) ? 0 : e[u].y;
+        for (int u = 0; u < U - 1; ++u) e[u].y = (u < (it.skip & 0xffff)) ? 0 : e[u].y;
     }
     for (int base = 0; base < maxlen; base += U) {
         int2 en[U];
@@ -602,6 +606,19 @@ __global__ void __launch_bounds__(PLSA_PASS_THREADS,
         finish_loglik(a, ll_acc);
     } else {
         float inv = 1.f;
+        if constexpr (MODE == MODE_DOC || MODE == MODE_DOC_LL) {
+            /* tiled doc pass: the row's head entries were summed by tile_pass_kernel */
+            if (a.add_partial != nullptr && has && lane_on && (it.slot < 0 || (it.skip & ITEM_FIRST))) {
+#pragma unroll
+                for (int q = 0; q < KV; ++q) {
+                    const int c = 4 * (j + G * q);
+                    if (c < a.kp) {
+                        const float4 h = ldg_f4(a.add_partial + (int64_t)it.row * a.kp + c);
+                        acc[q].x += h.x; acc[q].y += h.y; acc[q].z += h.z; acc[q].w += h.w;
+                    }
+                }
+            }
+        }
         if constexpr (MODE == MODE_DOC || MODE == MODE_DOC_LL) { /* plsa.py:199-202 */
             float part = 0.f;
 #pragma unroll
@@ -795,7 +812,9 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const double *__restr
  * no staging copy, no second read for the normaliser, 4*kp bytes per row and peer on the
  * wire.  Buffer reuse: a rank rewrites exchange buffer `parity` two iterations later, after
  * the barrier of the iteration in between, which no rank passes before all ranks have left
- * this kernel.  The wait is bounded (about two seconds); a rank that gives up raises *err. */
+ * this kernel.  The wait is bounded (option "p2p_timeout_ms", 30 s by default; the ranks enter the
+ * loop together behind a one-word all-reduce); a rank that gives up raises *err, and every later
+ * launch of the fit returns at once. */
 constexpr int SHARD_MAX_RANKS = 16;
 struct ShardReduceArgs {
     const float *part[SHARD_MAX_RANKS];      /* every rank's partial, [rows, stride]; [rank] is local */
@@ -807,6 +826,7 @@ struct ShardReduceArgs {
     int64_t rows;
     int32_t stride, kp, n_ranks, rank;
     unsigned int seq;
+    long long timeout_clocks;                /* bound of the wait for the peers' signals */
 };
 
 __device__ __forceinline__ float4 ld_peer_f4(const float *p)
@@ -821,6 +841,8 @@ __global__ void __launch_bounds__(256) shard_reduce_kernel(const ShardReduceArgs
 {
     __shared__ double sm[256][4];
     __shared__ int give_up;
+    /* a wait that timed out earlier in this fit: do not wait (or add stale sums) again */
+    if (*reinterpret_cast<volatile int *>(a.err)) return;
     if (threadIdx.x == 0) give_up = 0;
     /* (1) + (2): every CTA signals nothing but waits itself; CTA 0 does the signalling, so a
      * peer sees `seq` exactly once per iteration */
@@ -837,7 +859,7 @@ __global__ void __launch_bounds__(256) shard_reduce_kernel(const ShardReduceArgs
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v)
                          : "l"(const_cast<unsigned int *>(a.my_sig) + threadIdx.x) : "memory");
             if ((int)(v - a.seq) >= 0) break;
-            if (clock64() - t0 > 4000000000LL) {
+            if (clock64() - t0 > a.timeout_clocks) {
                 give_up = 1;
                 break;
             }

@@ -1,0 +1,362 @@
+/*
+ * plsa_tile.cuh — the "tiled" row pass: the hot rows of the gathered factor live in shared
+ * memory, staged by the TMA unit, and are consumed LANE-PER-ENTRY.
+ *
+ * Why (profiles/r2_microbench_stage.txt, profiles/r2_kernel_experiments.md): a k-wide factor
+ * row per stored entry costs 1.75 cycles/entry/SM through the texture path and every one of
+ * them crosses the L2->SM fabric; with a Zipf vocabulary two thirds of the doc pass's gathers
+ * hit the ~2.5 k most frequent terms, whose rows (80 B each at k = 20) fit one CTA's shared
+ * memory.  Those entries are split off into their own CSR ("head"), whose column index is the
+ * tile slot; the rest ("tail") stays with the group-per-row texture kernel of plsa_kernels.cuh.
+ *
+ * Head kernel (tile_pass_kernel): one persistent CTA per SM copies the tile with cp.async.bulk
+ * (TMA, mbarrier complete_tx) and then walks work items OCTET-PER-ITEM: 8 lanes share one row
+ * of X, each lane owns one stored entry per step, reads the whole factor row of its entry with
+ * KC LDS.128 and keeps the posterior normaliser in-lane — no shuffle per entry; the k
+ * accumulators are folded over the octet once per item.  An LDS.128 is served in quarter-warp
+ * phases of 8 lanes x 16 B; rows sit at an odd pitch (in 16-byte chunks), so the 8 lanes of a
+ * phase are conflict free exactly when their slots are distinct mod 8.  tile_place_kernel
+ * therefore lays every head row out in steps of 8 slots, position p of a step holding an entry
+ * whose slot is = p (mod 8) or a zero-valued padding entry (slot p): conflict free by
+ * construction (measured: an octet with a two-way conflict costs 3x a conflict-free one).
+ *
+ * E-step threshold (enstop/plsa.py:98-102) without compare/select: the owned row is multiplied
+ * by S = FLT_MIN / thresh, so a product at or below the threshold is subnormal and the
+ * flush-to-zero multiply drops it; posterior and M-step sums do not see the common factor.
+ * This needs gathered values <= 1, which is why the tiled mode keeps P(w|z) normalised in
+ * memory (normalise_rows_kernel) instead of folding the column scale into the owned row.
+ */
+#pragma once
+#include "plsa_kernels.cuh"
+
+namespace plsa {
+
+constexpr int TILE_THREADS = 512;                 /* 16 warps, one CTA per SM */
+constexpr int TILE_MIN_ROWS = 8;                  /* padding entries address slots 0..7 */
+
+__host__ __device__ constexpr int tile_pitch_chunks(int kc) { return kc | 1; } /* odd */
+
+struct TileArgs {
+    const int32_t *order;     /* [n_rows] rows by padded head length, longest first        */
+    const int32_t *indptr;    /* [n_rows + 1] head CSR; every row length is a multiple of 8 */
+    const int2 *ent;          /* head entries {tile slot, value bits}                      */
+    const float *own_old;     /* [rows, stride_own]                                        */
+    const float *tile_src;    /* [max(tile_rows, 8), pitch] compact image of the hot rows  */
+    float *partial_out;       /* [rows, kp] raw M-step sums of the head entries            */
+    const float *row_weight;  /* LL: sample_weight[d]                                      */
+    double *cta_partial;      /* LL: [grid]                                                */
+    unsigned int *ticket;     /* LL: zeroed counter                                        */
+    double *ll_out;           /* LL: log-likelihood of the head entries                    */
+    int *flag;                /* LL: raised when a normaliser is too small to trust        */
+    int64_t n_rows;
+    int32_t tile_rows, stride_own, kp;
+    float ftz_scale;          /* S = FLT_MIN / thresh                                      */
+    float inv_ftz_scale;      /* 1 / S                                                     */
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TILE_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TILE_DONE;\n"
+        "bra TILE_WAIT;\n"
+        "TILE_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+/* TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS UBLKCP) */
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+/* Sum K values over the 8 lanes of an octet by halving: at every level a lane keeps one half of
+ * its values and receives its partner's copy of that half.  After the three levels lane li
+ * holds the octet totals of `n` consecutive topics starting at `first` (n <= ceil(K/8)). */
+template <int N, int K>
+__device__ __forceinline__ void octet_fold_level(float (&a)[K], int li, int bit, int &first, int &n)
+{
+    constexpr int half = (N + 1) / 2;
+    const bool up = (li & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+        const float lo = a[i];
+        const float hi = (i + half < N) ? a[i + half < K ? i + half : 0] : 0.f;
+        const float send = up ? lo : hi;
+        const float keep = up ? hi : lo;
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+    first += up ? half : 0;
+    n = up ? max(0, n - half) : min(n, half);
+}
+
+template <int K>
+__device__ __forceinline__ int octet_fold(float (&a)[K], int li, int &first)
+{
+    constexpr int N0 = K, N1 = (N0 + 1) / 2, N2 = (N1 + 1) / 2;
+    int n = K;
+    first = 0;
+    octet_fold_level<N0, K>(a, li, 4, first, n);
+    octet_fold_level<N1, K>(a, li, 2, first, n);
+    octet_fold_level<N2, K>(a, li, 1, first, n);
+    return n;
+}
+
+template <int KC, bool LL>
+__global__ void __launch_bounds__(TILE_THREADS, 1) tile_pass_kernel(const TileArgs a)
+{
+    constexpr int PC = tile_pitch_chunks(KC);
+    constexpr int K = 4 * KC;
+    constexpr int NW = TILE_THREADS / 32;
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ double ll_sm[NW];
+    __shared__ bool ll_last;
+    const float4 *tile = reinterpret_cast<const float4 *>(tile_smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, li = lane & 7, oct = lane >> 3;
+
+    /* stage the tile: one elected thread arms the barrier with the byte count and issues the
+     * TMA bulk copies; everybody waits on the barrier's phase */
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)max(a.tile_rows, TILE_MIN_ROWS) * PC * 16u;
+        mbar_expect_tx(&bar, bytes);
+        for (uint32_t off = 0; off < bytes; off += 32768u)
+            bulk_g2s(tile_smem + off, reinterpret_cast<const char *>(a.tile_src) + off,
+                     min(bytes - off, 32768u), &bar);
+    }
+    mbar_wait(&bar, 0);
+
+    const int64_t n_batches = (a.n_rows + 3) >> 2;
+    const int64_t gw = (int64_t)blockIdx.x * NW + warp, GW = (int64_t)gridDim.x * NW;
+    double ll_acc = 0.0;
+    float min_norm = 3.0e38f;
+    for (int64_t b = gw; b < n_batches; b += GW) {
+        const int64_t i = b * 4 + oct;
+        const bool has = i < a.n_rows;
+        int row = 0, start = 0, len = 0;
+        if (has) {
+            row = a.order[i];
+            start = a.indptr[row];
+            len = a.indptr[row + 1] - start;
+        }
+        int maxlen = len;
+        maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, 8));
+        maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, 16));
+        if (maxlen == 0) { /* rows without head entries still own a (zero) partial */
+            if (has)
+                for (int z = li; z < a.kp; z += 8) a.partial_out[(int64_t)row * a.kp + z] = 0.f;
+            continue;
+        }
+        f32x2 own2[2 * KC], acc2[2 * KC];
+#pragma unroll
+        for (int c = 0; c < KC; ++c) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has) o = ldg_f4(a.own_old + (int64_t)row * a.stride_own + 4 * c);
+            own2[2 * c] = pk2(o.x * a.ftz_scale, o.y * a.ftz_scale);
+            own2[2 * c + 1] = pk2(o.z * a.ftz_scale, o.w * a.ftz_scale);
+            acc2[2 * c] = 0ull;
+            acc2[2 * c + 1] = 0ull;
+        }
+        float ll_row = 0.f;
+        const int2 *ent = a.ent + start + li;
+        int2 e = (len > 0) ? __ldg(ent) : make_int2(li, 0);
+        for (int t = 0; t < maxlen; t += 8) {
+            /* one step ahead; past the item's end: own residue class, value 0 */
+            const int2 en = (t + 8 < len) ? __ldg(ent + t + 8) : make_int2(li, 0);
+            float4 g[KC];
+#pragma unroll
+            for (int c = 0; c < KC; ++c) g[c] = tile[e.x * PC + c];
+            const float x = __int_as_float(e.y);
+            f32x2 v[2 * KC];
+#pragma unroll
+            for (int c = 0; c < KC; ++c) {
+                v[2 * c] = mul2_ftz(pk2(g[c].x, g[c].y), own2[2 * c]);
+                v[2 * c + 1] = mul2_ftz(pk2(g[c].z, g[c].w), own2[2 * c + 1]);
+            }
+            f32x2 s = add2(v[0], v[1]);
+#pragma unroll
+            for (int c = 1; c < KC; ++c) s = add2(s, add2(v[2 * c], v[2 * c + 1]));
+            float s_lo, s_hi;
+            upk2(s, s_lo, s_hi);
+            const float norm = s_lo + s_hi;
+            if constexpr (LL) {
+                /* plsa.py:383-384 on the unscaled sum; x == 0 marks padding */
+                const float lg = log2_ftz(norm * a.inv_ftz_scale) * 0.69314718f;
+                ll_row += (x != 0.f) ? x * lg : 0.f;
+                min_norm = fminf(min_norm, (x != 0.f) ? norm : 3.0e38f);
+            }
+            const float cf = fminf(x * rcp_fast(norm), 3.0e38f); /* see pass_block */
+            const f32x2 c2 = pk2(cf, cf);
+#pragma unroll
+            for (int q = 0; q < 2 * KC; ++q) acc2[q] = fma2(c2, v[q], acc2[q]);
+            e = en;
+        }
+        if constexpr (LL) {
+            if (has) ll_acc += (double)ll_row * (double)a.row_weight[row];
+        }
+        float acc[K];
+#pragma unroll
+        for (int q = 0; q < 2 * KC; ++q) upk2(acc2[q], acc[2 * q], acc[2 * q + 1]);
+        int first;
+        const int nv = octet_fold<K>(acc, li, first);
+        if (has) {
+            float *dst = a.partial_out + (int64_t)row * a.kp + first;
+#pragma unroll
+            for (int q = 0; q < (K + 7) / 8; ++q)
+                if (q < nv && first + q < a.kp) dst[q] = acc[q];
+        }
+    }
+    if constexpr (LL) {
+        if (min_norm < PLSA_FUSED_LL_MIN_NORM * a.ftz_scale) *a.flag = 1;
+        /* deterministic: lanes (butterfly), warps in order, CTAs in index order by the last
+         * CTA to arrive */
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) ll_acc += __shfl_xor_sync(0xffffffffu, ll_acc, off);
+        if (lane == 0) ll_sm[warp] = ll_acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < NW; ++w) t += ll_sm[w];
+            a.cta_partial[blockIdx.x] = t;
+            __threadfence();
+            ll_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (ll_last && threadIdx.x == 0) {
+            __threadfence();
+            double t = 0.0;
+            for (unsigned c = 0; c < gridDim.x; ++c) t += a.cta_partial[c];
+            *a.ll_out = t;
+            *a.ticket = 0u;
+        }
+    }
+}
+
+/* ---- corpus preparation for the tiled pass -------------------------------------------------- */
+/* how often every column occurs (the head of the vocabulary = the most frequent columns) */
+__global__ void col_count_kernel(const int2 *__restrict__ ent, int64_t nnz, int32_t *__restrict__ count)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz) atomicAdd(count + ent[i].x, 1);
+}
+
+/* slot_of[col] = s for the tile_rows most frequent columns (sorted_cols[0..tile_rows)) */
+__global__ void tile_slot_kernel(const int32_t *__restrict__ sorted_cols, int32_t tile_rows,
+                                 int32_t *__restrict__ slot_of)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < tile_rows) slot_of[sorted_cols[s]] = s;
+}
+
+/* per row: padded length of its head part (8 x the largest residue class) and its tail length;
+ * one warp per row */
+__global__ void tile_count_kernel(const int32_t *__restrict__ indptr, int64_t n_rows,
+                                  const int2 *__restrict__ ent, const int32_t *__restrict__ slot_of,
+                                  int32_t *__restrict__ head_len, int32_t *__restrict__ tail_len)
+{
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    const int32_t p0 = indptr[r], p1 = indptr[r + 1];
+    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int head = 0;
+    for (int32_t p = p0; p < p1; p += 32) {
+        const bool ok = p + lane < p1;
+        const int s = ok ? slot_of[ent[p + lane].x] : -1;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) cnt[q] += __popc(__ballot_sync(0xffffffffu, s >= 0 && (s & 7) == q));
+        head += __popc(__ballot_sync(0xffffffffu, s >= 0));
+    }
+    int mx = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) mx = max(mx, cnt[q]);
+    if (lane == 0) {
+        head_len[r] = 8 * mx;
+        tail_len[r] = (p1 - p0) - head;
+    }
+}
+
+/* write the head rows (steps of 8 slots, position p of a step = an entry with slot = p mod 8 or
+ * padding {p, 0}) and the tail rows (original order); one warp per row */
+__global__ void tile_place_kernel(const int32_t *__restrict__ indptr, int64_t n_rows,
+                                  const int2 *__restrict__ ent, const int32_t *__restrict__ slot_of,
+                                  const int32_t *__restrict__ head_indptr,
+                                  const int32_t *__restrict__ tail_indptr, int2 *__restrict__ head_ent,
+                                  int2 *__restrict__ tail_ent)
+{
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    const int32_t p0 = indptr[r], p1 = indptr[r + 1];
+    const int32_t h0 = head_indptr[r], h1 = head_indptr[r + 1], t0 = tail_indptr[r];
+    for (int32_t h = h0 + lane; h < h1; h += 32) head_ent[h] = make_int2((h - h0) & 7, 0);
+    __syncwarp();
+    int base[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int tbase = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int32_t p = p0; p < p1; p += 32) {
+        const bool ok = p + lane < p1;
+        int2 e = make_int2(0, 0);
+        int s = -1;
+        if (ok) {
+            e = ent[p + lane];
+            s = slot_of[e.x];
+        }
+        int rank = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const unsigned m = __ballot_sync(0xffffffffu, s >= 0 && (s & 7) == q);
+            if (s >= 0 && (s & 7) == q) rank = base[q] + __popc(m & lt);
+            base[q] += __popc(m);
+        }
+        const unsigned mt = __ballot_sync(0xffffffffu, ok && s < 0);
+        if (ok) {
+            if (s >= 0) head_ent[h0 + rank * 8 + (s & 7)] = make_int2(s, e.y);
+            else tail_ent[t0 + tbase + __popc(mt & lt)] = e;
+        }
+        tbase += __popc(mt);
+    }
+}
+
+/* P(w|z)^T rows times the per-topic scale, in place (plsa.py:196-198), and the compact image
+ * of the tile rows for the TMA copy; kp/4 threads per row */
+__global__ void normalise_rows_kernel(float *__restrict__ mat, int64_t rows, int stride, int kp,
+                                      const float *__restrict__ scale,
+                                      const int32_t *__restrict__ slot_of, float *__restrict__ tile_img,
+                                      int pitch_f)
+{
+    const int nv = kp >> 2;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * nv) return;
+    const int64_t r = i / nv;
+    const int c = (int)(i - r * nv);
+    float4 *p = reinterpret_cast<float4 *>(mat + r * stride) + c;
+    float4 v = *p;
+    if (scale) {
+        const float4 s = *reinterpret_cast<const float4 *>(scale + 4 * c);
+        v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
+        *p = v;
+    }
+    const int sl = slot_of[r];
+    if (sl >= 0) reinterpret_cast<float4 *>(tile_img + (int64_t)sl * pitch_f)[c] = v;
+}
+
+} // namespace plsa

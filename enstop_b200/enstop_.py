@@ -131,6 +131,58 @@ def resolve_devices(devices=None, n_jobs=None):
     return devices
 
 
+def fit_members_on_device(X, k, device, members, seeds, **kwargs):
+    """Fit the ensemble members ``members`` (indices into ``seeds``) on one GPU and leave their
+    P(w|z) stashed on it.  Two contexts ("lanes") per device, each with its own host thread and
+    stream: while one lane's member is in its EM loop the other draws its bootstrap and seeded
+    start on the host and rebuilds its device structures, so the GPU does not idle between
+    members.  Returns (context holding the device's stash, members in stash order, every
+    context used); the caller gathers, then hands the contexts to ``release_member_contexts``.
+    This is the per-GPU unit of enstop_.py:209-217 — one call per device in a one-process run
+    (``ensemble_of_topics``), one call per rank in a one-process-per-GPU run (bench.py)."""
+    members = list(members)
+    lanes = [members[0::2], members[1::2]] if len(members) > 1 else [members]
+    contexts, errors = [None] * len(lanes), []
+
+    def worker(lane):
+        try:
+            ctx = _lib.acquire_context(device)   # pooled: creating and destroying a context
+            contexts[lane] = ctx                 # (pinned staging, ~20 device buffers) costs more
+            ctx.upload_csr(X)                    # than several members
+            for slot, r in enumerate(lanes[lane]):
+                kw = dict(kwargs)
+                kw["random_state"] = seeds[r]
+                kw["context"] = ctx
+                kw["download"] = False           # the topics stay on the device until the gather
+                plsa_topics(X, k, **kw)
+                ctx.stash_topics(slot, len(lanes[lane]))
+        except Exception as exc:  # surfaced after join
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(lane,)) for lane in range(len(lanes))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    used = [c for c in contexts if c is not None]
+    if errors:
+        for c in used:
+            c.close()
+        raise errors[0]
+    if len(lanes) > 1:      # one stash per device: lane 0's members, then lane 1's
+        _lib.stash_append(contexts[0], contexts[1], len(lanes[0]), len(lanes[1]))
+    return contexts[0], [r for lane in lanes for r in lane], used
+
+
+def release_member_contexts(contexts, failed=False):
+    for ctx in contexts:
+        if failed:
+            ctx.close()
+        else:
+            ctx.bootstrap(None)
+            _lib.release_context(ctx)
+
+
 def ensemble_of_topics(X, k, model="plsa", n_jobs=4, n_runs=16, parallelism="threads",
                        devices=None, return_seeds=False, **kwargs):
     """Topics of ``n_runs`` bootstrapped pLSA fits stacked as [n_runs * k, n_words]
@@ -147,56 +199,33 @@ def ensemble_of_topics(X, k, model="plsa", n_jobs=4, n_runs=16, parallelism="thr
         devices = devices[:1]
     seeds = member_seeds(kwargs.get("random_state", None), n_runs)
     assign = dict(zip(devices, shard_members(n_runs, len(devices))))
-    # Two contexts ("lanes") per device, each with its own host thread and stream: while one
-    # lane's member is in its EM loop the other draws its bootstrap and seeded start on the
-    # host and rebuilds its term-major copy, so the GPU does not idle between members.
-    lanes = {d: [assign[d][0::2], assign[d][1::2]] if len(assign[d]) > 1 else [assign[d]]
-             for d in devices}
-    contexts, errors = {}, []
+    used = [d for d in devices if assign[d]]
+    results, errors = {}, []
 
-    def worker(dev, lane):
+    def worker(dev):
         try:
-            ctx = _lib.acquire_context(dev)   # pooled: creating and destroying a context
-            contexts[(dev, lane)] = ctx       # (pinned staging, ~20 device buffers) costs more
-            ctx.upload_csr(X)                 # than several members
-            members = lanes[dev][lane]
-            for slot, r in enumerate(members):
-                kw = dict(kwargs)
-                kw["random_state"] = seeds[r]
-                kw["context"] = ctx
-                kw["download"] = False        # the topics stay on the device until the gather
-                plsa_topics(X, k, **kw)
-                ctx.stash_topics(slot, len(members))
+            results[dev] = fit_members_on_device(X, k, dev, assign[dev], seeds, **kwargs)
         except Exception as exc:  # surfaced after join
             errors.append(exc)
 
-    used = [d for d in devices if assign[d]]
-    threads = [threading.Thread(target=worker, args=(d, lane))
-               for d in used for lane in range(len(lanes[d]))]
+    threads = [threading.Thread(target=worker, args=(d,)) for d in used]
     if len(used) > 1:   # NCCL communicators of the final gather, created meanwhile
         threads.append(threading.Thread(target=lambda: _lib.gather_warmup(used)))
     for t in threads:
         t.start()
     for t in threads:
         t.join()
+    all_contexts = [c for res in results.values() for c in res[2]]
     try:
         if errors:
             raise errors[0]
-        for d in used:      # one stash per device: lane 0's members, then lane 1's
-            if len(lanes[d]) > 1:
-                _lib.stash_append(contexts[(d, 0)], contexts[(d, 1)], len(lanes[d][0]),
-                                  len(lanes[d][1]))
-        stacked = _lib.gather_topics([contexts[(d, 0)] for d in used],
+        stacked = _lib.gather_topics([results[d][0] for d in used],
                                      [len(assign[d]) for d in used])
-    finally:
-        for ctx in contexts.values():
-            if errors:
-                ctx.close()
-            else:
-                ctx.bootstrap(None)
-                _lib.release_context(ctx)
-    order = [[r for lane in lanes[d] for r in lane] for d in used]
-    out = stack_in_member_order(stacked, order, k)
+    except BaseException:
+        release_member_contexts(all_contexts, failed=True)
+        raise
+    release_member_contexts(all_contexts)
+    out = stack_in_member_order(stacked, [results[d][1] for d in used], k)
     if return_seeds:
         return out, seeds
     return out

@@ -236,8 +236,8 @@ def plsa_fit_shard(X_rows, k, p_z_given_d_rows, p_w_given_z, sample_weight_rows,
         ctx.set_factors(np.ascontiguousarray(p_z_given_d_rows, dtype=np.float32),
                         np.ascontiguousarray(p_w_given_z, dtype=np.float32))
         ctx.set_sample_weight(sample_weight_rows if use_sample_weights else None)
+        ctx.prepare(k, False)    # sort, work items, module load: before the ranks line up
         p2p = bool(exchange(ctx, comm.rank)) if exchange is not None else False
-        ctx.prepare(k, False)
         if profile:
             ctx.set_profiling(True)
         iters, trace = ctx.em(n_iter, n_iter_per_test, tolerance, e_step_thresh, refit=False,

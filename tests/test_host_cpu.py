@@ -335,3 +335,15 @@ def test_planned_passes_are_one_em_iteration(order):
     assert iters == 1
     assert np.allclose(new_pzd, e_pzd, rtol=1e-10, atol=1e-15)
     assert np.allclose(new_pwz, e_pwz, rtol=1e-10, atol=1e-15)
+
+
+def test_combine_matches_reference_golden():
+    """Cluster representatives (mean of sqrt(topic), squared, renormalised) against the
+    reference's own statements (enstop_.py:309-312, :397-411; tests/golden/make_golden_combine.py)."""
+    from enstop_b200 import enstop_
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "topic_combine.npz"))
+    out = enstop_._combine(g["all_topics"], g["labels"])
+    assert out.dtype == np.float32 and out.shape == g["combined_mean"].shape
+    assert np.allclose(out, g["combined_mean"], rtol=1e-6, atol=0)
+    outw = enstop_._combine(g["all_topics"], g["labels"], g["strengths"])
+    assert np.allclose(outw, g["combined_weighted"], rtol=1e-6, atol=0)
