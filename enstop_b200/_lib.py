@@ -27,7 +27,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
               "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden,-mavx2", "-diag-suppress", "550"]
 
 PLSA_OK, PLSA_EINVAL, PLSA_ECUDA, PLSA_ENOMEM, PLSA_ENCCL = 0, 1, 2, 3, 4
-PROF_SLOTS = ("doc_pass", "word_pass", "fixup", "normalize", "loglik")
+PROF_SLOTS = ("doc_pass", "word_pass", "fixup", "normalize", "loglik", "doc_head", "term_head")
 
 _i32p = ctypes.POINTER(ctypes.c_int32)
 _i64p = ctypes.POINTER(ctypes.c_int64)
@@ -65,8 +65,10 @@ SIGNATURES = {
     "plsa_get_profile": (ctypes.c_int, [_ctx, _f64p, _i64p]),
     "plsa_launch_count": (ctypes.c_int, [_ctx, _i64p]),
     "plsa_set_option": (ctypes.c_int, [_ctx, ctypes.c_char_p, _i64]),
-    "plsa_plan_items": (ctypes.c_int, [_i32p, _i64, _i64, _i32, _i32, _i64, _i64p, _i32p, _i32p,
+    "plsa_plan_items": (ctypes.c_int, [_i32p, _i64, _i64, _i32, _i64, _i64p, _i32p, _i32p,
                                        _i32p, _i32p, _i64p, _i32p, _i32p]),
+    "plsa_debug_items": (ctypes.c_int, [_ctx, _i32, _i64, _i64p, _i32p, _i32p, _i32p, _i32p, _i64p,
+                                        _i32p, _i32p, _i64p, _i32p, _i32p, _i64]),
     "plsa_host_random_rows": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint32), _i32p, _i64, _i64, _f32p,
                                              _f64p]),
     "plsa_b200_fit_inner": (ctypes.c_int, [_i32p, _i32p, _f32p, _i64, _f32p, _f32p, _f32p, _i64,
@@ -192,7 +194,7 @@ def random_rows(rng, rows, cols, want_f64=False, out=None):
     return (out, out64) if want_f64 else out
 
 
-def plan_items(indptr, chunk, align=4, order=0):
+def plan_items(indptr, chunk, align=4):
     """Host-only: the work items a row pass over a CSR with these row pointers launches, in
     launch order (plsa_plan_items).  Returns a dict of arrays start/row/len/slot/skip plus
     n_split and n_slots."""
@@ -201,13 +203,13 @@ def plan_items(indptr, chunk, align=4, order=0):
     n = _i64(0)
     ns, nl = _i32(0), _i32(0)
     L = lib()
-    check(L.plsa_plan_items(_ptr(indptr, _i32p), rows, int(chunk), int(align), int(order), 0,
+    check(L.plsa_plan_items(_ptr(indptr, _i32p), rows, int(chunk), int(align), 0,
                             None, None, None, None, None, ctypes.byref(n), ctypes.byref(ns),
                             ctypes.byref(nl)))
     out = dict(start=np.empty(n.value, np.int64), row=np.empty(n.value, np.int32),
                len=np.empty(n.value, np.int32), slot=np.empty(n.value, np.int32),
                skip=np.empty(n.value, np.int32))
-    check(L.plsa_plan_items(_ptr(indptr, _i32p), rows, int(chunk), int(align), int(order), n.value,
+    check(L.plsa_plan_items(_ptr(indptr, _i32p), rows, int(chunk), int(align), n.value,
                             _ptr(out["start"], _i64p), _ptr(out["row"], _i32p),
                             _ptr(out["len"], _i32p), _ptr(out["slot"], _i32p),
                             _ptr(out["skip"], _i32p), ctypes.byref(n), ctypes.byref(ns),
@@ -246,8 +248,6 @@ class Context:
             self.set_option("texture", int(os.environ["ENSTOP_B200_TEXTURE"]))
         if os.environ.get("ENSTOP_B200_VEC"):       # 0: unaligned items, one 8-byte load per entry
             self.set_option("vec_entries", int(os.environ["ENSTOP_B200_VEC"]))
-        if os.environ.get("ENSTOP_B200_ITEM_ORDER"):  # 1: same-window chunks adjacent (L1 reuse)
-            self.set_option("item_order", int(os.environ["ENSTOP_B200_ITEM_ORDER"]))
 
     def close(self):
         if self._h:
@@ -428,6 +428,26 @@ class Context:
     def shard_p2p_detach(self):
         """Unmap the peers' exchange blocks (before any rank frees its own)."""
         check(self._L.plsa_shard_p2p_detach(self._h), self._h)
+
+    def debug_items(self, which):
+        """Test hook: the device-resident work items of a pass (0 doc, 1 term, 2 tiled tail) as a
+        dict like plan_items', plus chunk, align and the row pointers they were planned from."""
+        n, ns, nl, ch, al = _i64(0), _i32(0), _i32(0), _i64(0), _i32(0)
+        check(self._L.plsa_debug_items(self._h, int(which), 0, None, None, None, None, None,
+                                       ctypes.byref(n), ctypes.byref(ns), ctypes.byref(nl),
+                                       ctypes.byref(ch), ctypes.byref(al), None, 0), self._h)
+        rows = self.shape[1] if which == 1 else self.shape[0]
+        out = dict(start=np.empty(n.value, np.int64), row=np.empty(n.value, np.int32),
+                   len=np.empty(n.value, np.int32), slot=np.empty(n.value, np.int32),
+                   skip=np.empty(n.value, np.int32), indptr=np.empty(rows + 1, np.int32))
+        check(self._L.plsa_debug_items(self._h, int(which), n.value, _ptr(out["start"], _i64p),
+                                       _ptr(out["row"], _i32p), _ptr(out["len"], _i32p),
+                                       _ptr(out["slot"], _i32p), _ptr(out["skip"], _i32p),
+                                       ctypes.byref(n), ctypes.byref(ns), ctypes.byref(nl),
+                                       ctypes.byref(ch), ctypes.byref(al), _ptr(out["indptr"], _i32p),
+                                       rows + 1), self._h)
+        out.update(n_split=ns.value, n_slots=nl.value, chunk=ch.value, align=al.value)
+        return out
 
     def stash_topics(self, slot, n_slots):
         check(self._L.plsa_stash_topics(self._h, int(slot), int(n_slots)), self._h)

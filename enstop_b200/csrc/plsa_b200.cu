@@ -16,6 +16,7 @@
 #include <cub/cub.cuh>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <cmath>
@@ -86,12 +87,18 @@ static inline size_t ent_bytes(int64_t nnz) { return (size_t)(nnz + ENT_PAD) * s
 
 struct ItemSet {
     DevBuf items, split_rows, slot_begin;
+    DevBuf plan[9]; /* device planner scratch: 5 counts, their 5 scans share [5..], keys, perm, unsorted */
     int64_t n_items = 0;
     int32_t n_split = 0, n_heavy = 0, n_slots = 0;
     bool ready = false;
     int64_t chunk = 0;
     int align = 1; /* items start on multiples of this many entries (Item::skip) */
-    int order = 0; /* plan_items order the set was built with */
+    void release()
+    {
+        items.release(); split_rows.release(); slot_begin.release();
+        for (DevBuf &b : plan) b.release();
+        ready = false;
+    }
 };
 
 /* Tiled doc pass (plsa_tile.cuh): the doc-major corpus split into a "head" CSR whose columns
@@ -111,9 +118,33 @@ struct TileSet {
         for (DevBuf *b : {&col_count, &col_ids, &col_count_sorted, &col_sorted, &slot_of, &head_len,
                           &tail_len, &head_indptr, &tail_indptr, &head_ent, &tail_ent, &order,
                           &order_keys, &row_ids, &cub_tmp, &head_sum, &img[0], &img[1], &scale_raw,
-                          &ll_part, &ll_head, &ll_ticket, &tail_items.items, &tail_items.split_rows,
-                          &tail_items.slot_begin})
+                          &ll_part, &ll_head, &ll_ticket})
             b->release();
+        tail_items.release();
+        ready = false;
+    }
+};
+
+/* Tiled term pass: the frequent terms' rows of the term-major corpus cut at blocks of
+ * documents; item v = (tiled term, block) gathers P(z|d) rows of ONE block, which a CTA holds
+ * in shared memory; the per-block partial sums of a term are added by fixup_kernel.  The other
+ * terms stay with the group-per-row kernel (tail_items skips the tiled rows). */
+struct TermTiles {
+    bool ready = false, weighted = false;
+    int32_t kp = 0, block_rows = 0, n_blocks = 0, n_tiled = 0, pitch_f = 0, grid = 0;
+    int64_t n = 0, m = 0, n_items = 0, head_slots = 0;
+    DevBuf flag, tiled_at, tiled_terms, beg, end, own_row, head_len, head_indptr, head_ent, keys,
+        keys_sorted, ids, order, work, work_prefix, cta_begin, block_begin, partial, slot_begin, cub_tmp,
+        acomp[2];
+    std::vector<int32_t> h_flag;
+    ItemSet tail_items;
+    void release()
+    {
+        for (DevBuf *b : {&flag, &tiled_at, &tiled_terms, &beg, &end, &own_row, &head_len, &head_indptr,
+                          &head_ent, &keys, &keys_sorted, &ids, &order, &work, &work_prefix, &cta_begin,
+                          &block_begin, &partial, &slot_begin, &cub_tmp, &acomp[0], &acomp[1]})
+            b->release();
+        tail_items.release();
         ready = false;
     }
 };
@@ -132,12 +163,17 @@ struct plsa_ctx {
     const Corpus &cur() const { return use_boot ? boot : base; }
 
     /* term-major copy of the working corpus */
-    DevBuf t_ent, t_entw, up_cols, up_vals, flag, scratch[7];
+    DevBuf t_ent, t_entw, t_indptr, up_cols, up_vals, flag, scratch[7];
+    bool device_plan = true; /* option "device_plan": work items planned on the device */
     std::vector<int32_t> h_tindptr;
     bool t_ready = false, t_weighted_ready = false;
 
     ItemSet doc_items, term_items;
     TileSet tiles;
+    TermTiles tterm;
+    int term_tiled_opt = 1;             /* option "term_tiled": tile the term pass too (with "tiled") */
+    int64_t term_tile_min = 12;         /* option "term_tile_min": entries per (term, block) item, on average, for a term to be tiled */
+    bool a_comp[2] = {false, false};    /* tterm.acomp[i] is the compact image of A[i] */
     int tiled_opt = -1;                 /* option "tiled": -1 auto, 0 off, 1 on where possible */
     int64_t tile_bytes = 200 * 1024;    /* option "tile_kb": shared memory of the tile        */
     bool b_norm[2] = {false, false};    /* B[i] is column-normalised in place, tiles.img[i] holds its tile rows */
@@ -147,14 +183,13 @@ struct plsa_ctx {
     int32_t k_hint = 0;      /* plsa_prepare: k the items should be sized for */
     bool use_texture = true; /* gather through the texture pipe when the factor fits */
     bool vec_entries = true; /* items aligned to entry blocks, one wide load per block */
-    int item_order = 0;      /* option "item_order": 0 row, 1 window (see plan_items) */
     bool fuse_ll = true;     /* take the periodic log-likelihood from the next doc pass */
     double *mail = nullptr;  /* pinned host mailbox {ll, flag} */
     cudaEvent_t ev_ll = nullptr;
     bool overlap = true;     /* doc pass and term pass of an iteration on two streams */
     cudaStream_t stream2 = nullptr;
     /* pinned staging for host->device copies of pageable memory (see h2d_fast) */
-    static constexpr int H2D_THREADS = 4;
+    static constexpr int H2D_THREADS = 4; /* at most; h2d_threads() of them are used */
     static constexpr size_t H2D_CHUNK = (size_t)4 << 20;
     char *pin[H2D_THREADS] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t pin_stream[H2D_THREADS] = {nullptr, nullptr, nullptr, nullptr};
@@ -195,8 +230,8 @@ struct plsa_ctx {
     float last_em_ms = 0.f;
     int64_t launches = 0;
     bool profiling = false;
-    double prof_ms[PLSA_PROF_SLOTS] = {0, 0, 0, 0, 0};
-    int64_t prof_n[PLSA_PROF_SLOTS] = {0, 0, 0, 0, 0};
+    double prof_ms[PLSA_PROF_SLOTS] = {};
+    int64_t prof_n[PLSA_PROF_SLOTS] = {};
     struct ProfRec { int slot; cudaEvent_t a, b; };
     std::vector<ProfRec> prof_pending;
     std::vector<cudaEvent_t> ev_pool;
@@ -236,9 +271,27 @@ static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
  * Large uploads are instead cut into four slices, each moved by its own host thread through
  * a private pinned double buffer and stream, so the host-side memcpy runs four wide and
  * overlaps the DMA. */
+/* Upload threads of this process: the cores it may run on, shared with the other ranks of the
+ * box (LOCAL_WORLD_SIZE, set by torchrun) and with the fit's own helper threads (seeded init,
+ * value check) — eight ranks with four upload threads each oversubscribed a 32-core host. */
+static int h2d_threads()
+{
+    static const int n = [] {
+        cpu_set_t set;
+        int cores = 0;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set);
+        if (cores <= 0) cores = (int)std::thread::hardware_concurrency();
+        int ranks = 1;
+        if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+        if (const char *e = getenv("ENSTOP_B200_H2D_THREADS")) return std::max(1, std::min(4, atoi(e)));
+        return std::max(1, std::min(plsa_ctx::H2D_THREADS, cores / ranks / 2));
+    }();
+    return n;
+}
+
 static cudaError_t h2d_fast(plsa_ctx *ctx, void *dst, const void *src, size_t bytes)
 {
-    constexpr int T = plsa_ctx::H2D_THREADS;
+    const int T = h2d_threads();
     constexpr size_t CH = plsa_ctx::H2D_CHUNK;
     if (bytes < 8 * CH) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
     cudaError_t e;
@@ -254,8 +307,8 @@ static cudaError_t h2d_fast(plsa_ctx *ctx, void *dst, const void *src, size_t by
     /* everything queued on ctx->stream so far (e.g. buffer memsets) precedes the copies */
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return e;
     const size_t slice = (bytes / T + 255) / 256 * 256;
-    cudaError_t errs[T];
-    std::thread th[T];
+    cudaError_t errs[plsa_ctx::H2D_THREADS];
+    std::thread th[plsa_ctx::H2D_THREADS];
     const int device = ctx->device;
     for (int t = 0; t < T; ++t) {
         errs[t] = cudaSuccess;
@@ -418,13 +471,8 @@ static int launch_pass(plsa_ctx *ctx, int mode, const PassArgs &a, bool vec,
         static std::map<std::pair<int, pass_fn>, bool> configured; /* function attributes are per device */
         std::lock_guard<std::mutex> lock(mu);
         if (!configured[std::make_pair(ctx->device, fn)]) {
-#if PLSA_PASS_THREADS == 256
             cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  mode == MODE_TERM ? 15 : 5);
-#else /* occupancy experiments: more, smaller CTAs need a larger share for the same kernels */
-            cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 mode == MODE_TERM ? 30 : 12);
-#endif
             cudaGetLastError(); /* a hint: failure is not an error */
             configured[std::make_pair(ctx->device, fn)] = true;
         }
@@ -456,23 +504,10 @@ static int64_t choose_chunk(const plsa_ctx *ctx, int kp)
 }
 
 /* The plan of a pass, host side only (no CUDA): the items in launch order, the split rows
- * (heavy first) and the first partial-sum slot of each.
- *
- * order 0 ("row"): same-length items stay in row order — the chunks of a split row sit next to
- * each other, so a CTA (8 warps x 32/G consecutive items) typically walks 48 chunks of ONE
- * dense row, whose gathered rows are disjoint.
- * order 1 ("window"): same-length chunks are ordered by where they sit inside their row
- * (chunk number / chunks of the row): stored entries are sorted by gathered-row index, so a
- * chunk's position predicts the window of gathered rows it covers, and the chunks a CTA
- * carries then cover the SAME window — the gathers of one chunk hit L1 lines another chunk
- * of the CTA pulled in.  Modelled on the C2 corpus (scripts/sim_item_locality.py): share of
- * the term pass's gathers whose line another item of the same CTA also touches 4 % -> 37 %,
- * hit rate of a 1400-line LRU shared by four resident CTAs 3 % -> 12-14 %.
- * order 2 ("band"): all chunks first, in 32 bands of positions; inside a band longest first,
- * then by position; the whole rows follow, longest first.  The chunks in flight on the whole
- * GPU at one time then cover a narrow band of gathered rows — meant for corpora whose
- * gathered factor does not fit the L2 (C5: P(z|d) is 128 MB).
- * Item lengths, the slot of every chunk and hence every sum are the same in all orders. */
+ * (heavy first) and the first partial-sum slot of each.  Same-length items stay in row order:
+ * the chunks of a split row sit next to each other.  (Two other launch orders — chunks grouped
+ * by their position inside the row, for L1 reuse inside a CTA, and in bands of positions, for
+ * L2 reuse — were measured at C2 and gained nothing: profiles/r2a_ab_c2.txt.) */
 struct ItemPlan {
     std::vector<Item> sorted;
     std::vector<int32_t> split_rows, slot_begin;
@@ -480,7 +515,7 @@ struct ItemPlan {
 };
 
 static void plan_items(const int32_t *indptr, int64_t rows, const int64_t chunk_asked, int align,
-                       int order, ItemPlan &plan)
+                       ItemPlan &plan, const int32_t *skip_row = nullptr /* rows that get no item */)
 {
     const int64_t chunk = std::max<int64_t>(align, chunk_asked / align * align); /* chunks of a split row stay aligned */
     std::vector<Item> items;
@@ -489,7 +524,10 @@ static void plan_items(const int32_t *indptr, int64_t rows, const int64_t chunk_
      * entry; the entries in between (Item::skip of them, they belong to the row before) are
      * walked with value 0.  Lengths below include them. */
     auto lead = [&](int64_t r) { return (int64_t)indptr[r] & (int64_t)(align - 1); };
-    auto span = [&](int64_t r) { return (int64_t)indptr[r + 1] - indptr[r] + lead(r); };
+    auto skipped = [&](int64_t r) { return skip_row != nullptr && skip_row[r] != 0; };
+    auto span = [&](int64_t r) {
+        return skipped(r) ? (int64_t)0 : (int64_t)indptr[r + 1] - indptr[r] + lead(r);
+    };
     /* A split row is cut into equal pieces (not full chunks plus a short remainder), so that
      * the pieces of a row sort next to each other and none of them is a tiny item. */
     auto piece = [&](int64_t len) {
@@ -515,12 +553,9 @@ static void plan_items(const int32_t *indptr, int64_t rows, const int64_t chunk_
             split_rows.push_back((int32_t)r);
             slot_begin.push_back(slots);
         }
-    /* orders 1 and 2: the chunks are kept apart and binned by their position inside the row */
-    constexpr int POS_BINS = 4096, BANDS = 32;
-    struct Piece { Item it; int32_t pos; };
-    std::vector<Piece> pieces;
     for (int64_t r = 0; r < rows; ++r) {
         const int64_t skip = lead(r), s = indptr[r] - skip, len = span(r);
+        if (skipped(r)) continue;
         if (len <= chunk) {
             items.push_back(Item{s, (int32_t)r, (int32_t)len, -1, (int32_t)skip});
         } else {
@@ -530,23 +565,10 @@ static void plan_items(const int32_t *indptr, int64_t rows, const int64_t chunk_
                 const Item it{s + b, (int32_t)r, (int32_t)std::min(per, len - b),
                               first_slot[(size_t)r] + (int32_t)c,
                               (int32_t)(c == 0 ? (skip | ITEM_FIRST) : 0)};
-                if (order != 0) pieces.push_back(Piece{it, (int32_t)(b * POS_BINS / len)});
-                else items.push_back(it);
+                items.push_back(it);
             }
         }
     }
-    /* stable counting sort of the chunks by key(piece) in [0, n_keys) */
-    auto bucket = [&](int64_t n_keys, auto key) {
-        std::vector<int64_t> at((size_t)n_keys + 1, 0);
-        for (const Piece &p : pieces) at[(size_t)key(p) + 1]++;
-        for (int64_t b = 0; b < n_keys; ++b) at[(size_t)b + 1] += at[(size_t)b];
-        std::vector<Piece> out(pieces.size());
-        for (const Piece &p : pieces) out[(size_t)at[(size_t)key(p)]++] = p;
-        pieces.swap(out);
-    };
-    if (!pieces.empty()) bucket(POS_BINS, [](const Piece &p) { return (int64_t)p.pos; });
-    if (order == 1)
-        for (const Piece &p : pieces) items.push_back(p.it); /* behind the whole rows */
     /* counting sort by length, descending, stable */
     std::vector<int64_t> cnt((size_t)chunk + 2, 0);
     for (const Item &it : items) cnt[(size_t)(chunk - it.len)]++;
@@ -557,27 +579,20 @@ static void plan_items(const int32_t *indptr, int64_t rows, const int64_t chunk_
         run += t;
     }
     std::vector<Item> &sorted = plan.sorted;
-    const size_t lead_items = order == 2 ? pieces.size() : 0; /* order 2: the chunks go first */
-    sorted.resize(items.size() + lead_items);
-    for (const Item &it : items) sorted[lead_items + (size_t)cnt[(size_t)(chunk - it.len)]++] = it;
-    if (order == 2 && !pieces.empty()) {
-        /* band-major: BANDS bands of positions; inside a band longest first, then by position */
-        bucket(chunk + 1, [&](const Piece &p) { return chunk - (int64_t)p.it.len; });
-        bucket(BANDS, [](const Piece &p) { return (int64_t)p.pos / (POS_BINS / BANDS); });
-        for (size_t i = 0; i < pieces.size(); ++i) sorted[i] = pieces[i].it;
-    }
+    sorted.resize(items.size());
+    for (const Item &it : items) sorted[(size_t)cnt[(size_t)(chunk - it.len)]++] = it;
     plan.n_heavy = (int32_t)heavy.size();
     plan.slots = slots;
 }
 
 static int build_items(plsa_ctx *ctx, const std::vector<int32_t> &indptr, int64_t rows,
                        ItemSet &out, const int64_t chunk_asked, int align,
-                       cudaStream_t stream = nullptr)
+                       cudaStream_t stream = nullptr, const int32_t *h_skip_row = nullptr)
 {
     if (!stream) stream = ctx->stream;
     ItemPlan plan;
     try { /* no C++ exception crosses the C ABI */
-        plan_items(indptr.data(), rows, chunk_asked, align, ctx->item_order, plan);
+        plan_items(indptr.data(), rows, chunk_asked, align, plan, h_skip_row);
     } catch (const std::bad_alloc &) {
         return ctx->fail(PLSA_ENOMEM, "work items: out of host memory");
     }
@@ -604,7 +619,80 @@ static int build_items(plsa_ctx *ctx, const std::vector<int32_t> &indptr, int64_
     out.ready = true;
     out.chunk = chunk_asked;
     out.align = align;
-    out.order = ctx->item_order;
+    return PLSA_OK;
+}
+
+/* The same plan built on the device from the device copy of the row pointers: no host pass over
+ * the rows, one 20-byte read-back (the totals).  Bit-identical to plan_items: the items are
+ * generated in row order and put longest first by a STABLE radix sort, which is what the host's
+ * counting sort does (tests/test_gpu_parity.py::test_device_plan_is_the_host_plan). */
+static int build_items_device(plsa_ctx *ctx, const int32_t *d_indptr, int64_t rows, ItemSet &out,
+                              const int64_t chunk_asked, int align, cudaStream_t stream = nullptr,
+                              const int32_t *d_skip_row = nullptr /* rows that get no item */)
+{
+    if (!stream) stream = ctx->stream;
+    const int32_t chunk = (int32_t)std::max<int64_t>(align, chunk_asked / align * align);
+    const int T = 256;
+    const size_t cnt_bytes = (size_t)(rows + 1) * 4;
+    DevBuf &counts = out.plan[0], &scans = out.plan[1], &keys = out.plan[2], &keys_out = out.plan[3],
+           &perm_in = out.plan[4], &perm_out = out.plan[5], &unsorted = out.plan[6], &tmp = out.plan[7];
+    CK(counts.ensure(cnt_bytes * 5));
+    CK(scans.ensure(cnt_bytes * 5));
+    int32_t *c0 = counts.as<int32_t>(), *s0 = scans.as<int32_t>();
+    const size_t stride = (size_t)rows + 1;
+    plan_count_kernel<<<(unsigned)cdiv(rows + 1, T), T, 0, stream>>>(d_indptr, rows, chunk, align, d_skip_row, c0, c0 + stride,
+                                                                   c0 + 2 * stride, c0 + 3 * stride,
+                                                                   c0 + 4 * stride);
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c0, s0, (int)(rows + 1), stream));
+    CK(tmp.ensure(tmp_bytes));
+    for (int q = 0; q < 5; ++q) {
+        size_t tb = tmp.cap;
+        CK(cub::DeviceScan::ExclusiveSum(tmp.p, tb, c0 + q * stride, s0 + q * stride, (int)(rows + 1), stream));
+    }
+    int32_t totals[5] = {0, 0, 0, 0, 0};
+    for (int q = 0; q < 5; ++q)
+        CK(cudaMemcpyAsync(&totals[q], s0 + q * stride + rows, 4, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    const int64_t n_items = totals[0];
+    const int32_t n_heavy = totals[1], n_light = totals[2], slots = totals[3] + totals[4];
+    out.n_items = n_items;
+    out.n_split = n_heavy + n_light;
+    out.n_heavy = n_heavy;
+    out.n_slots = slots;
+    CK(out.items.ensure((size_t)std::max<int64_t>(n_items, 1) * sizeof(Item)));
+    CK(unsorted.ensure((size_t)std::max<int64_t>(n_items, 1) * sizeof(Item)));
+    CK(keys.ensure((size_t)std::max<int64_t>(n_items, 1) * 4));
+    CK(keys_out.ensure((size_t)std::max<int64_t>(n_items, 1) * 4));
+    CK(perm_in.ensure((size_t)std::max<int64_t>(n_items, 1) * 4));
+    CK(perm_out.ensure((size_t)std::max<int64_t>(n_items, 1) * 4));
+    CK(out.split_rows.ensure((size_t)std::max(out.n_split, 1) * 4));
+    CK(out.slot_begin.ensure((size_t)(out.n_split + 1) * 4));
+    CK(cudaMemsetAsync(out.slot_begin.p, 0, 4, stream)); /* rows == 0: the closing entry */
+    if (rows > 0 && n_items > 0) {
+        plan_emit_kernel<<<(unsigned)cdiv(rows, T), T, 0, stream>>>(
+            d_indptr, rows, chunk, align, d_skip_row, s0, s0 + stride, s0 + 2 * stride, s0 + 3 * stride, s0 + 4 * stride,
+            unsorted.as<Item>(), keys.as<int32_t>(), out.split_rows.as<int32_t>(), out.slot_begin.as<int32_t>());
+        iota_kernel<<<(unsigned)cdiv(n_items, T), T, 0, stream>>>(perm_in.as<int32_t>(), n_items);
+        int end_bit = 1;
+        while (((int64_t)1 << end_bit) <= chunk) ++end_bit;
+        size_t sb = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, sb, keys.as<int32_t>(), keys_out.as<int32_t>(),
+                                           perm_in.as<int32_t>(), perm_out.as<int32_t>(), (int)n_items, 0,
+                                           end_bit, stream));
+        CK(tmp.ensure(sb));
+        sb = tmp.cap;
+        CK(cub::DeviceRadixSort::SortPairs(tmp.p, sb, keys.as<int32_t>(), keys_out.as<int32_t>(),
+                                           perm_in.as<int32_t>(), perm_out.as<int32_t>(), (int)n_items, 0,
+                                           end_bit, stream));
+        plan_gather_kernel<<<(unsigned)cdiv(n_items, T), T, 0, stream>>>(unsorted.as<Item>(), perm_out.as<int32_t>(),
+                                                                       n_items, out.items.as<Item>());
+        ctx->launches += 4;
+        CK(cudaGetLastError());
+    }
+    out.ready = true;
+    out.chunk = chunk_asked;
+    out.align = align;
     return PLSA_OK;
 }
 
@@ -619,7 +707,7 @@ static int build_term_major(plsa_ctx *ctx)
     /* scratch (20 B per entry) is kept with the context for the next corpus unless it is
      * large: repeated fits then skip seven cudaMalloc/cudaFree pairs */
     DevBuf &rows_exp = ctx->scratch[0], &keys_in = ctx->scratch[1], &perm_in = ctx->scratch[2],
-           &perm_out = ctx->scratch[3], &keys_out = ctx->scratch[4], &tindptr = ctx->scratch[5],
+           &perm_out = ctx->scratch[3], &keys_out = ctx->scratch[4], &tindptr = ctx->t_indptr,
            &tmp = ctx->scratch[6];
     auto cleanup = [&]() {
         if (nnz > ((int64_t)32 << 20))
@@ -638,6 +726,8 @@ static int build_term_major(plsa_ctx *ctx)
     CKT(ctx->t_ent.ensure(ent_bytes(nnz)));
     CKT(cudaMemsetAsync(ctx->t_ent.as<int2>() + nnz, 0, ENT_PAD * sizeof(int2), s));
     ctx->h_tindptr.assign((size_t)m + 1, 0);
+    CKT(tindptr.ensure((size_t)(m + 1) * 4));
+    if (nnz == 0) CKT(cudaMemsetAsync(tindptr.p, 0, (size_t)(m + 1) * 4, s));
     if (nnz > 0) {
         CKT(rows_exp.ensure(nz * 4));
         CKT(keys_in.ensure(nz * 4));
@@ -739,7 +829,7 @@ static int ensure_tiles(plsa_ctx *ctx, int kp)
     const int64_t chunk = choose_chunk(ctx, kp);
     const int align = ctx->vec_entries ? pass_entry_block(kp) : 1;
     if (t.ready && t.kp == kp && t.tile_rows == tile_rows && t.n == n && t.tail_items.ready &&
-        t.tail_items.chunk == chunk && t.tail_items.align == align && t.tail_items.order == ctx->item_order)
+        t.tail_items.chunk == chunk && t.tail_items.align == align)
         return PLSA_OK;
     cudaStream_t s = ctx->stream;
     const int T = 256;
@@ -784,8 +874,9 @@ static int ensure_tiles(plsa_ctx *ctx, int kp)
     /* per row: padded head length and tail length, then the two row-pointer arrays */
     CK(cudaMemsetAsync(t.head_len.as<int32_t>() + n, 0, 4, s));
     CK(cudaMemsetAsync(t.tail_len.as<int32_t>() + n, 0, 4, s));
-    tile_count_kernel<<<(unsigned)cdiv(n * 32, T), T, 0, s>>>(c.indptr.as<int32_t>(), n, c.ent.as<int2>(),
-                                                            t.slot_of.as<int32_t>(), t.head_len.as<int32_t>(),
+    const SlotMap map{t.slot_of.as<int32_t>(), 1, 0};
+    tile_count_kernel<<<(unsigned)cdiv(n * 32, T), T, 0, s>>>(c.indptr.as<int32_t>(), c.indptr.as<int32_t>() + 1, n,
+                                                            c.ent.as<int2>(), map, t.head_len.as<int32_t>(),
                                                             t.tail_len.as<int32_t>());
     tmp = t.cub_tmp.cap;
     CK(cub::DeviceScan::ExclusiveSum(t.cub_tmp.p, tmp, t.head_len.as<int32_t>(), t.head_indptr.as<int32_t>(),
@@ -802,25 +893,29 @@ static int ensure_tiles(plsa_ctx *ctx, int kp)
                                                  t.order.as<int32_t>(), (int)n, 0, 32, s));
     ctx->launches += 6;
     CK(cudaGetLastError());
-    try {
-        t.h_tail_indptr.resize((size_t)n + 1);
-    } catch (const std::bad_alloc &) {
-        return ctx->fail(PLSA_ENOMEM, "tiles: out of host memory");
+    int32_t head_total = 0, tail_total = 0;
+    if (!ctx->device_plan) { /* the host planner walks the tail's row pointers */
+        try {
+            t.h_tail_indptr.resize((size_t)n + 1);
+        } catch (const std::bad_alloc &) {
+            return ctx->fail(PLSA_ENOMEM, "tiles: out of host memory");
+        }
+        CK(cudaMemcpyAsync(t.h_tail_indptr.data(), t.tail_indptr.p, (size_t)(n + 1) * 4,
+                           cudaMemcpyDeviceToHost, s));
     }
-    int32_t head_total = 0;
-    CK(cudaMemcpyAsync(t.h_tail_indptr.data(), t.tail_indptr.p, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&tail_total, t.tail_indptr.as<int32_t>() + n, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(&head_total, t.head_indptr.as<int32_t>() + n, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     t.head_slots = head_total;
-    t.tail_nnz = t.h_tail_indptr[(size_t)n];
+    t.tail_nnz = tail_total;
     if (t.head_slots < 0 || t.tail_nnz < 0 || t.tail_nnz > nnz)
         return ctx->fail(PLSA_ECUDA, "tiles: inconsistent head / tail split");
     CK(t.head_ent.ensure((size_t)std::max<int64_t>(t.head_slots, 1) * sizeof(int2)));
     CK(t.tail_ent.ensure(ent_bytes(t.tail_nnz)));
     CK(cudaMemsetAsync(t.tail_ent.as<int2>() + t.tail_nnz, 0, ENT_PAD * sizeof(int2), s));
     tile_place_kernel<<<(unsigned)cdiv(n * 32, T), T, 0, s>>>(
-        c.indptr.as<int32_t>(), n, c.ent.as<int2>(), t.slot_of.as<int32_t>(), t.head_indptr.as<int32_t>(),
-        t.tail_indptr.as<int32_t>(), t.head_ent.as<int2>(), t.tail_ent.as<int2>());
+        c.indptr.as<int32_t>(), c.indptr.as<int32_t>() + 1, n, c.ent.as<int2>(), map, t.head_indptr.as<int32_t>(),
+        t.tail_indptr.as<int32_t>(), t.head_ent.as<int2>(), t.tail_ent.as<int2>(), nullptr);
     ctx->launches++;
     CK(cudaGetLastError());
     /* compact images of the tile rows (ping-pong like B), zero beyond the last row */
@@ -836,7 +931,8 @@ static int ensure_tiles(plsa_ctx *ctx, int kp)
     CK(t.ll_head.ensure(8));
     CK(t.ll_ticket.ensure(4));
     CK(cudaMemsetAsync(t.ll_ticket.p, 0, 4, s));
-    int rc = build_items(ctx, t.h_tail_indptr, n, t.tail_items, chunk, align);
+    int rc = ctx->device_plan ? build_items_device(ctx, t.tail_indptr.as<int32_t>(), n, t.tail_items, chunk, align)
+                              : build_items(ctx, t.h_tail_indptr, n, t.tail_items, chunk, align);
     if (rc) return rc;
     /* opt in to the tile's dynamic shared memory once per kernel and device */
     for (int ll = 0; ll < 2; ++ll)
@@ -861,10 +957,167 @@ static int normalise_b(plsa_ctx *ctx, int which, const float *scale, cudaStream_
     return PLSA_OK;
 }
 
+/* ---- tiled term pass: (term, document block) items of the frequent terms ---------------------- */
+static int ensure_term_tiles(plsa_ctx *ctx, int kp, bool weighted)
+{
+    TermTiles &t = ctx->tterm;
+    const Corpus &c = ctx->cur();
+    const int64_t n = c.n, m = c.m;
+    const int pc = tile_pitch_chunks(kp / 4);
+    int32_t block_rows = (int32_t)std::max<int64_t>(TILE_MIN_ROWS, ctx->tile_bytes / (pc * 16) / 8 * 8);
+    block_rows = (int32_t)std::min<int64_t>(block_rows, (n + 7) / 8 * 8);
+    const int32_t n_blocks = (int32_t)cdiv(n, block_rows);
+    const int64_t chunk = choose_chunk(ctx, kp);
+    const int align = ctx->vec_entries ? pass_entry_block(kp) : 1;
+    if (t.ready && t.kp == kp && t.block_rows == block_rows && t.n == n && t.m == m && t.weighted == weighted &&
+        t.grid == ctx->n_sms && t.tail_items.ready && t.tail_items.chunk == chunk && t.tail_items.align == align)
+        return PLSA_OK;
+    cudaStream_t s = ctx->stream;
+    const int T = 256;
+    t.ready = false;
+    t.kp = kp; t.block_rows = block_rows; t.n_blocks = n_blocks; t.n = n; t.m = m; t.weighted = weighted;
+    t.pitch_f = pc * 4;
+    t.grid = ctx->n_sms;
+    const int2 *t_ent = ctx->t_ent.as<int2>(); /* unweighted: the weights are applied when placing */
+    /* which terms are tiled */
+    CK(t.flag.ensure((size_t)(m + 1) * 4));
+    CK(t.tiled_at.ensure((size_t)(m + 1) * 4));
+    const int32_t min_count = (int32_t)std::min<int64_t>(((int64_t)1 << 30), ctx->term_tile_min * n_blocks);
+    term_tiled_flag_kernel<<<(unsigned)cdiv(m + 1, T), T, 0, s>>>(ctx->t_indptr.as<int32_t>(), m, min_count,
+                                                                t.flag.as<int32_t>());
+    size_t tb = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, t.flag.as<int32_t>(), t.tiled_at.as<int32_t>(), (int)(m + 1), s));
+    CK(t.cub_tmp.ensure(std::max<size_t>(tb, 1 << 20)));
+    tb = t.cub_tmp.cap;
+    CK(cub::DeviceScan::ExclusiveSum(t.cub_tmp.p, tb, t.flag.as<int32_t>(), t.tiled_at.as<int32_t>(), (int)(m + 1), s));
+    int32_t n_tiled = 0;
+    CK(cudaMemcpyAsync(&n_tiled, t.tiled_at.as<int32_t>() + m, 4, cudaMemcpyDeviceToHost, s));
+    if (!ctx->device_plan) {
+        try {
+            t.h_flag.resize((size_t)m + 1);
+        } catch (const std::bad_alloc &) {
+            return ctx->fail(PLSA_ENOMEM, "term tiles: out of host memory");
+        }
+        CK(cudaMemcpyAsync(t.h_flag.data(), t.flag.p, (size_t)(m + 1) * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    if ((int64_t)n_tiled * n_blocks >= ((int64_t)1 << 30)) n_tiled = 0; /* item numbers stay int32 */
+    t.n_tiled = n_tiled;
+    t.n_items = (int64_t)n_tiled * n_blocks;
+    const int64_t V = t.n_items;
+    if (V == 0) { /* nothing worth tiling: the whole term pass stays with the group-per-row kernel */
+        t.ready = true;
+        t.tail_items.ready = false;
+        return PLSA_OK;
+    }
+    /* the items: entry ranges, owned term */
+    CK(t.tiled_terms.ensure((size_t)n_tiled * 4));
+    CK(t.beg.ensure((size_t)V * 4));
+    CK(t.end.ensure((size_t)V * 4));
+    CK(t.own_row.ensure((size_t)V * 4));
+    CK(t.head_len.ensure((size_t)(V + 1) * 4));
+    CK(t.head_indptr.ensure((size_t)(V + 1) * 4));
+    term_items_kernel<<<(unsigned)cdiv(m * n_blocks, T), T, 0, s>>>(
+        ctx->t_indptr.as<int32_t>(), m, t.flag.as<int32_t>(), t.tiled_at.as<int32_t>(), t_ent, n_blocks, block_rows,
+        t.beg.as<int32_t>(), t.end.as<int32_t>(), t.own_row.as<int32_t>(), t.tiled_terms.as<int32_t>());
+    const SlotMap map{nullptr, n_blocks, block_rows};
+    CK(cudaMemsetAsync(t.head_len.as<int32_t>() + V, 0, 4, s));
+    tile_count_kernel<<<(unsigned)cdiv(V * 32, T), T, 0, s>>>(t.beg.as<int32_t>(), t.end.as<int32_t>(), V, t_ent, map,
+                                                            t.head_len.as<int32_t>(), nullptr);
+    tb = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, t.head_len.as<int32_t>(), t.head_indptr.as<int32_t>(), (int)(V + 1), s));
+    CK(t.cub_tmp.ensure(tb));
+    tb = t.cub_tmp.cap;
+    CK(cub::DeviceScan::ExclusiveSum(t.cub_tmp.p, tb, t.head_len.as<int32_t>(), t.head_indptr.as<int32_t>(), (int)(V + 1), s));
+    int32_t head_total = 0;
+    CK(cudaMemcpyAsync(&head_total, t.head_indptr.as<int32_t>() + V, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (head_total < 0) return ctx->fail(PLSA_ECUDA, "term tiles: inconsistent item lengths");
+    t.head_slots = head_total;
+    CK(t.head_ent.ensure((size_t)std::max<int64_t>(t.head_slots, 1) * sizeof(int2)));
+    tile_place_kernel<<<(unsigned)cdiv(V * 32, T), T, 0, s>>>(
+        t.beg.as<int32_t>(), t.end.as<int32_t>(), V, t_ent, map, t.head_indptr.as<int32_t>(), nullptr,
+        t.head_ent.as<int2>(), nullptr, weighted ? ctx->sw.as<float>() : nullptr);
+    /* launch order: block-major, inside a block longest first; one range of equal work per CTA */
+    CK(t.keys.ensure((size_t)V * 4));
+    CK(t.keys_sorted.ensure((size_t)V * 4));
+    CK(t.ids.ensure((size_t)V * 4));
+    CK(t.order.ensure((size_t)V * 4));
+    CK(t.work.ensure((size_t)(V + 1) * 4));
+    CK(t.work_prefix.ensure((size_t)(V + 1) * 4));
+    CK(t.cta_begin.ensure((size_t)(t.grid + 1) * 4));
+    CK(t.block_begin.ensure((size_t)(n_blocks + 1) * 4));
+    term_item_keys_kernel<<<(unsigned)cdiv(V, T), T, 0, s>>>(t.head_len.as<int32_t>(), V, n_blocks, block_rows,
+                                                           t.keys.as<int32_t>());
+    iota_kernel<<<(unsigned)cdiv(V, T), T, 0, s>>>(t.ids.as<int32_t>(), V);
+    int end_bit = 1;
+    while (((int64_t)1 << end_bit) < (int64_t)(n_blocks + 1) * (block_rows / 8 + 1)) ++end_bit;
+    tb = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, t.keys.as<int32_t>(), t.keys_sorted.as<int32_t>(),
+                                       t.ids.as<int32_t>(), t.order.as<int32_t>(), (int)V, 0, end_bit, s));
+    CK(t.cub_tmp.ensure(tb));
+    tb = t.cub_tmp.cap;
+    CK(cub::DeviceRadixSort::SortPairs(t.cub_tmp.p, tb, t.keys.as<int32_t>(), t.keys_sorted.as<int32_t>(),
+                                       t.ids.as<int32_t>(), t.order.as<int32_t>(), (int)V, 0, end_bit, s));
+    term_work_kernel<<<(unsigned)cdiv(V + 1, T), T, 0, s>>>(t.order.as<int32_t>(), t.head_len.as<int32_t>(), V,
+                                                          t.work.as<int32_t>());
+    tb = t.cub_tmp.cap;
+    CK(cub::DeviceScan::ExclusiveSum(t.cub_tmp.p, tb, t.work.as<int32_t>(), t.work_prefix.as<int32_t>(), (int)(V + 1), s));
+    term_ranges_kernel<<<(unsigned)cdiv(std::max(t.grid, n_blocks) + 1, T), T, 0, s>>>(
+        t.work_prefix.as<int32_t>(), t.keys_sorted.as<int32_t>(), V, t.grid, n_blocks, block_rows,
+        t.cta_begin.as<int32_t>(), t.block_begin.as<int32_t>());
+    ctx->launches += 9;
+    CK(cudaGetLastError());
+    /* partial sums: one slot per item; a term's slots are consecutive (fixup_kernel adds them) */
+    CK(t.partial.ensure((size_t)V * kp * 4));
+    std::vector<int32_t> h_slot_begin;
+    try {
+        h_slot_begin.resize((size_t)n_tiled + 1);
+    } catch (const std::bad_alloc &) {
+        return ctx->fail(PLSA_ENOMEM, "term tiles: out of host memory");
+    }
+    for (int32_t i = 0; i <= n_tiled; ++i) h_slot_begin[(size_t)i] = i * n_blocks;
+    CK(t.slot_begin.ensure(h_slot_begin.size() * 4));
+    CK(cudaMemcpyAsync(t.slot_begin.p, h_slot_begin.data(), h_slot_begin.size() * 4, cudaMemcpyHostToDevice, s));
+    /* compact images of P(z|d) (ping-pong like A), zero behind the last row */
+    const size_t img_bytes = ((size_t)n_blocks * block_rows + TILE_MIN_ROWS) * t.pitch_f * 4;
+    for (int i = 0; i < 2; ++i) {
+        CK(t.acomp[i].ensure(img_bytes));
+        CK(cudaMemsetAsync(t.acomp[i].p, 0, img_bytes, s));
+    }
+    ctx->a_comp[0] = ctx->a_comp[1] = false;
+    CK(cudaStreamSynchronize(s)); /* h_slot_begin dies here */
+    /* the other terms: group-per-row items that skip the tiled rows */
+    int rc = ctx->device_plan
+                 ? build_items_device(ctx, ctx->t_indptr.as<int32_t>(), m, t.tail_items, chunk, align, nullptr,
+                                      t.flag.as<int32_t>())
+                 : build_items(ctx, ctx->h_tindptr, m, t.tail_items, chunk, align, nullptr, t.h_flag.data());
+    if (rc) return rc;
+    const size_t smem = (size_t)std::max<int32_t>(block_rows, TILE_MIN_ROWS) * t.pitch_f * 4;
+    CK(cudaFuncSetAttribute(pick_tile_kernel(kp, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    t.ready = true;
+    return PLSA_OK;
+}
+
+/* A[which] (padded rows) -> its compact image, the TMA source of the term pass's tiles */
+static int compact_a(plsa_ctx *ctx, int which, cudaStream_t stream)
+{
+    TermTiles &t = ctx->tterm;
+    const int64_t n = ctx->cur().n;
+    const int64_t threads = n * (ctx->kp / 4);
+    compact_rows_kernel<<<(unsigned)cdiv(threads, 256), 256, 0, stream>>>(
+        ctx->A[which].as<float>(), n, ctx->strideA, ctx->kp, t.acomp[which].as<float>(), t.pitch_f);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return PLSA_OK;
+}
+
 static void corpus_changed(plsa_ctx *ctx)
 {
     ctx->tiles.ready = false;
     ctx->tiles.tail_items.ready = false;
+    ctx->tterm.ready = false;
+    ctx->tterm.tail_items.ready = false;
     ctx->t_ready = false;
     ctx->t_weighted_ready = false;
     ctx->doc_items.ready = false;
@@ -930,6 +1183,10 @@ API int plsa_ctx_create(int device, plsa_ctx **out)
     if (ctx->n_sms <= 0) ctx->n_sms = 148;
     /* every context of the process, the one-shot entry points' included (A/B runs, tests) */
     if (const char *e = getenv("ENSTOP_B200_TILED")) ctx->tiled_opt = std::max(-1, std::min(1, atoi(e)));
+    if (const char *e = getenv("ENSTOP_B200_TERM_TILED")) ctx->term_tiled_opt = atoi(e) != 0;
+    if (const char *e = getenv("ENSTOP_B200_TERM_TILE_MIN"))
+        ctx->term_tile_min = std::max(1, std::min(100000, atoi(e)));
+    if (const char *e = getenv("ENSTOP_B200_DEVICE_PLAN")) ctx->device_plan = atoi(e) != 0;
     if (const char *e = getenv("ENSTOP_B200_TILE_KB"))
         ctx->tile_bytes = (int64_t)std::max(1, std::min(220, atoi(e))) * 1024;
     *out = ctx;
@@ -948,11 +1205,12 @@ API int plsa_ctx_destroy(plsa_ctx *ctx)
     }
     p2p_release(ctx);
     ctx->tiles.release();
+    ctx->tterm.release();
     for (DevBuf &b : ctx->scratch) b.release();
-    for (DevBuf *b : {&ctx->t_ent, &ctx->t_entw, &ctx->up_cols, &ctx->up_vals, &ctx->flag,
-                      &ctx->doc_items.items, &ctx->doc_items.split_rows, &ctx->doc_items.slot_begin,
-                      &ctx->term_items.items, &ctx->term_items.split_rows,
-                      &ctx->term_items.slot_begin, &ctx->A[0], &ctx->A[1], &ctx->B[0], &ctx->B[1],
+    ctx->doc_items.release();
+    ctx->term_items.release();
+    for (DevBuf *b : {&ctx->t_ent, &ctx->t_entw, &ctx->t_indptr, &ctx->up_cols, &ctx->up_vals, &ctx->flag,
+                      &ctx->A[0], &ctx->A[1], &ctx->B[0], &ctx->B[1],
                       &ctx->scale, &ctx->ones, &ctx->colnorm, &ctx->colpart, &ctx->partialA,
                       &ctx->partialB, &ctx->sw, &ctx->ll_part, &ctx->ll_out, &ctx->stage, &ctx->tickets,
                       &ctx->topics_dev, &ctx->ll2, &ctx->colpart2})
@@ -1253,6 +1511,7 @@ API int plsa_set_factors(plsa_ctx *ctx, const float *p_z_given_d, const float *p
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->curA = ctx->curB = 0;
     ctx->b_norm[0] = ctx->b_norm[1] = false;
+    ctx->a_comp[0] = ctx->a_comp[1] = false;
     ctx->have_factors = true;
     return PLSA_OK;
 }
@@ -1298,6 +1557,7 @@ API int plsa_set_sample_weight(plsa_ctx *ctx, const float *sample_weight)
     }
     ctx->have_sw = true;
     ctx->t_weighted_ready = false;
+    if (ctx->tterm.weighted) ctx->tterm.ready = false; /* its entries carry the old weights */
     return PLSA_OK;
 }
 
@@ -1342,30 +1602,18 @@ static int ensure_items(plsa_ctx *ctx, bool refit, int kp, bool want_doc = true)
      * and are built when that pass first runs */
     const bool need_doc = want_doc &&
                           (!ctx->doc_items.ready || ctx->doc_items.chunk != chunk ||
-                           ctx->doc_items.align != align || ctx->doc_items.order != ctx->item_order);
-    if (need_doc && !refit && !ctx->t_ready) {
-        /* the doc items are host work (plus one small copy on the second stream): build them on
-         * a helper thread while this one drives the term-major sort on the device */
-        int rc_doc = PLSA_OK;
-        const int device = ctx->device;
-        std::thread helper([&]() {
-            cudaSetDevice(device);
-            rc_doc = build_items(ctx, ctx->cur().h_indptr, ctx->cur().n, ctx->doc_items, chunk, align,
-                                 ctx->stream2);
-        });
-        rc = build_term_major(ctx);
-        helper.join();
-        if (rc_doc) return rc_doc;
-        if (rc) return rc;
-    } else if (need_doc) {
-        if ((rc = build_items(ctx, ctx->cur().h_indptr, ctx->cur().n, ctx->doc_items, chunk, align)))
-            return rc;
-    }
+                           ctx->doc_items.align != align);
+    auto make = [&](const std::vector<int32_t> &h_ptr, const int32_t *d_ptr, int64_t rows, ItemSet &set) {
+        return ctx->device_plan ? build_items_device(ctx, d_ptr, rows, set, chunk, align)
+                                : build_items(ctx, h_ptr, rows, set, chunk, align);
+    };
+    if (need_doc &&
+        (rc = make(ctx->cur().h_indptr, ctx->cur().indptr.as<int32_t>(), ctx->cur().n, ctx->doc_items)))
+        return rc;
     if (!refit) {
         if (!ctx->t_ready && (rc = build_term_major(ctx))) return rc;
-        if (!ctx->term_items.ready || ctx->term_items.chunk != chunk ||
-            ctx->term_items.align != align || ctx->term_items.order != ctx->item_order)
-            if ((rc = build_items(ctx, ctx->h_tindptr, ctx->cur().m, ctx->term_items, chunk, align)))
+        if (!ctx->term_items.ready || ctx->term_items.chunk != chunk || ctx->term_items.align != align)
+            if ((rc = make(ctx->h_tindptr, ctx->t_indptr.as<int32_t>(), ctx->cur().m, ctx->term_items)))
                 return rc;
     }
     return PLSA_OK;
@@ -1420,6 +1668,8 @@ API int plsa_prepare(plsa_ctx *ctx, int32_t refit, int32_t k)
     const bool tiled = tiled_wanted(ctx, kp);
     int rc = ensure_items(ctx, refit != 0, kp, !tiled);
     if (rc == PLSA_OK && tiled) rc = ensure_tiles(ctx, kp);
+    if (rc == PLSA_OK && tiled && !refit && ctx->term_tiled_opt != 0)
+        rc = ensure_term_tiles(ctx, kp, false); /* rebuilt by plsa_em if sample weights are in use */
     return rc;
 }
 
@@ -1433,12 +1683,24 @@ API int plsa_log_likelihood(plsa_ctx *ctx, double *ll)
 
 /* split rows of one factor (which = 0: P(z|d), normalised; 1: P(w|z)^T) on `stream` */
 static int run_fixup(plsa_ctx *ctx, int which, float *own_new, cudaStream_t stream,
-                     const ItemSet *doc_set = nullptr)
+                     const ItemSet *set = nullptr, bool with_tiled_terms = false)
 {
-    const ItemSet &is = which ? ctx->term_items : (doc_set ? *doc_set : ctx->doc_items);
-    if (is.n_split == 0) return PLSA_OK;
+    const ItemSet &is = set ? *set : (which ? ctx->term_items : ctx->doc_items);
+    if (is.n_split == 0 && !with_tiled_terms) return PLSA_OK;
     ProfScope ps(ctx, PLSA_PROF_FIXUP, stream);
     FixArgs f{}, none{};
+    if (with_tiled_terms) { /* a tiled term's row = the sum of its per-block partials, in block order */
+        const TermTiles &t = ctx->tterm;
+        none.rows = t.tiled_terms.as<int32_t>();
+        none.slot_begin = t.slot_begin.as<int32_t>();
+        none.partial = t.partial.as<float>();
+        none.own_new = own_new;
+        none.n_split = t.n_tiled;
+        none.n_heavy = t.n_blocks > 32 ? t.n_tiled : 0;
+        none.kp = ctx->kp;
+        none.stride_own = ctx->strideB;
+        none.normalise = 0;
+    }
     f.rows = is.split_rows.as<int32_t>();
     f.slot_begin = is.slot_begin.as<int32_t>();
     f.partial = which ? ctx->partialB.as<float>() : ctx->partialA.as<float>();
@@ -1448,7 +1710,8 @@ static int run_fixup(plsa_ctx *ctx, int which, float *own_new, cudaStream_t stre
     f.kp = ctx->kp;
     f.stride_own = which ? ctx->strideB : ctx->strideA;
     f.normalise = which ? 0 : 1;
-    const int blocks = f.n_heavy + (int)cdiv(f.n_split - f.n_heavy, 8);
+    const int blocks = f.n_heavy + (int)cdiv(f.n_split - f.n_heavy, 8) + none.n_heavy +
+                       (int)cdiv(none.n_split - none.n_heavy, 8);
     fixup_kernel<<<(unsigned)blocks, 256, 0, stream>>>(f, none);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -1475,7 +1738,14 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
     if (tiled && (rc = ensure_tiles(ctx, kp))) return rc;
     if (!ctx->have_sw && (rc = plsa_set_sample_weight(ctx, nullptr))) return rc;
     if (!refit && use_sample_weights && (rc = ensure_weighted_vals(ctx))) return rc;
+    /* the term pass tiled as well: (term, document block) items of the frequent terms */
+    if (tiled && !refit && ctx->term_tiled_opt != 0 &&
+        (rc = ensure_term_tiles(ctx, kp, use_sample_weights != 0)))
+        return rc;
+    const bool term_tiled = tiled && !refit && ctx->term_tiled_opt != 0 && ctx->tterm.ready &&
+                            ctx->tterm.n_items > 0;
     const ItemSet &doc_set = tiled ? ctx->tiles.tail_items : ctx->doc_items;
+    const ItemSet &term_set = term_tiled ? ctx->tterm.tail_items : ctx->term_items;
     /* products at or below the threshold are dropped (plsa.py:98-102); subnormal products
      * are dropped as well so that a surviving posterior normaliser is never subnormal */
     e_step_thresh = std::max(e_step_thresh, 1.17549435e-38f);
@@ -1487,9 +1757,13 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
         if ((rc = fill(ctx, ctx->scale.as<float>(), 2 * kp, 1.f))) return rc;
         ctx->b_norm[ctx->curB] = true;
     }
+    if (term_tiled && !ctx->a_comp[ctx->curA]) {
+        if ((rc = compact_a(ctx, ctx->curA, ctx->stream))) return rc;
+        ctx->a_comp[ctx->curA] = true;
+    }
     /* the flush-to-zero scale of the tiled pass: S = FLT_MIN / thresh (>= thresh is kept) */
     const float ftz_scale = (float)(1.17549435e-38 / (double)e_step_thresh);
-    if (!refit) CK(ctx->partialB.ensure((size_t)std::max(ctx->term_items.n_slots, 1) * kp * 4));
+    if (!refit) CK(ctx->partialB.ensure((size_t)std::max(term_set.n_slots, 1) * kp * 4));
 
     /* plsa.py:913 — the refit loop's early stop is guarded by LL > 0, which a
      * log-likelihood never satisfies: LL is evaluated there only when a trace is asked for */
@@ -1506,7 +1780,7 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
         CK(ctx->ll_part.ensure((size_t)std::max<int64_t>(pass_grid(doc_set.n_items, kp), 1) * 8));
     }
     if (!refit) { /* per-CTA column sums of the term pass and its last-arrival tickets */
-        const int64_t tgrid = pass_grid(ctx->term_items.n_items, kp);
+        const int64_t tgrid = pass_grid(term_set.n_items, kp);
         CK(ctx->colpart.ensure((size_t)(tgrid + tgrid / 32 + 2) * kp * 8));
         if (ctx->tickets.cap < (size_t)(tgrid / 32 + 8) * 4) {
             CK(ctx->tickets.ensure((size_t)(tgrid / 32 + 8) * 4 * 2));
@@ -1553,10 +1827,8 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
      * same stop decision. */
     const bool sharded = ctx->shard != nullptr; /* one rank: same path, empty collectives */
     const int colsum_grid = 148;
-    if (sharded) {
-        CK(ctx->ll2.ensure(16));
-        CK(ctx->colpart2.ensure((size_t)colsum_grid * kp * 8));
-    }
+    if (sharded) CK(ctx->ll2.ensure(16));
+    if (sharded || term_tiled) CK(ctx->colpart2.ensure((size_t)colsum_grid * kp * 8));
     /* Peer-memory path (plsa_shard_p2p_*): the term pass writes into this rank's exchange
      * buffer and ONE kernel per rank adds the ranks' buffers over NVLink and takes the column
      * sums (shard_reduce_kernel); otherwise NCCL all-reduce + separate column sums. */
@@ -1588,12 +1860,14 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                 h.own_old = ctx->A[ctx->curA].as<float>();
                 h.tile_src = t.img[ctx->curB].as<float>();
                 h.partial_out = t.head_sum.as<float>();
-                h.n_rows = c.n;
-                h.tile_rows = t.tile_rows;
+                h.n_items = c.n;
+                h.src_rows = t.tile_rows;
+                h.block_rows = t.tile_rows;
+                h.n_blocks = 1;
                 h.stride_own = ctx->strideA;
                 h.kp = kp;
                 h.ftz_scale = ftz_scale;
-                h.inv_ftz_scale = 1.f / ftz_scale;
+                h.log2_ftz_scale = std::log2((double)ftz_scale);
                 if (fused_now) {
                     h.row_weight = ctx->sw.as<float>();
                     h.cta_partial = t.ll_part.as<double>();
@@ -1603,6 +1877,7 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                     CK(cudaMemsetAsync(ctx->flag.p, 0, 4, ctx->stream));
                 }
                 const size_t smem = (size_t)std::max<int32_t>(t.tile_rows, TILE_MIN_ROWS) * t.pitch_f * 4;
+                ProfScope ph(ctx, PLSA_PROF_DOC_HEAD);
                 pick_tile_kernel(kp, fused_now)<<<ctx->n_sms, TILE_THREADS, smem, ctx->stream>>>(h);
                 ctx->launches++;
                 CK(cudaGetLastError());
@@ -1643,12 +1918,38 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
             if (fused_now && sharded) CK(cudaEventRecord(ctx->ev_a, s1)); /* doc pass done */
         }
         if ((rc = run_fixup(ctx, 0, ctx->A[nA].as<float>(), s1, &doc_set))) return rc;
+        if (term_tiled && (rc = compact_a(ctx, nA, s1))) return rc; /* next iteration's tiles */
         if (!refit) {
             {   /* E-step + M-step of P(w|z): plsa.py:91-105, :189-193 (P(w|z) part) */
                 ProfScope ps(ctx, PLSA_PROF_WORD_PASS, s2);
+                if (term_tiled) { /* frequent terms: P(z|d) blocks in shared memory */
+                    TermTiles &t = ctx->tterm;
+                    TileArgs h{};
+                    h.order = t.order.as<int32_t>();
+                    h.indptr = t.head_indptr.as<int32_t>();
+                    h.ent = t.head_ent.as<int2>();
+                    h.own_row = t.own_row.as<int32_t>();
+                    h.own_old = ctx->B[ctx->curB].as<float>();
+                    h.tile_src = t.acomp[ctx->curA].as<float>();
+                    h.partial_out = t.partial.as<float>();
+                    h.cta_begin = t.cta_begin.as<int32_t>();
+                    h.block_begin = t.block_begin.as<int32_t>();
+                    h.n_items = t.n_items;
+                    h.src_rows = c.n;
+                    h.block_rows = t.block_rows;
+                    h.n_blocks = t.n_blocks;
+                    h.stride_own = ctx->strideB;
+                    h.kp = kp;
+                    h.ftz_scale = ftz_scale;
+                    const size_t smem = (size_t)std::max<int32_t>(t.block_rows, TILE_MIN_ROWS) * t.pitch_f * 4;
+                    ProfScope ph(ctx, PLSA_PROF_TERM_HEAD, s2);
+                    pick_tile_kernel(kp, false)<<<t.grid, TILE_THREADS, smem, s2>>>(h);
+                    ctx->launches++;
+                    CK(cudaGetLastError());
+                }
                 PassArgs a{};
-                a.items = ctx->term_items.items.as<Item>();
-                a.n_items = ctx->term_items.n_items;
+                a.items = term_set.items.as<Item>();
+                a.n_items = term_set.n_items;
                 a.ent = use_sample_weights ? ctx->t_entw.as<int2>() : ctx->t_ent.as<int2>();
                 a.own_old = ctx->B[ctx->curB].as<float>();
                 a.gat_old = ctx->A[ctx->curA].as<float>();
@@ -1661,7 +1962,8 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                 a.partial = ctx->partialB.as<float>();
                 a.gat_tex = ctx->texA[ctx->curA];
                 /* plsa.py:196-198: per-topic normaliser of the new P(w|z), applied lazily */
-                a.cta_partial = ctx->colpart.as<double>();
+                /* (tiled term pass: the column sums are taken from the finished matrix instead) */
+                a.cta_partial = term_tiled ? nullptr : ctx->colpart.as<double>();
                 a.ticket = ctx->tickets.as<unsigned int>() + 1; /* [0] is the log-likelihood's */
                 a.scale_out = tiled ? ctx->tiles.scale_raw.as<float>() + (size_t)nB * kp
                                     : reinterpret_cast<float *>(ctx->scale.p) + (size_t)nB * kp;
@@ -1670,14 +1972,25 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                 a.stride_gat = ctx->strideA;
                 a.kp = kp;
                 a.thresh = e_step_thresh;
-                if ((rc = launch_pass(ctx, MODE_TERM, a, ctx->term_items.align > 1, s2))) return rc;
+                if ((rc = launch_pass(ctx, MODE_TERM, a, term_set.align > 1, s2))) return rc;
             }
-            /* split rows: ordered sums of their chunk partials */
+            /* split rows: ordered sums of their chunk partials (and, tiled, of the tiled terms'
+             * per-block partials) */
             if ((rc = run_fixup(ctx, 1,
                                 p2p ? reinterpret_cast<float *>(ctx->p2p.block.as<char>() +
                                                                 ((ctx->p2p.seq + 1) & 1u) * ctx->p2p.part_bytes)
-                                    : ctx->B[nB].as<float>(), s2)))
+                                    : ctx->B[nB].as<float>(), s2, &term_set, term_tiled)))
                 return rc;
+            if (term_tiled && c.m > 0) { /* plsa.py:196-198: column sums of the finished matrix */
+                ProfScope ps(ctx, PLSA_PROF_NORMALIZE, s2);
+                colsum_partial_kernel<<<colsum_grid, 256, 0, s2>>>(ctx->B[nB].as<float>(), c.m, ctx->strideB, kp,
+                                                                  ctx->colpart2.as<double>());
+                colsum_final_kernel<<<1, 256, 0, s2>>>(ctx->colpart2.as<double>(), colsum_grid, kp,
+                                                       ctx->tiles.scale_raw.as<float>() + (size_t)nB * kp,
+                                                       ctx->colnorm.as<double>());
+                ctx->launches += 2;
+                CK(cudaGetLastError());
+            }
             if (tiled) { /* plsa.py:196-198 applied now, not lazily: B[nB] *= scale, + tile image */
                 ProfScope ps(ctx, PLSA_PROF_NORMALIZE, s2);
                 if ((rc = normalise_b(ctx, nB, ctx->tiles.scale_raw.as<float>() + (size_t)nB * kp, s2)))
@@ -1766,6 +2079,7 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
             ctx->b_norm[nB] = tiled;
         }
         ctx->curA = nA;
+        ctx->a_comp[nA] = term_tiled;
         done = i + 1;
         if (want_ll && !fuse && i % n_iter_per_test == 0) { /* plsa.py:630-638 / :909-918 */
             double cur = 0.0;
@@ -1867,6 +2181,11 @@ API int plsa_set_option(plsa_ctx *ctx, const char *name, int64_t value)
         ctx->p2p.timeout_ms = value;
         return PLSA_OK;
     }
+    if (!strcmp(name, "device_plan")) { /* 0: plan the work items on the host (the CPU-testable twin) */
+        ctx->device_plan = value != 0;
+        ctx->doc_items.ready = ctx->term_items.ready = ctx->tiles.tail_items.ready = false;
+        return PLSA_OK;
+    }
     if (!strcmp(name, "vec_entries")) {
         ctx->vec_entries = value != 0; /* item sets are rebuilt on the next prepare / em */
         return PLSA_OK;
@@ -1876,35 +2195,41 @@ API int plsa_set_option(plsa_ctx *ctx, const char *name, int64_t value)
         ctx->tiled_opt = (int)value;
         return PLSA_OK;
     }
+    if (!strcmp(name, "term_tiled")) { /* with "tiled": the term pass reads P(z|d) blocks from shared memory too */
+        ctx->term_tiled_opt = value != 0;
+        return PLSA_OK;
+    }
+    if (!strcmp(name, "term_tile_min")) { /* average entries per (term, block) item for a term to be tiled */
+        if (value < 1 || value > 100000) return ctx->fail(PLSA_EINVAL, "term_tile_min: 1..100000");
+        ctx->term_tile_min = value;
+        ctx->tterm.ready = false;
+        return PLSA_OK;
+    }
     if (!strcmp(name, "tile_kb")) { /* shared memory of the tile, per CTA */
         if (value < 1 || value > 220) return ctx->fail(PLSA_EINVAL, "tile_kb: 1..220");
         ctx->tile_bytes = value * 1024;
         ctx->tiles.ready = false;
-        return PLSA_OK;
-    }
-    if (!strcmp(name, "item_order")) { /* 0 row, 1 window, 2 band: see plan_items */
-        if (value < 0 || value > 2) return ctx->fail(PLSA_EINVAL, "item_order: 0, 1 or 2");
-        ctx->item_order = (int)value; /* item sets are rebuilt on the next prepare / em */
+        ctx->tterm.ready = false;
         return PLSA_OK;
     }
     return ctx->fail(PLSA_EINVAL, std::string("unknown option: ") + name);
 }
 
 /* Host-only view of the work-item plan of a pass (no device needed): lets the CPU tests check
- * that the items of either order cover every stored entry exactly once. */
+ * that the items cover every stored entry exactly once. */
 API int plsa_plan_items(const int32_t *indptr, int64_t rows, int64_t chunk, int32_t align,
-                        int32_t order, int64_t cap, int64_t *start, int32_t *row, int32_t *len,
+                        int64_t cap, int64_t *start, int32_t *row, int32_t *len,
                         int32_t *slot, int32_t *skip, int64_t *n_items, int32_t *n_split,
                         int32_t *n_slots)
 {
     if (!indptr || rows < 0 || chunk < 1 || align < 1 || (align & (align - 1)) || chunk < align ||
-        order < 0 || order > 2 || !n_items) {
+        !n_items) {
         g_err = "plan_items: bad argument";
         return PLSA_EINVAL;
     }
     ItemPlan plan;
     try {
-        plan_items(indptr, rows, chunk, align, order, plan);
+        plan_items(indptr, rows, chunk, align, plan);
     } catch (const std::bad_alloc &) {
         g_err = "plan_items: out of host memory";
         return PLSA_ENOMEM;
@@ -1920,6 +2245,48 @@ API int plsa_plan_items(const int32_t *indptr, int64_t rows, int64_t chunk, int3
         if (len) len[i] = it.len;
         if (slot) slot[i] = it.slot;
         if (skip) skip[i] = it.skip & 0xffff;
+    }
+    return PLSA_OK;
+}
+
+/* Read back the work items a context holds on the device (which: 0 doc pass, 1 term pass,
+ * 2 tail part of the tiled doc pass) together with the row pointers they were planned from,
+ * so that a test can compare the device planner with plsa_plan_items. */
+API int plsa_debug_items(plsa_ctx *ctx, int32_t which, int64_t cap, int64_t *start, int32_t *row,
+                         int32_t *len, int32_t *slot, int32_t *skip, int64_t *n_items, int32_t *n_split,
+                         int32_t *n_slots, int64_t *chunk, int32_t *align, int32_t *indptr_out,
+                         int64_t indptr_cap)
+{
+    CHECK_CTX(ctx);
+    const ItemSet &is = which == 0 ? ctx->doc_items : which == 1 ? ctx->term_items : ctx->tiles.tail_items;
+    if (!is.ready || !n_items) return ctx->fail(PLSA_EINVAL, "debug_items: item set not built");
+    *n_items = is.n_items;
+    if (n_split) *n_split = is.n_split;
+    if (n_slots) *n_slots = is.n_slots;
+    if (chunk) *chunk = is.chunk;
+    if (align) *align = is.align;
+    const int64_t w = std::min<int64_t>(cap, is.n_items);
+    if (w > 0) {
+        std::vector<Item> h;
+        try {
+            h.resize((size_t)w);
+        } catch (const std::bad_alloc &) {
+            return ctx->fail(PLSA_ENOMEM, "debug_items: out of host memory");
+        }
+        CK(cudaMemcpy(h.data(), is.items.p, (size_t)w * sizeof(Item), cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < w; ++i) {
+            if (start) start[i] = h[(size_t)i].start;
+            if (row) row[i] = h[(size_t)i].row;
+            if (len) len[i] = h[(size_t)i].len;
+            if (slot) slot[i] = h[(size_t)i].slot;
+            if (skip) skip[i] = h[(size_t)i].skip & 0xffff;
+        }
+    }
+    if (indptr_out && indptr_cap > 0) {
+        const DevBuf &src = which == 0 ? ctx->cur().indptr : which == 1 ? ctx->t_indptr : ctx->tiles.tail_indptr;
+        const int64_t rows = which == 1 ? ctx->cur().m : ctx->cur().n;
+        CK(cudaMemcpy(indptr_out, src.p, (size_t)std::min<int64_t>(indptr_cap, rows + 1) * 4,
+                      cudaMemcpyDeviceToHost));
     }
     return PLSA_OK;
 }

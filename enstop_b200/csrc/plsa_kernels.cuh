@@ -144,28 +144,12 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
-/* Experiment (build with -DPLSA_EXP_FTZ_THRESH=1, off by default): the threshold of
- * plsa.py:98-102 without compare/select instructions.  The owned row is scaled by a power of
- * two S <= FLT_MIN / thresh, so a product at or below the threshold becomes subnormal and the
- * flush-to-zero multiply drops it; the posterior v / sum(v) and the M-step sums do not see
- * the common factor, the log-likelihood subtracts log2(S).  Exact scaling; the products that
- * are dropped are those below T = FLT_MIN / S, thresh <= T < 2 thresh (the reference drops
- * v <= thresh).  8 of the 33 instructions per stored entry go away.  Known edge: a surviving
- * normaliser can be as small as FLT_MIN, so x / norm overflows (and is clamped) for an entry
- * with count x > 4 whose true normaliser lies in [T, T x / 4) — entries the reference keeps at
- * full weight although they sit a hair above its own cut-off. */
-#ifndef PLSA_EXP_FTZ_THRESH
-#define PLSA_EXP_FTZ_THRESH 0
-#endif
+/* flush-to-zero product: the tiled pass (plsa_tile.cuh) applies the E-step threshold with it */
 __device__ __forceinline__ f32x2 mul2_ftz(f32x2 a, f32x2 b)
 {
     f32x2 r;
     asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
-}
-__device__ __forceinline__ float ftz_thresh_scale(float thresh)
-{   /* largest power of two <= FLT_MIN / thresh (thresh >= FLT_MIN: at most 1) */
-    return __int_as_float(__float_as_int(1.17549435e-38f / thresh) & 0x7f800000);
 }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
 {
@@ -363,8 +347,7 @@ __device__ __forceinline__ void pass_block(const PassArgs &a, const int2 (&e)[U]
                                            const char *gat_base, const uint32_t (&lane_off)[KV],
                                            uint32_t stride_bytes, const float4 (&own)[KV],
                                            float4 (&acc)[KV], double &ll_acc, float &min_norm,
-                                           float rw, float thresh, int j, int gbase, bool lane_on,
-                                           float ll_shift = 0.f /* log2(S), FTZ experiment */)
+                                           float rw, float thresh, int j, int gbase, bool lane_on)
 {
     float4 g[U][KV];
     float llt[U]; /* log-likelihood terms of the block (MODE_LOGLIK / MODE_DOC_LL) */
@@ -401,15 +384,7 @@ __device__ __forceinline__ void pass_block(const PassArgs &a, const int2 (&e)[U]
 #pragma unroll
         for (int q = 0; q < KV; ++q) {
             float4 v;
-#if PLSA_PACKED_MATH && PLSA_EXP_FTZ_THRESH
-            if constexpr (MODE != MODE_LOGLIK) { /* the owned row carries S: see above */
-                upk2(mul2_ftz(pk2(g[u][q].x, g[u][q].y), own2[q][0]), v.x, v.y);
-                upk2(mul2_ftz(pk2(g[u][q].z, g[u][q].w), own2[q][1]), v.z, v.w);
-            } else {
-                upk2(mul2(pk2(g[u][q].x, g[u][q].y), own2[q][0]), v.x, v.y);
-                upk2(mul2(pk2(g[u][q].z, g[u][q].w), own2[q][1]), v.z, v.w);
-            }
-#elif PLSA_PACKED_MATH
+#if PLSA_PACKED_MATH
             upk2(mul2(pk2(g[u][q].x, g[u][q].y), own2[q][0]), v.x, v.y);
             upk2(mul2(pk2(g[u][q].z, g[u][q].w), own2[q][1]), v.z, v.w);
 #else
@@ -418,7 +393,7 @@ __device__ __forceinline__ void pass_block(const PassArgs &a, const int2 (&e)[U]
             v.z = g[u][q].z * own[q].z;
             v.w = g[u][q].w * own[q].w;
 #endif
-            if constexpr (MODE != MODE_LOGLIK && !(PLSA_PACKED_MATH && PLSA_EXP_FTZ_THRESH)) { /* plsa.py:98-102 */
+            if constexpr (MODE != MODE_LOGLIK) { /* plsa.py:98-102 */
                 v.x = v.x > thresh ? v.x : 0.f;
                 v.y = v.y > thresh ? v.y : 0.f;
                 v.z = v.z > thresh ? v.z : 0.f;
@@ -441,11 +416,7 @@ __device__ __forceinline__ void pass_block(const PassArgs &a, const int2 (&e)[U]
              * the block's terms are added in float32, blocks in float64. */
             float lg; /* fused pass: the sum is 0 or a normal float (thresholded products), so the
                          flush-to-zero MUFU.LG2 needs no subnormal pre-scaling branch */
-#if PLSA_PACKED_MATH && PLSA_EXP_FTZ_THRESH
-            if constexpr (MODE == MODE_DOC_LL) lg = (log2_ftz(norm) - ll_shift) * 0.69314718f;
-#else
             if constexpr (MODE == MODE_DOC_LL) lg = log2_ftz(norm) * 0.69314718f;
-#endif
             else lg = __logf(norm);
             llt[u] = (x != 0.f) ? x * rw * lg : 0.f;
             /* idle lanes (32 % G of them) shadow the last group with a zero owned row: their
@@ -495,21 +466,12 @@ __device__ __forceinline__ void pass_block(const PassArgs &a, const int2 (&e)[U]
 /* entries of an item in flight = the entry block aligned items start on */
 __host__ __device__ constexpr int pass_block_entries(int KV) { return (KV >= 4) ? 1 : (KV == 2) ? 2 : 4; }
 
-/* CTA shape of the row pass: 8 warps, 4 CTAs per SM at 64 registers (KV == 1).  The macros
- * exist for occupancy experiments (scripts/build_variants.sh); the host side launches with
- * PLSA_PASS_THREADS and sizes the grid from it. */
-#ifndef PLSA_PASS_THREADS
-#define PLSA_PASS_THREADS 256
-#endif
-#ifndef PLSA_PASS_MIN_CTAS
-#define PLSA_PASS_MIN_CTAS 4
-#endif
-static_assert(PLSA_PASS_THREADS == 256 || PLSA_PASS_THREADS == 128, "row pass: 4 or 8 warps per CTA");
+/* CTA shape of the row pass: 8 warps, 4 CTAs per SM at 64 registers (KV == 1).  128-thread
+ * CTAs at 9 per SM (36 resident warps) were measured slower (profiles/r2a_ab_c2.txt). */
+constexpr int PLSA_PASS_THREADS = 256;
 
 template <int G, int KV, int MODE, bool TEX, bool VEC>
-__global__ void __launch_bounds__(PLSA_PASS_THREADS,
-                                  (KV == 1) ? PLSA_PASS_MIN_CTAS
-                                            : ((KV == 2) ? 2 : 1) * (256 / PLSA_PASS_THREADS))
+__global__ void __launch_bounds__(PLSA_PASS_THREADS, (KV == 1) ? 4 : (KV == 2) ? 2 : 1)
     row_pass_kernel(const PassArgs a)
 {
     constexpr int NG = 32 / G;
@@ -555,17 +517,6 @@ __global__ void __launch_bounds__(PLSA_PASS_THREADS,
     }
     float rw = 1.f;
     if constexpr (MODE == MODE_LOGLIK || MODE == MODE_DOC_LL) rw = has ? a.row_weight[it.row] : 0.f;
-    float ll_shift = 0.f, norm_scale = 1.f;
-#if PLSA_PACKED_MATH && PLSA_EXP_FTZ_THRESH
-    if constexpr (MODE != MODE_LOGLIK) {
-        norm_scale = ftz_thresh_scale(a.thresh);
-        ll_shift = log2_ftz(norm_scale); /* exact: a power of two */
-#pragma unroll
-        for (int q = 0; q < KV; ++q)
-            own[q] = make_float4(own[q].x * norm_scale, own[q].y * norm_scale,
-                                 own[q].z * norm_scale, own[q].w * norm_scale);
-    }
-#endif
 
     const int2 *ent = a.ent + it.start;
     const int len = it.len;
@@ -592,7 +543,7 @@ __global__ void __launch_bounds__(PLSA_PASS_THREADS,
         load_entries<U, VEC>(ent + base + U, en);
         pass_block<G, KV, U, MODE, TEX, true>(a, e, base, len, gat_base, lane_off, stride_bytes,
                                               own, acc, ll_acc, min_norm, rw, thresh, j, gbase,
-                                              lane_on, ll_shift);
+                                              lane_on);
 #pragma unroll
         for (int u = 0; u < U; ++u) e[u] = en[u];
     }
@@ -600,7 +551,7 @@ __global__ void __launch_bounds__(PLSA_PASS_THREADS,
     if constexpr (MODE == MODE_LOGLIK || MODE == MODE_DOC_LL) {
         if (!(j == 0 && lane_on)) ll_acc = 0.0; /* one lane per item contributes */
         if constexpr (MODE == MODE_DOC_LL)
-            if (min_norm < PLSA_FUSED_LL_MIN_NORM * norm_scale) *a.flag = 1;
+            if (min_norm < PLSA_FUSED_LL_MIN_NORM) *a.flag = 1;
     }
     if constexpr (MODE == MODE_LOGLIK) {
         finish_loglik(a, ll_acc);
@@ -637,7 +588,9 @@ __global__ void __launch_bounds__(PLSA_PASS_THREADS,
                         acc[q].x * inv, acc[q].y * inv, acc[q].z * inv, acc[q].w * inv);
             }
         }
-        if constexpr (MODE == MODE_TERM) finish_colsum<G, KV>(a, acc, lane, warp, j, lane_on);
+        if constexpr (MODE == MODE_TERM) { /* nullptr: the column sums are taken elsewhere (tiled term pass) */
+            if (a.cta_partial != nullptr) finish_colsum<G, KV>(a, acc, lane, warp, j, lane_on);
+        }
         if constexpr (MODE == MODE_DOC_LL) finish_loglik(a, ll_acc);
     }
 }
@@ -1134,6 +1087,100 @@ __global__ void gather_rows_kernel(const int32_t *__restrict__ src, int64_t n_ne
     const int32_t len = base_indptr[src[r] + 1] - b0;
     const int32_t o0 = new_indptr[r];
     for (int32_t p = lane; p < len; p += 32) ent[o0 + p] = base_ent[b0 + p];
+}
+
+/* ---- work items, planned on the device (same plan as the host's plan_items) ------------------
+ * A row of `span` entries (its stored entries plus the lead-in up to the previous multiple of
+ * `align`) is one item, or — longer than `chunk` — nc equal pieces of `per` entries.  Split rows
+ * with more than 32 pieces are "heavy" (fixup_kernel gives them a CTA); partial-sum slots are
+ * numbered heavy rows first, in row order. */
+struct PlanRow { int32_t pieces, per, lead, span; };
+__device__ __forceinline__ PlanRow plan_row(const int32_t *indptr, int64_t r, int32_t chunk, int32_t align,
+                                            const int32_t *skip_row)
+{
+    PlanRow p;
+    p.lead = indptr[r] & (align - 1);
+    p.span = indptr[r + 1] - indptr[r] + p.lead;
+    if (skip_row && skip_row[r]) { /* the row is served elsewhere (tiled term pass): no item */
+        p.pieces = 0;
+        p.per = 0;
+        p.span = 0;
+    } else if (p.span <= chunk) {
+        p.pieces = 1;
+        p.per = p.span;
+    } else {
+        const int32_t nc = (p.span + chunk - 1) / chunk;
+        const int32_t eq = (p.span + nc - 1) / nc;
+        p.per = min(chunk, (eq + align - 1) / align * align);
+        p.pieces = (p.span + p.per - 1) / p.per;
+    }
+    return p;
+}
+
+/* per row: pieces, heavy / light flags and their piece counts (inputs of five exclusive scans) */
+__global__ void plan_count_kernel(const int32_t *__restrict__ indptr, int64_t rows, int32_t chunk,
+                                  int32_t align, const int32_t *__restrict__ skip_row,
+                                  int32_t *__restrict__ pieces,
+                                  int32_t *__restrict__ heavy, int32_t *__restrict__ light,
+                                  int32_t *__restrict__ heavy_pieces, int32_t *__restrict__ light_pieces)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > rows) return;
+    if (r == rows) { /* the scans run over rows + 1 elements: the last one yields the totals */
+        pieces[r] = heavy[r] = light[r] = heavy_pieces[r] = light_pieces[r] = 0;
+        return;
+    }
+    const PlanRow p = plan_row(indptr, r, chunk, align, skip_row);
+    const bool split = p.span > chunk, hv = split && p.pieces > 32;
+    pieces[r] = p.pieces;
+    heavy[r] = hv;
+    light[r] = split && !hv;
+    heavy_pieces[r] = hv ? p.pieces : 0;
+    light_pieces[r] = (split && !hv) ? p.pieces : 0;
+}
+
+/* the items in row order (pieces of a row adjacent) with their sort keys, and the split-row list */
+__global__ void plan_emit_kernel(const int32_t *__restrict__ indptr, int64_t rows, int32_t chunk,
+                                 int32_t align, const int32_t *__restrict__ skip_row,
+                                 const int32_t *__restrict__ item_at,
+                                 const int32_t *__restrict__ heavy_at, const int32_t *__restrict__ light_at,
+                                 const int32_t *__restrict__ heavy_slot, const int32_t *__restrict__ light_slot,
+                                 Item *__restrict__ items, int32_t *__restrict__ keys,
+                                 int32_t *__restrict__ split_rows, int32_t *__restrict__ slot_begin)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const PlanRow p = plan_row(indptr, r, chunk, align, skip_row);
+    const int32_t n_heavy = heavy_at[rows], heavy_slots = heavy_slot[rows];
+    const bool split = p.span > chunk, hv = split && p.pieces > 32;
+    const int64_t s = (int64_t)indptr[r] - p.lead;
+    int32_t first_slot = -1;
+    if (split) {
+        first_slot = hv ? heavy_slot[r] : heavy_slots + light_slot[r];
+        const int32_t pos = hv ? heavy_at[r] : n_heavy + light_at[r];
+        split_rows[pos] = (int32_t)r;
+        slot_begin[pos] = first_slot;
+    }
+    if (r == rows - 1) /* closing entry: total number of slots */
+        slot_begin[n_heavy + light_at[rows]] = heavy_slots + light_slot[rows];
+    const int32_t at = item_at[r];
+    for (int32_t c = 0; c < p.pieces; ++c) {
+        Item it;
+        it.start = s + (int64_t)c * p.per;
+        it.row = (int32_t)r;
+        it.len = min(p.per, p.span - c * p.per);
+        it.slot = split ? first_slot + c : -1;
+        it.skip = (c == 0) ? (p.lead | (split ? ITEM_FIRST : 0)) : 0;
+        items[at + c] = it;
+        keys[at + c] = chunk - it.len; /* ascending key = longest first */
+    }
+}
+
+__global__ void plan_gather_kernel(const Item *__restrict__ in, const int32_t *__restrict__ perm,
+                                   int64_t n, Item *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[perm[i]];
 }
 
 __global__ void fill_kernel(float *p, int64_t n, float v)

@@ -37,21 +37,29 @@ constexpr int TILE_MIN_ROWS = 8;                  /* padding entries address slo
 __host__ __device__ constexpr int tile_pitch_chunks(int kc) { return kc | 1; } /* odd */
 
 struct TileArgs {
-    const int32_t *order;     /* [n_rows] rows by padded head length, longest first        */
-    const int32_t *indptr;    /* [n_rows + 1] head CSR; every row length is a multiple of 8 */
-    const int2 *ent;          /* head entries {tile slot, value bits}                      */
-    const float *own_old;     /* [rows, stride_own]                                        */
-    const float *tile_src;    /* [max(tile_rows, 8), pitch] compact image of the hot rows  */
-    float *partial_out;       /* [rows, kp] raw M-step sums of the head entries            */
-    const float *row_weight;  /* LL: sample_weight[d]                                      */
-    double *cta_partial;      /* LL: [grid]                                                */
-    unsigned int *ticket;     /* LL: zeroed counter                                        */
-    double *ll_out;           /* LL: log-likelihood of the head entries                    */
-    int *flag;                /* LL: raised when a normaliser is too small to trust        */
-    int64_t n_rows;
-    int32_t tile_rows, stride_own, kp;
-    float ftz_scale;          /* S = FLT_MIN / thresh                                      */
-    float inv_ftz_scale;      /* 1 / S                                                     */
+    const int32_t *order;     /* [n_items] work items (rows of the tiled CSR) in launch order:
+                                 doc side by padded length, longest first; term side by tile
+                                 block, then by length                                       */
+    const int32_t *indptr;    /* [n_items + 1] tiled CSR; every row length is a multiple of 8 */
+    const int2 *ent;          /* entries {slot inside the tile, value bits}                  */
+    const int32_t *own_row;   /* [n_items] factor row an item owns; nullptr: the item's number */
+    const float *own_old;     /* [rows, stride_own]                                          */
+    const float *tile_src;    /* compact image of the gathered factor, [*, pitch]; block b of
+                                 the tile starts at row b * block_rows                        */
+    float *partial_out;       /* [n_items, kp] raw M-step sums of each item                  */
+    const int32_t *cta_begin; /* [grid + 1] ranges into `order`, one per CTA (equal work);
+                                 nullptr: batches of four items dealt round-robin to all warps */
+    const int32_t *block_begin; /* [n_blocks + 1] ranges into `order`; nullptr: one block     */
+    const float *row_weight;  /* LL: sample_weight[d]                                        */
+    double *cta_partial;      /* LL: [grid]                                                  */
+    unsigned int *ticket;     /* LL: zeroed counter                                          */
+    double *ll_out;           /* LL: log-likelihood of the tiled entries                     */
+    int *flag;                /* LL: raised when a normaliser is too small to trust          */
+    int64_t n_items;
+    int64_t src_rows;         /* rows of the gathered factor (last block may be short)       */
+    int32_t block_rows, n_blocks, stride_own, kp;
+    float ftz_scale;          /* S = FLT_MIN / thresh                                        */
+    double log2_ftz_scale;    /* LL: log2(S), subtracted once per item in double             */
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -115,11 +123,100 @@ __device__ __forceinline__ int octet_fold(float (&a)[K], int li, int &first)
     return n;
 }
 
+/* four items (one per octet of the warp) starting at item `first`, items at or past `limit`
+ * are idle */
+template <int KC, bool LL>
+__device__ __forceinline__ void tile_batch(const TileArgs &a, const float4 *tile, int64_t first,
+                                           int64_t limit, int li, int oct, double &ll_acc,
+                                           float &min_norm)
+{
+    constexpr int PC = tile_pitch_chunks(KC);
+    constexpr int K = 4 * KC;
+    const int64_t i = first + oct;
+    const bool has = i < limit;
+    int item = 0, row = 0, start = 0, len = 0;
+    if (has) {
+        item = a.order[i];
+        row = a.own_row ? a.own_row[item] : item;
+        start = a.indptr[item];
+        len = a.indptr[item + 1] - start;
+    }
+    int maxlen = len;
+    maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, 8));
+    maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, 16));
+    if (maxlen == 0) { /* items without entries still own a (zero) partial */
+        if (has)
+            for (int z = li; z < a.kp; z += 8) a.partial_out[(int64_t)item * a.kp + z] = 0.f;
+        return;
+    }
+    f32x2 own2[2 * KC], acc2[2 * KC];
+#pragma unroll
+    for (int c = 0; c < KC; ++c) {
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has) o = ldg_f4(a.own_old + (int64_t)row * a.stride_own + 4 * c);
+        own2[2 * c] = pk2(o.x * a.ftz_scale, o.y * a.ftz_scale);
+        own2[2 * c + 1] = pk2(o.z * a.ftz_scale, o.w * a.ftz_scale);
+        acc2[2 * c] = 0ull;
+        acc2[2 * c + 1] = 0ull;
+    }
+    float ll_row = 0.f, x_sum = 0.f; /* LL: sum of x * log2(scaled normaliser), sum of x */
+    const int2 *ent = a.ent + start + li;
+    int2 e = (len > 0) ? __ldg(ent) : make_int2(li, 0);
+    for (int t = 0; t < maxlen; t += 8) {
+        /* one step ahead; past the item's end: own residue class, value 0 */
+        const int2 en = (t + 8 < len) ? __ldg(ent + t + 8) : make_int2(li, 0);
+        float4 g[KC];
+#pragma unroll
+        for (int c = 0; c < KC; ++c) g[c] = tile[e.x * PC + c];
+        const float x = __int_as_float(e.y);
+        f32x2 v[2 * KC];
+#pragma unroll
+        for (int c = 0; c < KC; ++c) {
+            v[2 * c] = mul2_ftz(pk2(g[c].x, g[c].y), own2[2 * c]);
+            v[2 * c + 1] = mul2_ftz(pk2(g[c].z, g[c].w), own2[2 * c + 1]);
+        }
+        f32x2 s = add2(v[0], v[1]);
+#pragma unroll
+        for (int c = 1; c < KC; ++c) s = add2(s, add2(v[2 * c], v[2 * c + 1]));
+        float s_lo, s_hi;
+        upk2(s, s_lo, s_hi);
+        const float norm = s_lo + s_hi;
+        if constexpr (LL) {
+            /* plsa.py:383-384; x == 0 marks padding.  The sum carries S: log2(S) * sum of x is
+             * taken off per item in double (a float correction per entry would be biased) */
+            ll_row += (x != 0.f) ? x * log2_ftz(norm) : 0.f;
+            x_sum += x;
+            min_norm = fminf(min_norm, (x != 0.f) ? norm : 3.0e38f);
+        }
+        const float cf = fminf(x * rcp_fast(norm), 3.0e38f); /* see pass_block */
+        const f32x2 c2 = pk2(cf, cf);
+#pragma unroll
+        for (int q = 0; q < 2 * KC; ++q) acc2[q] = fma2(c2, v[q], acc2[q]);
+        e = en;
+    }
+    if constexpr (LL) {
+        /* same float ln 2 as __logf / the group-per-row pass, so that the paths agree */
+        if (has)
+            ll_acc += ((double)ll_row - a.log2_ftz_scale * (double)x_sum) * (double)0.69314718f *
+                      (double)a.row_weight[row];
+    }
+    float acc[K];
+#pragma unroll
+    for (int q = 0; q < 2 * KC; ++q) upk2(acc2[q], acc[2 * q], acc[2 * q + 1]);
+    int first_topic;
+    const int nv = octet_fold<K>(acc, li, first_topic);
+    if (has) {
+        float *dst = a.partial_out + (int64_t)item * a.kp + first_topic;
+#pragma unroll
+        for (int q = 0; q < (K + 7) / 8; ++q)
+            if (q < nv && first_topic + q < a.kp) dst[q] = acc[q];
+    }
+}
+
 template <int KC, bool LL>
 __global__ void __launch_bounds__(TILE_THREADS, 1) tile_pass_kernel(const TileArgs a)
 {
     constexpr int PC = tile_pitch_chunks(KC);
-    constexpr int K = 4 * KC;
     constexpr int NW = TILE_THREADS / 32;
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -128,100 +225,57 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) tile_pass_kernel(const TileAr
     const float4 *tile = reinterpret_cast<const float4 *>(tile_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, li = lane & 7, oct = lane >> 3;
 
-    /* stage the tile: one elected thread arms the barrier with the byte count and issues the
-     * TMA bulk copies; everybody waits on the barrier's phase */
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t bytes = (uint32_t)max(a.tile_rows, TILE_MIN_ROWS) * PC * 16u;
-        mbar_expect_tx(&bar, bytes);
-        for (uint32_t off = 0; off < bytes; off += 32768u)
-            bulk_g2s(tile_smem + off, reinterpret_cast<const char *>(a.tile_src) + off,
-                     min(bytes - off, 32768u), &bar);
-    }
-    mbar_wait(&bar, 0);
+    uint32_t phase = 0;
+    /* stage block `b` of the gathered factor: one elected thread arms the barrier with the byte
+     * count and issues the TMA bulk copies; everybody waits on the barrier's phase */
+    auto load_tile = [&](int b) {
+        if (threadIdx.x == 0) {
+            const int64_t r0 = (int64_t)b * a.block_rows;
+            const int rows = (int)min((int64_t)a.block_rows, a.src_rows - r0);
+            const uint32_t bytes = (uint32_t)max(rows, TILE_MIN_ROWS) * PC * 16u;
+            /* shared memory the generic proxy has read is about to be written by the async proxy */
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&bar, bytes);
+            const char *src = reinterpret_cast<const char *>(a.tile_src) + r0 * (PC * 16);
+            for (uint32_t off = 0; off < bytes; off += 32768u)
+                bulk_g2s(tile_smem + off, src + off, min(bytes - off, 32768u), &bar);
+        }
+        mbar_wait(&bar, phase);
+        phase ^= 1u;
+    };
 
-    const int64_t n_batches = (a.n_rows + 3) >> 2;
-    const int64_t gw = (int64_t)blockIdx.x * NW + warp, GW = (int64_t)gridDim.x * NW;
     double ll_acc = 0.0;
     float min_norm = 3.0e38f;
-    for (int64_t b = gw; b < n_batches; b += GW) {
-        const int64_t i = b * 4 + oct;
-        const bool has = i < a.n_rows;
-        int row = 0, start = 0, len = 0;
-        if (has) {
-            row = a.order[i];
-            start = a.indptr[row];
-            len = a.indptr[row + 1] - start;
-        }
-        int maxlen = len;
-        maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, 8));
-        maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, 16));
-        if (maxlen == 0) { /* rows without head entries still own a (zero) partial */
-            if (has)
-                for (int z = li; z < a.kp; z += 8) a.partial_out[(int64_t)row * a.kp + z] = 0.f;
-            continue;
-        }
-        f32x2 own2[2 * KC], acc2[2 * KC];
-#pragma unroll
-        for (int c = 0; c < KC; ++c) {
-            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has) o = ldg_f4(a.own_old + (int64_t)row * a.stride_own + 4 * c);
-            own2[2 * c] = pk2(o.x * a.ftz_scale, o.y * a.ftz_scale);
-            own2[2 * c + 1] = pk2(o.z * a.ftz_scale, o.w * a.ftz_scale);
-            acc2[2 * c] = 0ull;
-            acc2[2 * c + 1] = 0ull;
-        }
-        float ll_row = 0.f;
-        const int2 *ent = a.ent + start + li;
-        int2 e = (len > 0) ? __ldg(ent) : make_int2(li, 0);
-        for (int t = 0; t < maxlen; t += 8) {
-            /* one step ahead; past the item's end: own residue class, value 0 */
-            const int2 en = (t + 8 < len) ? __ldg(ent + t + 8) : make_int2(li, 0);
-            float4 g[KC];
-#pragma unroll
-            for (int c = 0; c < KC; ++c) g[c] = tile[e.x * PC + c];
-            const float x = __int_as_float(e.y);
-            f32x2 v[2 * KC];
-#pragma unroll
-            for (int c = 0; c < KC; ++c) {
-                v[2 * c] = mul2_ftz(pk2(g[c].x, g[c].y), own2[2 * c]);
-                v[2 * c + 1] = mul2_ftz(pk2(g[c].z, g[c].w), own2[2 * c + 1]);
+    if (a.cta_begin == nullptr) {
+        /* one block for everybody; batches dealt round-robin over all warps of the grid: with
+         * the items sorted by length every warp gets the same work to within its last batch */
+        load_tile(0);
+        const int64_t gw = (int64_t)blockIdx.x * NW + warp, GW = (int64_t)gridDim.x * NW;
+        for (int64_t b = gw * 4; b < a.n_items; b += GW * 4)
+            tile_batch<KC, LL>(a, tile, b, a.n_items, li, oct, ll_acc, min_norm);
+    } else {
+        /* this CTA's range of items, cut at tile-block boundaries; a new block = a new tile */
+        const int lo = a.cta_begin[blockIdx.x], hi = a.cta_begin[blockIdx.x + 1];
+        int blk = 0;
+        if (a.block_begin) /* first block whose range ends behind lo */
+            while (blk + 1 < a.n_blocks && a.block_begin[blk + 1] <= lo) ++blk;
+        bool first_tile = true;
+        for (int cur = lo; cur < hi;) {
+            const int seg_end = a.block_begin ? min(hi, a.block_begin[blk + 1]) : hi;
+            if (seg_end > cur) {
+                if (!first_tile) __syncthreads(); /* everybody is done with the previous tile */
+                first_tile = false;
+                load_tile(blk);
+                for (int64_t b = cur + warp * 4; b < seg_end; b += NW * 4)
+                    tile_batch<KC, LL>(a, tile, b, seg_end, li, oct, ll_acc, min_norm);
+                cur = seg_end;
             }
-            f32x2 s = add2(v[0], v[1]);
-#pragma unroll
-            for (int c = 1; c < KC; ++c) s = add2(s, add2(v[2 * c], v[2 * c + 1]));
-            float s_lo, s_hi;
-            upk2(s, s_lo, s_hi);
-            const float norm = s_lo + s_hi;
-            if constexpr (LL) {
-                /* plsa.py:383-384 on the unscaled sum; x == 0 marks padding */
-                const float lg = log2_ftz(norm * a.inv_ftz_scale) * 0.69314718f;
-                ll_row += (x != 0.f) ? x * lg : 0.f;
-                min_norm = fminf(min_norm, (x != 0.f) ? norm : 3.0e38f);
-            }
-            const float cf = fminf(x * rcp_fast(norm), 3.0e38f); /* see pass_block */
-            const f32x2 c2 = pk2(cf, cf);
-#pragma unroll
-            for (int q = 0; q < 2 * KC; ++q) acc2[q] = fma2(c2, v[q], acc2[q]);
-            e = en;
-        }
-        if constexpr (LL) {
-            if (has) ll_acc += (double)ll_row * (double)a.row_weight[row];
-        }
-        float acc[K];
-#pragma unroll
-        for (int q = 0; q < 2 * KC; ++q) upk2(acc2[q], acc[2 * q], acc[2 * q + 1]);
-        int first;
-        const int nv = octet_fold<K>(acc, li, first);
-        if (has) {
-            float *dst = a.partial_out + (int64_t)row * a.kp + first;
-#pragma unroll
-            for (int q = 0; q < (K + 7) / 8; ++q)
-                if (q < nv && first + q < a.kp) dst[q] = acc[q];
+            ++blk;
         }
     }
     if constexpr (LL) {
@@ -266,21 +320,35 @@ __global__ void tile_slot_kernel(const int32_t *__restrict__ sorted_cols, int32_
     if (s < tile_rows) slot_of[sorted_cols[s]] = s;
 }
 
-/* per row: padded length of its head part (8 x the largest residue class) and its tail length;
- * one warp per row */
-__global__ void tile_count_kernel(const int32_t *__restrict__ indptr, int64_t n_rows,
-                                  const int2 *__restrict__ ent, const int32_t *__restrict__ slot_of,
+/* Slot of an entry inside its item's tile.  Doc side: the tile holds the most frequent terms,
+ * slot_of[term] (< 0: not in the tile, the entry goes to the tail).  Term side: an item is one
+ * (term, block of documents) pair and the tile holds that block's rows of P(z|d): slot =
+ * document - first document of the block. */
+struct SlotMap {
+    const int32_t *slot_of; /* doc side */
+    int32_t n_blocks, block_rows; /* term side (slot_of == nullptr): item v covers block v % n_blocks */
+    __device__ __forceinline__ int operator()(int64_t item, int col) const
+    {
+        if (slot_of) return slot_of[col];
+        return col - (int)(item % n_blocks) * block_rows;
+    }
+};
+
+/* per item: padded length of its tiled part (8 x the largest residue class) and its tail
+ * length; one warp per item; item r covers entries [beg[r], end[r]) */
+__global__ void tile_count_kernel(const int32_t *__restrict__ beg, const int32_t *__restrict__ end,
+                                  int64_t n_items, const int2 *__restrict__ ent, const SlotMap map,
                                   int32_t *__restrict__ head_len, int32_t *__restrict__ tail_len)
 {
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (r >= n_rows) return;
+    if (r >= n_items) return;
     const int lane = threadIdx.x & 31;
-    const int32_t p0 = indptr[r], p1 = indptr[r + 1];
+    const int32_t p0 = beg[r], p1 = end[r];
     int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int head = 0;
     for (int32_t p = p0; p < p1; p += 32) {
         const bool ok = p + lane < p1;
-        const int s = ok ? slot_of[ent[p + lane].x] : -1;
+        const int s = ok ? map(r, ent[p + lane].x) : -1;
 #pragma unroll
         for (int q = 0; q < 8; ++q) cnt[q] += __popc(__ballot_sync(0xffffffffu, s >= 0 && (s & 7) == q));
         head += __popc(__ballot_sync(0xffffffffu, s >= 0));
@@ -290,23 +358,24 @@ __global__ void tile_count_kernel(const int32_t *__restrict__ indptr, int64_t n_
     for (int q = 0; q < 8; ++q) mx = max(mx, cnt[q]);
     if (lane == 0) {
         head_len[r] = 8 * mx;
-        tail_len[r] = (p1 - p0) - head;
+        if (tail_len) tail_len[r] = (p1 - p0) - head;
     }
 }
 
-/* write the head rows (steps of 8 slots, position p of a step = an entry with slot = p mod 8 or
- * padding {p, 0}) and the tail rows (original order); one warp per row */
-__global__ void tile_place_kernel(const int32_t *__restrict__ indptr, int64_t n_rows,
-                                  const int2 *__restrict__ ent, const int32_t *__restrict__ slot_of,
+/* write the tiled rows (steps of 8 slots, position p of a step = an entry with slot = p mod 8 or
+ * padding {p, 0}) and the tail rows (original order); one warp per item.  `weight` (term side,
+ * sample weights): values are multiplied by weight[column] (plsa.py:293-297). */
+__global__ void tile_place_kernel(const int32_t *__restrict__ beg, const int32_t *__restrict__ end,
+                                  int64_t n_items, const int2 *__restrict__ ent, const SlotMap map,
                                   const int32_t *__restrict__ head_indptr,
                                   const int32_t *__restrict__ tail_indptr, int2 *__restrict__ head_ent,
-                                  int2 *__restrict__ tail_ent)
+                                  int2 *__restrict__ tail_ent, const float *__restrict__ weight)
 {
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (r >= n_rows) return;
+    if (r >= n_items) return;
     const int lane = threadIdx.x & 31;
-    const int32_t p0 = indptr[r], p1 = indptr[r + 1];
-    const int32_t h0 = head_indptr[r], h1 = head_indptr[r + 1], t0 = tail_indptr[r];
+    const int32_t p0 = beg[r], p1 = end[r];
+    const int32_t h0 = head_indptr[r], h1 = head_indptr[r + 1], t0 = tail_indptr ? tail_indptr[r] : 0;
     for (int32_t h = h0 + lane; h < h1; h += 32) head_ent[h] = make_int2((h - h0) & 7, 0);
     __syncwarp();
     int base[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -318,7 +387,8 @@ __global__ void tile_place_kernel(const int32_t *__restrict__ indptr, int64_t n_
         int s = -1;
         if (ok) {
             e = ent[p + lane];
-            s = slot_of[e.x];
+            s = map(r, e.x);
+            if (weight) e.y = __float_as_int(__int_as_float(e.y) * weight[e.x]);
         }
         int rank = 0;
 #pragma unroll
@@ -330,10 +400,113 @@ __global__ void tile_place_kernel(const int32_t *__restrict__ indptr, int64_t n_
         const unsigned mt = __ballot_sync(0xffffffffu, ok && s < 0);
         if (ok) {
             if (s >= 0) head_ent[h0 + rank * 8 + (s & 7)] = make_int2(s, e.y);
-            else tail_ent[t0 + tbase + __popc(mt & lt)] = e;
+            else if (tail_ent) tail_ent[t0 + tbase + __popc(mt & lt)] = e;
         }
         tbase += __popc(mt);
     }
+}
+
+/* ---- term side: which terms are tiled, and their (term, document block) items ---------------- */
+/* a term is tiled when it has at least `min_count` entries (an average item then has enough
+ * entries to amortise its owned row and its partial sum) */
+__global__ void term_tiled_flag_kernel(const int32_t *__restrict__ tindptr, int64_t m, int32_t min_count,
+                                       int32_t *__restrict__ flag)
+{
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w > m) return;
+    flag[w] = (w < m && tindptr[w + 1] - tindptr[w] >= min_count) ? 1 : 0;
+}
+
+/* item v = (tiled term ti, block b): its range of term-major entries (documents ascending inside
+ * a term: binary search for the block's first document), the term it owns, its sort key
+ * (block-major, inside a block longest first) */
+__global__ void term_items_kernel(const int32_t *__restrict__ tindptr, int64_t m,
+                                  const int32_t *__restrict__ flag, const int32_t *__restrict__ tiled_at,
+                                  const int2 *__restrict__ t_ent, int32_t n_blocks, int32_t block_rows,
+                                  int32_t *__restrict__ beg, int32_t *__restrict__ end,
+                                  int32_t *__restrict__ own_row, int32_t *__restrict__ tiled_terms)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m * n_blocks) return;
+    const int64_t w = i / n_blocks;
+    const int b = (int)(i - w * n_blocks);
+    if (!flag[w]) return;
+    const int32_t ti = tiled_at[w];
+    auto lower = [&](int32_t doc) { /* first entry of term w with document >= doc */
+        int32_t lo = tindptr[w], hi = tindptr[w + 1];
+        while (lo < hi) {
+            const int32_t mid = (lo + hi) >> 1;
+            if (t_ent[mid].x < doc) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    const int64_t v = (int64_t)ti * n_blocks + b;
+    beg[v] = lower(b * block_rows);
+    end[v] = (b + 1 == n_blocks) ? tindptr[w + 1] : lower((b + 1) * block_rows);
+    own_row[v] = (int32_t)w;
+    if (b == 0) tiled_terms[ti] = (int32_t)w;
+}
+
+/* sort key of an item: block-major, inside a block longest first (len is a multiple of 8,
+ * at most block_rows) */
+__global__ void term_item_keys_kernel(const int32_t *__restrict__ head_len, int64_t n_items,
+                                      int32_t n_blocks, int32_t block_rows, int32_t *__restrict__ keys)
+{
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_items) return;
+    const int per = block_rows / 8 + 1;
+    keys[v] = (int32_t)(v % n_blocks) * per + (block_rows / 8 - head_len[v] / 8);
+}
+
+/* work of the items in launch order (padded entries + a per-item constant), input of the scan
+ * that cuts the launch order into one range per CTA */
+__global__ void term_work_kernel(const int32_t *__restrict__ order, const int32_t *__restrict__ head_len,
+                                 int64_t n_items, int32_t *__restrict__ work)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n_items) return;
+    work[i] = (i < n_items) ? head_len[order[i]] + 24 : 0;
+}
+
+/* cta_begin[c] = first item whose work prefix reaches c / grid of the total; block_begin[b] =
+ * first item (in launch order) of block b */
+__global__ void term_ranges_kernel(const int32_t *__restrict__ work_prefix, const int32_t *__restrict__ sorted_keys,
+                                   int64_t n_items, int32_t grid, int32_t n_blocks, int32_t block_rows,
+                                   int32_t *__restrict__ cta_begin, int32_t *__restrict__ block_begin)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t <= grid) {
+        const int64_t total = work_prefix[n_items];
+        const int64_t target = total * t / grid;
+        int64_t lo = 0, hi = n_items;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (work_prefix[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        cta_begin[t] = (t == grid) ? (int32_t)n_items : (int32_t)lo;
+    }
+    if (t <= n_blocks) {
+        const int per = block_rows / 8 + 1;
+        const int32_t key = t * per;
+        int64_t lo = 0, hi = n_items;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (sorted_keys[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        block_begin[t] = (int32_t)lo;
+    }
+}
+
+/* padded [rows, stride] -> compact [rows, pitch] (the TMA source of the term side's tiles) */
+__global__ void compact_rows_kernel(const float *__restrict__ src, int64_t rows, int stride, int kp,
+                                    float *__restrict__ dst, int pitch_f)
+{
+    const int nv = kp >> 2;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * nv) return;
+    const int64_t r = i / nv;
+    const int c = (int)(i - r * nv);
+    reinterpret_cast<float4 *>(dst + r * pitch_f)[c] = reinterpret_cast<const float4 *>(src + r * stride)[c];
 }
 
 /* P(w|z)^T rows times the per-topic scale, in place (plsa.py:196-198), and the compact image

@@ -120,7 +120,11 @@ int plsa_last_em_ms(const plsa_ctx *ctx, float *ms);
 #define PLSA_PROF_FIXUP 2      /* ordered sums of split rows (both factors)            */
 #define PLSA_PROF_NORMALIZE 3  /* sharded fit: all-reduce of P(w|z) + its column sums   */
 #define PLSA_PROF_LOGLIK 4     /* log-likelihood pass                                  */
-#define PLSA_PROF_SLOTS 5
+#define PLSA_PROF_DOC_HEAD 5   /* tiled doc pass: the shared-memory tile kernel alone (also
+                                  counted in PLSA_PROF_DOC_PASS)                        */
+#define PLSA_PROF_TERM_HEAD 6  /* tiled term pass: the tile kernel alone (also counted in
+                                  PLSA_PROF_WORD_PASS)                                  */
+#define PLSA_PROF_SLOTS 7
 int plsa_set_profiling(plsa_ctx *ctx, int32_t on);
 int plsa_get_profile(plsa_ctx *ctx, double *ms /*[PLSA_PROF_SLOTS]*/,
                      int64_t *launches /*[PLSA_PROF_SLOTS]*/);
@@ -130,10 +134,10 @@ int plsa_launch_count(const plsa_ctx *ctx, int64_t *launches);
  * are split),
  * "texture" (1: gather factor rows through the texture pipe when they fit, 0: plain loads),
  * "fuse_ll" (1: the periodic log-likelihood rides on the next doc pass, 0: separate pass),
- * "item_order" (launch order of same-length work items: 0 = chunks of a split row adjacent,
- * 1 = chunks that cover the same window of gathered rows adjacent, for L1 reuse inside a CTA,
- * 2 = all chunks first in bands of positions, for L2 reuse when the gathered factor exceeds
- * the L2; the sums are the same in all orders). */
+ * "tiled" (-1: automatic by corpus size, 0: never, 1: wherever possible — the doc pass reads
+ * the rows of the most frequent terms from a TMA-staged shared-memory tile, csrc/plsa_tile.cuh),
+ * "tile_kb" (shared memory of that tile per CTA, 1..220),
+ * "p2p_timeout_ms" (sharded fit: bound of a rank's wait for a peer's partial sums). */
 int plsa_set_option(plsa_ctx *ctx, const char *name, int64_t value);
 /* Host-only (no device): the work items a pass over a CSR with these row pointers would launch,
  * in launch order.  A row longer than `chunk` entries is cut into equal chunks that write
@@ -141,9 +145,16 @@ int plsa_set_option(plsa_ctx *ctx, const char *name, int64_t value);
  * `align` entries and its first `skip` entries belong to the row before.  Writes at most
  * `cap` items into the optional arrays; *n_items is the full count. */
 int plsa_plan_items(const int32_t *indptr, int64_t rows, int64_t chunk, int32_t align,
-                    int32_t order, int64_t cap, int64_t *start, int32_t *row, int32_t *len,
+                    int64_t cap, int64_t *start, int32_t *row, int32_t *len,
                     int32_t *slot, int32_t *skip, int64_t *n_items, int32_t *n_split,
                     int32_t *n_slots);
+
+/* Test hook: the work items the context holds on the device (which: 0 doc pass, 1 term pass,
+ * 2 tail part of the tiled doc pass) and the row pointers they were planned from. */
+int plsa_debug_items(plsa_ctx *ctx, int32_t which, int64_t cap, int64_t *start, int32_t *row,
+                     int32_t *len, int32_t *slot, int32_t *skip, int64_t *n_items, int32_t *n_split,
+                     int32_t *n_slots, int64_t *chunk, int32_t *align, int32_t *indptr_out,
+                     int64_t indptr_cap);
 
 /* ---- host helper: the reference's seeded random initialisation, faster ------------------------ */
 /* plsa.py:454-456 + :510-511 + :709-710: draw rows*cols doubles from a numpy legacy

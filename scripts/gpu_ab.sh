@@ -1,14 +1,13 @@
 #!/bin/bash
-# A/B of row-pass variants on one box: usage gpu_ab.sh CONFIG "LIB VEC CHUNK [TEX [ORDER]]" ...
-# ORDER: work-item launch order (0 row, 1 window; plsa_set_option "item_order")
+# A/B of row-pass variants on one box: usage gpu_ab.sh CONFIG "LIB VEC CHUNK [TEX]" ...
 # LIB: d = enstop_b200/libplsa_b200.so, anything else = build/libplsa_<LIB>.so
 mkdir -p gpurun_out
 export ENSTOP_B200_CORPUS_CACHE=${ENSTOP_B200_CORPUS_CACHE:-/dev/shm}   # generate each corpus once per box
 CFG=$1; shift
-for V in "$@"; do set -- $V; L=$1; VEC=$2; C=$3; TX=${4:-1}; ORD=${5:-0}
+for V in "$@"; do set -- $V; L=$1; VEC=$2; C=$3; TX=${4:-1}
   LIBP=""; [ "$L" != "d" ] && LIBP=$PWD/build/libplsa_$L.so
-  TAG=${CFG}_${L}_v${VEC}_c${C}_t${TX}_o${ORD}
-  ENSTOP_B200_LIB=$LIBP ENSTOP_B200_TEXTURE=$TX ENSTOP_B200_VEC=$VEC ENSTOP_B200_CHUNK=$C ENSTOP_B200_ITEM_ORDER=$ORD timeout ${AB_TIMEOUT:-300} python bench.py --config $CFG --steps 50 --warmup 3 --no-cpu-baseline --profile-iters 10 --e2e-repeats 1 > gpurun_out/ab_$TAG.json 2> gpurun_out/ab_$TAG.err
+  TAG=${CFG}_${L}_v${VEC}_c${C}_t${TX}
+  ENSTOP_B200_LIB=$LIBP ENSTOP_B200_TEXTURE=$TX ENSTOP_B200_VEC=$VEC ENSTOP_B200_CHUNK=$C timeout ${AB_TIMEOUT:-300} python bench.py --config $CFG --steps 50 --warmup 3 --no-cpu-baseline --profile-iters 10 --e2e-repeats 1 > gpurun_out/ab_$TAG.json 2> gpurun_out/ab_$TAG.err
   python - <<PY
 import json
 try:

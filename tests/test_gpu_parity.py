@@ -361,3 +361,27 @@ def test_errors_are_codes_not_aborts():
             ctx.bootstrap(bad)
     with pytest.raises(_lib.PlsaError):
         _lib.Context(10_000)
+
+
+@pytest.mark.parametrize("chunk", [0, 32, 100])
+def test_device_plan_is_the_host_plan(chunk, golden_c1_planted):
+    """Work items planned on the device (plan_count / plan_emit kernels + stable radix sort) are
+    the host planner's, item for item, for the doc pass, the term pass and the tiled tail."""
+    g, X = golden_c1_planted
+    with _lib.Context(0) as ctx:
+        ctx.set_option("tiled", 1)
+        ctx.set_option("tile_kb", 40)      # a small tile, so that a tail exists
+        if chunk:
+            ctx.set_option("chunk", chunk)
+        ctx.upload_csr(X)
+        ctx.prepare(10, False)
+        ctx.set_factors(g["pzd0"], g["pwz0"])
+        ctx.log_likelihood()               # builds the doc items (lazy in tiled mode)
+        for which in (0, 1, 2):
+            d = ctx.debug_items(which)
+            h = _lib.plan_items(d["indptr"], d["chunk"], align=d["align"])
+            assert d["n_split"] == h["n_split"] and d["n_slots"] == h["n_slots"]
+            for key in ("start", "row", "len", "slot", "skip"):
+                assert np.array_equal(d[key], h[key]), (which, key)
+        tail = ctx.debug_items(2)
+        assert 0 < tail["indptr"][-1] < X.nnz

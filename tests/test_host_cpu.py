@@ -198,24 +198,18 @@ def _ragged_indptr(rng, rows, long_rows):
 
 
 @pytest.mark.parametrize("chunk,align", [(256, 4), (32, 4), (64, 1), (2048, 2), (100, 4)])
-@pytest.mark.parametrize("order", [0, 1, 2])
-def test_work_item_plan_covers_every_entry_once(chunk, align, order):
-    """plan_items (host side of the row pass, csrc/plsa_b200.cu): in either launch order the
+def test_work_item_plan_covers_every_entry_once(chunk, align):
+    """plan_items (host side of the row pass, csrc/plsa_b200.cu): the
     items tile the stored entries exactly, chunks of a split row own consecutive slots, items
     start on entry-block boundaries and are sorted longest first."""
-    rng = np.random.default_rng(chunk * 7 + align + order)
+    rng = np.random.default_rng(chunk * 7 + align)
     indptr = _ragged_indptr(rng, 3000, 12)
-    p = _lib.plan_items(indptr, chunk, align=align, order=order)
+    p = _lib.plan_items(indptr, chunk, align=align)
     start, row, ln, slot, skip = p["start"], p["row"], p["len"], p["slot"], p["skip"]
     eff = chunk // align * align
     assert np.all(ln <= eff) and np.all(ln >= 0) and np.all(skip >= 0) and np.all(skip < align)
     assert np.all(start % align == 0)
-    if order < 2:
-        assert np.all(np.diff(ln) <= 0), "items must be sorted by length, longest first"
-    else:   # band order: every chunk ahead of every whole row, whole rows longest first
-        n_chunks = int(np.sum(slot >= 0))
-        assert np.all(slot[:n_chunks] >= 0) and np.all(slot[n_chunks:] < 0)
-        assert np.all(np.diff(ln[n_chunks:]) <= 0)
+    assert np.all(np.diff(ln) <= 0), "items must be sorted by length, longest first"
     # every stored entry is covered by exactly one item of its own row
     cover = np.zeros(int(indptr[-1]), dtype=np.int32)
     owner = np.full(int(indptr[-1]), -1, dtype=np.int64)
@@ -240,39 +234,11 @@ def test_work_item_plan_covers_every_entry_once(chunk, align, order):
         assert np.all(skip[by_start][1:] == 0)
 
 
-def test_work_item_orders_hold_the_same_items():
-    """The window order only permutes same-length items; and it does put chunks that sit at the
-    same position of their rows next to each other."""
+def test_work_item_plan_rejects_bad_alignment():
     rng = np.random.default_rng(11)
-    indptr = _ragged_indptr(rng, 2000, 40)
-    a = _lib.plan_items(indptr, 256, align=4, order=0)
-    b = _lib.plan_items(indptr, 256, align=4, order=1)
-    key = lambda p: sorted(zip(p["start"].tolist(), p["row"].tolist(), p["len"].tolist(),
-                               p["slot"].tolist(), p["skip"].tolist()))
-    assert key(a) == key(b)
-    assert a["n_slots"] == b["n_slots"] and a["n_split"] == b["n_split"]
-    assert np.array_equal(a["len"], b["len"])
-    # relative position of a chunk inside its row, for runs of equal-length chunks
-    def positions(p):
-        span = (indptr[p["row"] + 1] - (indptr[p["row"]] & ~3)).astype(np.float64)
-        return (p["start"] - (indptr[p["row"]] & ~3)) / np.maximum(span, 1.0)
-    chunks_b = b["slot"] >= 0
-    pos_b, len_b = positions(b)[chunks_b], b["len"][chunks_b]
-    same = len_b[1:] == len_b[:-1]
-    assert np.all(np.diff(pos_b)[same] >= -1.0 / 4096 - 1e-12)
+    indptr = _ragged_indptr(rng, 200, 40)
     with pytest.raises(_lib.PlsaError):
-        _lib.plan_items(indptr, 256, align=3, order=0)
-    # band order: the same items again; the band (1/32 of the row) never decreases along the
-    # chunks, and inside a band the lengths never increase
-    c = _lib.plan_items(indptr, 256, align=4, order=2)
-    assert key(c) == key(a)
-    chunks_c = c["slot"] >= 0
-    band = np.floor(positions(c)[chunks_c] * 4096).astype(np.int64) // 128
-    assert np.all(np.diff(band) >= 0)
-    same_band = band[1:] == band[:-1]
-    assert np.all(np.diff(c["len"][chunks_c])[same_band] <= 0)
-    with pytest.raises(_lib.PlsaError):
-        _lib.plan_items(indptr, 256, align=4, order=3)
+        _lib.plan_items(indptr, 256, align=3)
 
 
 def _emulate_pass(indptr, idx, val, own, gat, plan, thresh, normalise):
@@ -306,10 +272,9 @@ def _emulate_pass(indptr, idx, val, own, gat, plan, thresh, normalise):
     return own_new
 
 
-@pytest.mark.parametrize("order", [0, 1, 2])
-def test_planned_passes_are_one_em_iteration(order):
+def test_planned_passes_are_one_em_iteration():
     """Host-side plan semantics end to end on the CPU: a doc pass and a term pass carried out
-    item by item from plsa_plan_items (both launch orders, aligned items, split rows), with
+    item by item from plsa_plan_items (aligned items, split rows), with
     the lazily normalised P(w|z), equal one EM iteration of the oracle's float64
     restatement of plsa_fit_inner."""
     X = synth.make_corpus(400, 300, 14_000, seed=9, planted=True, k_true=4).astype(np.float64)
@@ -320,8 +285,8 @@ def test_planned_passes_are_one_em_iteration(order):
     Xt = X.T.tocsr()
     Xt.sort_indices()
     thresh = 1e-32
-    plan_d = _lib.plan_items(X.indptr, 32, align=4, order=order)
-    plan_t = _lib.plan_items(Xt.indptr, 32, align=4, order=order)
+    plan_d = _lib.plan_items(X.indptr, 32, align=4)
+    plan_t = _lib.plan_items(Xt.indptr, 32, align=4)
     assert plan_d["n_split"] > 0 and plan_t["n_split"] > 0
     new_pzd = _emulate_pass(X.indptr, X.indices, X.data, pzd, pwz.T.copy(), plan_d, thresh, True)
     raw = _emulate_pass(Xt.indptr, Xt.indices, Xt.data, pwz.T.copy(), pzd, plan_t, thresh, False)
