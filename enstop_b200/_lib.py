@@ -67,6 +67,7 @@ SIGNATURES = {
     "plsa_set_option": (ctypes.c_int, [_ctx, ctypes.c_char_p, _i64]),
     "plsa_plan_items": (ctypes.c_int, [_i32p, _i64, _i64, _i32, _i64, _i64p, _i32p, _i32p,
                                        _i32p, _i32p, _i64p, _i32p, _i32p]),
+    "plsa_gathered_distances": (ctypes.c_int, [_ctx, _i32, _f64p, _i64p]),
     "plsa_debug_items": (ctypes.c_int, [_ctx, _i32, _i64, _i64p, _i32p, _i32p, _i32p, _i32p, _i64p,
                                         _i32p, _i32p, _i64p, _i32p, _i32p, _i64]),
     "plsa_host_random_rows": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint32), _i32p, _i64, _i64, _f32p,
@@ -526,6 +527,17 @@ def topic_distances(topics, kind, device=0):
     code = {"hellinger": 0, "kl": 1}[kind]
     check(lib().plsa_topic_distances(int(device), _ptr(topics, _f32p), n, m, code,
                                      _ptr(out, _f64p)))
+    return out
+
+
+def gathered_distances(ctx, kind):
+    """All-pairs distances ("hellinger" / "kl") of the topic stack the last gather left on
+    ``ctx``'s device (rows in the gather's own order: context / rank major)."""
+    n = _i64(0)
+    code = {"hellinger": 0, "kl": 1}[kind]
+    check(lib().plsa_gathered_distances(ctx._h, code, None, ctypes.byref(n)), ctx._h)
+    out = np.zeros((n.value, n.value), dtype=np.float64)
+    check(lib().plsa_gathered_distances(ctx._h, code, _ptr(out, _f64p), ctypes.byref(n)), ctx._h)
     return out
 
 

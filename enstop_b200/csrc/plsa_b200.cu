@@ -108,17 +108,17 @@ struct TileSet {
     bool ready = false;
     int32_t kp = 0, tile_rows = 0, pitch_f = 0;
     int64_t n = 0, head_slots = 0, tail_nnz = 0;
-    DevBuf col_count, col_ids, col_count_sorted, col_sorted, slot_of, head_len, tail_len,
+    DevBuf col_count, col_ids, col_count_sorted, col_sorted, slot_of, head_len, head_mem, tail_len,
         head_indptr, tail_indptr, head_ent, tail_ent, order, order_keys, row_ids, cub_tmp, head_sum,
-        img[2], scale_raw, ll_part, ll_head, ll_ticket;
+        img[2], scale_raw, ll_part, ll_head, ll_ticket, headers;
     std::vector<int32_t> h_tail_indptr;
     ItemSet tail_items;
     void release()
     {
-        for (DevBuf *b : {&col_count, &col_ids, &col_count_sorted, &col_sorted, &slot_of, &head_len,
+        for (DevBuf *b : {&col_count, &col_ids, &col_count_sorted, &col_sorted, &slot_of, &head_len, &head_mem,
                           &tail_len, &head_indptr, &tail_indptr, &head_ent, &tail_ent, &order,
                           &order_keys, &row_ids, &cub_tmp, &head_sum, &img[0], &img[1], &scale_raw,
-                          &ll_part, &ll_head, &ll_ticket})
+                          &ll_part, &ll_head, &ll_ticket, &headers})
             b->release();
         tail_items.release();
         ready = false;
@@ -133,16 +133,16 @@ struct TermTiles {
     bool ready = false, weighted = false;
     int32_t kp = 0, block_rows = 0, n_blocks = 0, n_tiled = 0, pitch_f = 0, grid = 0;
     int64_t n = 0, m = 0, n_items = 0, head_slots = 0;
-    DevBuf flag, tiled_at, tiled_terms, beg, end, own_row, head_len, head_indptr, head_ent, keys,
+    DevBuf flag, tiled_at, tiled_terms, beg, end, own_row, head_len, head_mem, head_indptr, head_ent, keys,
         keys_sorted, ids, order, work, work_prefix, cta_begin, block_begin, partial, slot_begin, cub_tmp,
-        acomp[2];
+        acomp[2], headers;
     std::vector<int32_t> h_flag;
     ItemSet tail_items;
     void release()
     {
-        for (DevBuf *b : {&flag, &tiled_at, &tiled_terms, &beg, &end, &own_row, &head_len, &head_indptr,
+        for (DevBuf *b : {&flag, &tiled_at, &tiled_terms, &beg, &end, &own_row, &head_len, &head_mem, &head_indptr,
                           &head_ent, &keys, &keys_sorted, &ids, &order, &work, &work_prefix, &cta_begin,
-                          &block_begin, &partial, &slot_begin, &cub_tmp, &acomp[0], &acomp[1]})
+                          &block_begin, &partial, &slot_begin, &cub_tmp, &acomp[0], &acomp[1], &headers})
             b->release();
         tail_items.release();
         ready = false;
@@ -171,10 +171,11 @@ struct plsa_ctx {
     ItemSet doc_items, term_items;
     TileSet tiles;
     TermTiles tterm;
-    int term_tiled_opt = 1;             /* option "term_tiled": tile the term pass too (with "tiled") */
+    int term_tiled_opt = 0;             /* option "term_tiled": tile the term pass too (with "tiled") */
     int64_t term_tile_min = 12;         /* option "term_tile_min": entries per (term, block) item, on average, for a term to be tiled */
     bool a_comp[2] = {false, false};    /* tterm.acomp[i] is the compact image of A[i] */
-    int tiled_opt = -1;                 /* option "tiled": -1 auto, 0 off, 1 on where possible */
+    int tiled_opt = 0;                  /* option "tiled": -1 by corpus size, 0 off (default: measured no faster
+                                           at C2, profiles/r2_kernel_experiments.md), 1 on where possible */
     int64_t tile_bytes = 200 * 1024;    /* option "tile_kb": shared memory of the tile        */
     bool b_norm[2] = {false, false};    /* B[i] is column-normalised in place, tiles.img[i] holds its tile rows */
     int n_sms = 0;
@@ -205,6 +206,8 @@ struct plsa_ctx {
     int32_t k = 0, kp = 0, strideA = 0, strideB = 0;
     DevBuf A[2], B[2], scale, ones, colnorm, colpart, partialA, partialB;
     DevBuf sw, ll_part, ll_out, stage, topics_dev, tickets;
+    DevBuf gathered;                /* stack of topic matrices the last gather brought to this device */
+    int64_t gathered_n = 0, gathered_m = 0;
     int32_t stash_slots = 0;
     size_t stash_per = 0;
     int curA = 0, curB = 0;
@@ -853,6 +856,7 @@ static int ensure_tiles(plsa_ctx *ctx, int kp)
                                                  t.col_count_sorted.as<int32_t>(), t.col_ids.as<int32_t>(),
                                                  t.col_sorted.as<int32_t>(), (int)m, 0, 32, s));
     CK(t.head_len.ensure((size_t)(n + 1) * 4));
+    CK(t.head_mem.ensure((size_t)(n + 1) * 4));
     CK(t.tail_len.ensure((size_t)(n + 1) * 4));
     CK(t.head_indptr.ensure((size_t)(n + 1) * 4));
     CK(t.tail_indptr.ensure((size_t)(n + 1) * 4));
@@ -873,13 +877,14 @@ static int ensure_tiles(plsa_ctx *ctx, int kp)
                                                               t.slot_of.as<int32_t>());
     /* per row: padded head length and tail length, then the two row-pointer arrays */
     CK(cudaMemsetAsync(t.head_len.as<int32_t>() + n, 0, 4, s));
+    CK(cudaMemsetAsync(t.head_mem.as<int32_t>() + n, 0, 4, s));
     CK(cudaMemsetAsync(t.tail_len.as<int32_t>() + n, 0, 4, s));
     const SlotMap map{t.slot_of.as<int32_t>(), 1, 0};
     tile_count_kernel<<<(unsigned)cdiv(n * 32, T), T, 0, s>>>(c.indptr.as<int32_t>(), c.indptr.as<int32_t>() + 1, n,
                                                             c.ent.as<int2>(), map, t.head_len.as<int32_t>(),
-                                                            t.tail_len.as<int32_t>());
+                                                            t.head_mem.as<int32_t>(), t.tail_len.as<int32_t>());
     tmp = t.cub_tmp.cap;
-    CK(cub::DeviceScan::ExclusiveSum(t.cub_tmp.p, tmp, t.head_len.as<int32_t>(), t.head_indptr.as<int32_t>(),
+    CK(cub::DeviceScan::ExclusiveSum(t.cub_tmp.p, tmp, t.head_mem.as<int32_t>(), t.head_indptr.as<int32_t>(),
                                      (int)(n + 1), s));
     tmp = t.cub_tmp.cap;
     CK(cub::DeviceScan::ExclusiveSum(t.cub_tmp.p, tmp, t.tail_len.as<int32_t>(), t.tail_indptr.as<int32_t>(),
@@ -891,7 +896,10 @@ static int ensure_tiles(plsa_ctx *ctx, int kp)
     CK(cub::DeviceRadixSort::SortPairsDescending(t.cub_tmp.p, tmp, t.head_len.as<int32_t>(),
                                                  t.order_keys.as<int32_t>(), t.row_ids.as<int32_t>(),
                                                  t.order.as<int32_t>(), (int)n, 0, 32, s));
-    ctx->launches += 6;
+    CK(t.headers.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(int4)));
+    tile_headers_kernel<<<(unsigned)cdiv(n, T), T, 0, s>>>(t.order.as<int32_t>(), t.head_indptr.as<int32_t>(),
+                                                         t.head_len.as<int32_t>(), nullptr, n, t.headers.as<int4>());
+    ctx->launches += 7;
     CK(cudaGetLastError());
     int32_t head_total = 0, tail_total = 0;
     if (!ctx->device_plan) { /* the host planner walks the tail's row pointers */
@@ -910,7 +918,8 @@ static int ensure_tiles(plsa_ctx *ctx, int kp)
     t.tail_nnz = tail_total;
     if (t.head_slots < 0 || t.tail_nnz < 0 || t.tail_nnz > nnz)
         return ctx->fail(PLSA_ECUDA, "tiles: inconsistent head / tail split");
-    CK(t.head_ent.ensure((size_t)std::max<int64_t>(t.head_slots, 1) * sizeof(int2)));
+    CK(t.head_ent.ensure((size_t)(t.head_slots + 32) * sizeof(int2))); /* + a readable block */
+    CK(cudaMemsetAsync(t.head_ent.as<int2>() + t.head_slots, 0, 32 * sizeof(int2), s));
     CK(t.tail_ent.ensure(ent_bytes(t.tail_nnz)));
     CK(cudaMemsetAsync(t.tail_ent.as<int2>() + t.tail_nnz, 0, ENT_PAD * sizeof(int2), s));
     tile_place_kernel<<<(unsigned)cdiv(n * 32, T), T, 0, s>>>(
@@ -934,10 +943,11 @@ static int ensure_tiles(plsa_ctx *ctx, int kp)
     int rc = ctx->device_plan ? build_items_device(ctx, t.tail_indptr.as<int32_t>(), n, t.tail_items, chunk, align)
                               : build_items(ctx, t.h_tail_indptr, n, t.tail_items, chunk, align);
     if (rc) return rc;
-    /* opt in to the tile's dynamic shared memory once per kernel and device */
+    /* opt in to the tile's dynamic shared memory (the doc side and the term side share the
+     * kernels and ask for different sizes: allow the largest tile the option permits) */
     for (int ll = 0; ll < 2; ++ll)
         CK(cudaFuncSetAttribute(pick_tile_kernel(kp, ll != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)img_bytes));
+                                TILE_MAX_SMEM));
     t.ready = true;
     return PLSA_OK;
 }
@@ -1016,25 +1026,29 @@ static int ensure_term_tiles(plsa_ctx *ctx, int kp, bool weighted)
     CK(t.end.ensure((size_t)V * 4));
     CK(t.own_row.ensure((size_t)V * 4));
     CK(t.head_len.ensure((size_t)(V + 1) * 4));
+    CK(t.head_mem.ensure((size_t)(V + 1) * 4));
     CK(t.head_indptr.ensure((size_t)(V + 1) * 4));
     term_items_kernel<<<(unsigned)cdiv(m * n_blocks, T), T, 0, s>>>(
         ctx->t_indptr.as<int32_t>(), m, t.flag.as<int32_t>(), t.tiled_at.as<int32_t>(), t_ent, n_blocks, block_rows,
         t.beg.as<int32_t>(), t.end.as<int32_t>(), t.own_row.as<int32_t>(), t.tiled_terms.as<int32_t>());
     const SlotMap map{nullptr, n_blocks, block_rows};
     CK(cudaMemsetAsync(t.head_len.as<int32_t>() + V, 0, 4, s));
+    CK(cudaMemsetAsync(t.head_mem.as<int32_t>() + V, 0, 4, s));
     tile_count_kernel<<<(unsigned)cdiv(V * 32, T), T, 0, s>>>(t.beg.as<int32_t>(), t.end.as<int32_t>(), V, t_ent, map,
-                                                            t.head_len.as<int32_t>(), nullptr);
+                                                            t.head_len.as<int32_t>(), t.head_mem.as<int32_t>(),
+                                                            nullptr);
     tb = 0;
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, t.head_len.as<int32_t>(), t.head_indptr.as<int32_t>(), (int)(V + 1), s));
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, t.head_mem.as<int32_t>(), t.head_indptr.as<int32_t>(), (int)(V + 1), s));
     CK(t.cub_tmp.ensure(tb));
     tb = t.cub_tmp.cap;
-    CK(cub::DeviceScan::ExclusiveSum(t.cub_tmp.p, tb, t.head_len.as<int32_t>(), t.head_indptr.as<int32_t>(), (int)(V + 1), s));
+    CK(cub::DeviceScan::ExclusiveSum(t.cub_tmp.p, tb, t.head_mem.as<int32_t>(), t.head_indptr.as<int32_t>(), (int)(V + 1), s));
     int32_t head_total = 0;
     CK(cudaMemcpyAsync(&head_total, t.head_indptr.as<int32_t>() + V, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (head_total < 0) return ctx->fail(PLSA_ECUDA, "term tiles: inconsistent item lengths");
     t.head_slots = head_total;
-    CK(t.head_ent.ensure((size_t)std::max<int64_t>(t.head_slots, 1) * sizeof(int2)));
+    CK(t.head_ent.ensure((size_t)(t.head_slots + 32) * sizeof(int2))); /* + a readable block */
+    CK(cudaMemsetAsync(t.head_ent.as<int2>() + t.head_slots, 0, 32 * sizeof(int2), s));
     tile_place_kernel<<<(unsigned)cdiv(V * 32, T), T, 0, s>>>(
         t.beg.as<int32_t>(), t.end.as<int32_t>(), V, t_ent, map, t.head_indptr.as<int32_t>(), nullptr,
         t.head_ent.as<int2>(), nullptr, weighted ? ctx->sw.as<float>() : nullptr);
@@ -1059,6 +1073,10 @@ static int ensure_term_tiles(plsa_ctx *ctx, int kp, bool weighted)
     tb = t.cub_tmp.cap;
     CK(cub::DeviceRadixSort::SortPairs(t.cub_tmp.p, tb, t.keys.as<int32_t>(), t.keys_sorted.as<int32_t>(),
                                        t.ids.as<int32_t>(), t.order.as<int32_t>(), (int)V, 0, end_bit, s));
+    CK(t.headers.ensure((size_t)V * sizeof(int4)));
+    tile_headers_kernel<<<(unsigned)cdiv(V, T), T, 0, s>>>(t.order.as<int32_t>(), t.head_indptr.as<int32_t>(),
+                                                         t.head_len.as<int32_t>(), t.own_row.as<int32_t>(), V,
+                                                         t.headers.as<int4>());
     term_work_kernel<<<(unsigned)cdiv(V + 1, T), T, 0, s>>>(t.order.as<int32_t>(), t.head_len.as<int32_t>(), V,
                                                           t.work.as<int32_t>());
     tb = t.cub_tmp.cap;
@@ -1093,8 +1111,8 @@ static int ensure_term_tiles(plsa_ctx *ctx, int kp, bool weighted)
                                       t.flag.as<int32_t>())
                  : build_items(ctx, ctx->h_tindptr, m, t.tail_items, chunk, align, nullptr, t.h_flag.data());
     if (rc) return rc;
-    const size_t smem = (size_t)std::max<int32_t>(block_rows, TILE_MIN_ROWS) * t.pitch_f * 4;
-    CK(cudaFuncSetAttribute(pick_tile_kernel(kp, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(pick_tile_kernel(kp, false), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            TILE_MAX_SMEM));
     t.ready = true;
     return PLSA_OK;
 }
@@ -1213,7 +1231,7 @@ API int plsa_ctx_destroy(plsa_ctx *ctx)
                       &ctx->A[0], &ctx->A[1], &ctx->B[0], &ctx->B[1],
                       &ctx->scale, &ctx->ones, &ctx->colnorm, &ctx->colpart, &ctx->partialA,
                       &ctx->partialB, &ctx->sw, &ctx->ll_part, &ctx->ll_out, &ctx->stage, &ctx->tickets,
-                      &ctx->topics_dev, &ctx->ll2, &ctx->colpart2})
+                      &ctx->topics_dev, &ctx->gathered, &ctx->ll2, &ctx->colpart2})
         b->release();
     for (int i = 0; i < 2; ++i) {
         if (ctx->texA[i]) cudaDestroyTextureObject(ctx->texA[i]);
@@ -1696,7 +1714,7 @@ static int run_fixup(plsa_ctx *ctx, int which, float *own_new, cudaStream_t stre
         none.partial = t.partial.as<float>();
         none.own_new = own_new;
         none.n_split = t.n_tiled;
-        none.n_heavy = t.n_blocks > 32 ? t.n_tiled : 0;
+        none.n_heavy = t.n_blocks > 256 ? t.n_tiled : 0; /* a warp adds up to 256 slots per term quickly enough */
         none.kp = ctx->kp;
         none.stride_own = ctx->strideB;
         none.normalise = 0;
@@ -1826,7 +1844,7 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
      * ranks; the log-likelihood is the sum of the shards' values, so all ranks take the
      * same stop decision. */
     const bool sharded = ctx->shard != nullptr; /* one rank: same path, empty collectives */
-    const int colsum_grid = 148;
+    const int colsum_grid = term_tiled ? 592 : 148; /* 4 CTAs per SM / the sharded fit's reduce kernel: 1 */
     if (sharded) CK(ctx->ll2.ensure(16));
     if (sharded || term_tiled) CK(ctx->colpart2.ensure((size_t)colsum_grid * kp * 8));
     /* Peer-memory path (plsa_shard_p2p_*): the term pass writes into this rank's exchange
@@ -1854,8 +1872,7 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
             if (tiled) { /* head entries: shared-memory tile, TMA-staged, lane per entry */
                 TileSet &t = ctx->tiles;
                 TileArgs h{};
-                h.order = t.order.as<int32_t>();
-                h.indptr = t.head_indptr.as<int32_t>();
+                h.items = t.headers.as<int4>();
                 h.ent = t.head_ent.as<int2>();
                 h.own_old = ctx->A[ctx->curA].as<float>();
                 h.tile_src = t.img[ctx->curB].as<float>();
@@ -1867,7 +1884,8 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                 h.stride_own = ctx->strideA;
                 h.kp = kp;
                 h.ftz_scale = ftz_scale;
-                h.log2_ftz_scale = std::log2((double)ftz_scale);
+                h.inv_ftz_scale = 1.f / ftz_scale;
+                h.log2_ftz_corr = std::log2((double)ftz_scale * (double)h.inv_ftz_scale);
                 if (fused_now) {
                     h.row_weight = ctx->sw.as<float>();
                     h.cta_partial = t.ll_part.as<double>();
@@ -1925,10 +1943,8 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                 if (term_tiled) { /* frequent terms: P(z|d) blocks in shared memory */
                     TermTiles &t = ctx->tterm;
                     TileArgs h{};
-                    h.order = t.order.as<int32_t>();
-                    h.indptr = t.head_indptr.as<int32_t>();
+                    h.items = t.headers.as<int4>();
                     h.ent = t.head_ent.as<int2>();
-                    h.own_row = t.own_row.as<int32_t>();
                     h.own_old = ctx->B[ctx->curB].as<float>();
                     h.tile_src = t.acomp[ctx->curA].as<float>();
                     h.partial_out = t.partial.as<float>();
@@ -2340,52 +2356,93 @@ API int plsa_b200_refit_inner(const int32_t *X_rows, const int32_t *X_cols, cons
 }
 
 /* ---- all-pairs distances between topic vectors (ensemble clustering input) ------------------------ */
-API int plsa_topic_distances(int32_t device, const float *topics, int64_t n_topics, int64_t n_terms,
-                             int32_t kind, double *out)
+/* distances of a [n_topics, n_terms] matrix that already lives on `device` (host_src: uploaded
+ * first); out is a host array [n_topics, n_topics] */
+static int topic_distances_impl(int32_t device, const float *dev_src, const float *host_src,
+                                int64_t n_topics, int64_t n_terms, int32_t kind, double *out)
 {
-    if (!topics || !out || n_topics < 0 || n_terms < 0 || (kind != 0 && kind != 1) ||
+    if ((!dev_src && !host_src) || !out || n_topics < 0 || n_terms < 0 || (kind != 0 && kind != 1) ||
         n_topics >= ((int64_t)1 << 24)) {
         g_err = "topic_distances: bad arguments";
         return PLSA_EINVAL;
     }
     if (n_topics == 0) return PLSA_OK;
     cudaError_t e = cudaSetDevice(device);
-    DevBuf P, A, B, l1, D;
+    DevBuf P, A, B, l1, D, part;
     cudaStream_t st = nullptr;
     const size_t cells = (size_t)n_topics * (size_t)std::max<int64_t>(n_terms, 1);
     auto done = [&](int rc, const char *what) {
         if (rc != PLSA_OK) g_err = std::string("topic_distances: ") + what + ": " + cudaGetErrorString(e);
-        P.release(); A.release(); B.release(); l1.release(); D.release();
+        P.release(); A.release(); B.release(); l1.release(); D.release(); part.release();
         if (st) cudaStreamDestroy(st);
         return rc;
     };
     if (e != cudaSuccess) return done(PLSA_ECUDA, "cudaSetDevice");
     if ((e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)) != cudaSuccess)
         return done(PLSA_ECUDA, "stream");
-    if ((e = P.ensure(cells * 4)) != cudaSuccess || (e = A.ensure(cells * 4)) != cudaSuccess ||
+    /* term slices: enough CTAs to fill the GPU a few times over */
+    const int64_t tiles = cdiv(n_topics, 32) * cdiv(n_topics, 32);
+    int n_sms = 148;
+    cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device);
+    const int slices = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(64, cdiv(n_terms, 1024)),
+                                                                   cdiv(4 * (int64_t)n_sms, tiles)));
+    if ((!dev_src && (e = P.ensure(cells * 4)) != cudaSuccess) || (e = A.ensure(cells * 4)) != cudaSuccess ||
         (e = B.ensure(kind == 1 ? cells * 4 : 16)) != cudaSuccess ||
         (e = l1.ensure((size_t)n_topics * 8)) != cudaSuccess ||
-        (e = D.ensure((size_t)n_topics * n_topics * 8)) != cudaSuccess)
+        (e = D.ensure((size_t)n_topics * n_topics * 8)) != cudaSuccess ||
+        (e = part.ensure((size_t)slices * n_topics * n_topics * 8)) != cudaSuccess)
         return done(PLSA_ENOMEM, "allocation");
-    if (n_terms > 0 &&
-        (e = cudaMemcpyAsync(P.p, topics, cells * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess)
-        return done(PLSA_ECUDA, "upload");
-    topic_rowsum_kernel<<<(unsigned)n_topics, 256, 0, st>>>(P.as<float>(), n_terms, l1.as<double>());
+    const float *src = dev_src;
+    if (!dev_src) {
+        if (n_terms > 0 &&
+            (e = cudaMemcpyAsync(P.p, host_src, cells * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+            return done(PLSA_ECUDA, "upload");
+        src = P.as<float>();
+    }
+    topic_rowsum_kernel<<<(unsigned)n_topics, 256, 0, st>>>(src, n_terms, l1.as<double>());
     if (n_terms > 0)
         topic_prep_kernel<<<(unsigned)cdiv((int64_t)cells, 256), 256, 0, st>>>(
-            P.as<float>(), l1.as<double>(), n_topics, n_terms, kind, A.as<float>(), B.as<float>());
-    const dim3 grid((unsigned)cdiv(n_topics, 32), (unsigned)cdiv(n_topics, 32));
+            src, l1.as<double>(), n_topics, n_terms, kind, A.as<float>(), B.as<float>());
+    const dim3 grid((unsigned)cdiv(n_topics, 32), (unsigned)cdiv(n_topics, 32), (unsigned)slices);
     if (kind == 0)
-        topic_pairs_kernel<0><<<grid, 256, 0, st>>>(A.as<float>(), B.as<float>(), l1.as<double>(),
-                                                    (int)n_topics, n_terms, D.as<double>());
+        topic_pairs_kernel<0><<<grid, 256, 0, st>>>(A.as<float>(), B.as<float>(), (int)n_topics, n_terms,
+                                                    part.as<double>());
     else
-        topic_pairs_kernel<1><<<grid, 256, 0, st>>>(A.as<float>(), B.as<float>(), l1.as<double>(),
-                                                    (int)n_topics, n_terms, D.as<double>());
+        topic_pairs_kernel<1><<<grid, 256, 0, st>>>(A.as<float>(), B.as<float>(), (int)n_topics, n_terms,
+                                                    part.as<double>());
+    topic_pairs_finish_kernel<<<(unsigned)cdiv(n_topics * n_topics, 256), 256, 0, st>>>(
+        part.as<double>(), slices, l1.as<double>(), (int)n_topics, kind, D.as<double>());
     if ((e = cudaGetLastError()) != cudaSuccess) return done(PLSA_ECUDA, "launch");
     if ((e = cudaMemcpyAsync(out, D.p, (size_t)n_topics * n_topics * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
         (e = cudaStreamSynchronize(st)) != cudaSuccess)
         return done(PLSA_ECUDA, "download");
     return done(PLSA_OK, "");
+}
+
+API int plsa_topic_distances(int32_t device, const float *topics, int64_t n_topics, int64_t n_terms,
+                             int32_t kind, double *out)
+{
+    if (!topics) {
+        g_err = "topic_distances: bad arguments";
+        return PLSA_EINVAL;
+    }
+    return topic_distances_impl(device, nullptr, topics, n_topics, n_terms, kind, out);
+}
+
+/* The same on the stack of topic matrices the last gather left on this context's device
+ * (plsa_gather_topics / plsa_comm_gather_topics keep it there): no second trip over PCIe for the
+ * 64 MB the clustering stage would otherwise upload again. */
+API int plsa_gathered_distances(plsa_ctx *ctx, int32_t kind, double *out, int64_t *n_topics)
+{
+    CHECK_CTX(ctx);
+    if (!ctx->gathered.p || ctx->gathered_n <= 0)
+        return ctx->fail(PLSA_EINVAL, "gathered_distances: no gathered topics on this context");
+    if (n_topics) *n_topics = ctx->gathered_n;
+    if (!out) return PLSA_OK; /* size query */
+    int rc = topic_distances_impl(ctx->device, ctx->gathered.as<float>(), nullptr, ctx->gathered_n,
+                                  ctx->gathered_m, kind, out);
+    if (rc) ctx->err = g_err;
+    return rc;
 }
 
 /* ---- ensemble topic stash + gather over NCCL ------------------------------------------------------ */
@@ -2601,7 +2658,8 @@ API int plsa_gather_topics(plsa_ctx **ctxs, int32_t n_ctx, const int32_t *n_slot
     }
     if (total == 0) return PLSA_OK;
     cudaSetDevice(root->device);
-    DevBuf stack;
+    DevBuf &stack = root->gathered; /* stays on the root device for plsa_gathered_distances */
+    root->gathered_n = root->gathered_m = 0;
     if (stack.ensure(per * total * 4) != cudaSuccess) {
         g_err = "gather_topics: staging allocation failed";
         return PLSA_ENOMEM;
@@ -2616,7 +2674,6 @@ API int plsa_gather_topics(plsa_ctx **ctxs, int32_t n_ctx, const int32_t *n_slot
     if (ce == cudaSuccess && any_remote) {
         Nccl *nc = load_nccl();
         if (!nc) {
-            stack.release();
             g_err = "gather_topics: libnccl.so.2 could not be loaded";
             return PLSA_ENCCL;
         }
@@ -2625,7 +2682,6 @@ API int plsa_gather_topics(plsa_ctx **ctxs, int32_t n_ctx, const int32_t *n_slot
         std::vector<ncclComm_t> *cached = nullptr;
         int r = cached_comms(nc, devs, &cached);
         if (r != 0) {
-            stack.release();
             return nccl_fail(nc, "gather_topics: ncclCommInitAll", r);
         }
         std::vector<ncclComm_t> &comms = *cached;
@@ -2655,7 +2711,10 @@ API int plsa_gather_topics(plsa_ctx **ctxs, int32_t n_ctx, const int32_t *n_slot
     if (rc == PLSA_OK && ce == cudaSuccess)
         ce = cudaMemcpyAsync(out, stack.p, per * total * 4, cudaMemcpyDeviceToHost, root->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(root->stream);
-    stack.release();
+    if (rc == PLSA_OK && ce == cudaSuccess && root->k > 0) {
+        root->gathered_n = (int64_t)total * root->k;
+        root->gathered_m = (int64_t)(per / (size_t)root->k);
+    }
     if (rc == PLSA_OK && ce != cudaSuccess) {
         g_err = std::string("gather_topics: ") + cudaGetErrorString(ce);
         rc = PLSA_ECUDA;
@@ -2907,7 +2966,8 @@ API int plsa_comm_gather_topics(plsa_comm *c, plsa_ctx *ctx, const int32_t *n_pe
     for (int r = 0; r < c->n_ranks; ++r) total += (size_t)n_per_rank[r];
     const bool is_root = c->rank == root;
     if (is_root && !out && total > 0) return ctx->fail(PLSA_EINVAL, "comm_gather_topics: null output");
-    DevBuf stack;
+    DevBuf &stack = ctx->gathered; /* stays on the root's device for plsa_gathered_distances */
+    ctx->gathered_n = ctx->gathered_m = 0;
     if (is_root && total > 0) CK(stack.ensure(per * total * 4));
     Nccl *nc = c->n_ranks > 1 ? load_nccl() : nullptr;
     int r = 0;
@@ -2939,7 +2999,10 @@ API int plsa_comm_gather_topics(plsa_comm *c, plsa_ctx *ctx, const int32_t *n_pe
     }
     cudaError_t ce2 = cudaStreamSynchronize(c->stream);
     if (ce == cudaSuccess) ce = ce2;
-    stack.release();
+    if (is_root && total > 0 && r == 0 && ce == cudaSuccess) {
+        ctx->gathered_n = (int64_t)total * ctx->k;
+        ctx->gathered_m = (int64_t)(per / (size_t)ctx->k);
+    }
     if (r != 0) {
         const int rc = nccl_fail(nc, "comm_gather_topics", r);
         ctx->err = g_err;

@@ -463,6 +463,14 @@ __device__ __forceinline__ void pass_block(const PassArgs &a, const int2 (&e)[U]
 #endif
 }
 
+/* how far ahead (in entries) the row pass pulls an item's entry stream into L2; 0 = off */
+#ifndef PLSA_ENT_PREFETCH
+#define PLSA_ENT_PREFETCH 32
+#endif
+#ifndef PLSA_ENT_PREFETCH_L1
+#define PLSA_ENT_PREFETCH_L1 0
+#endif
+
 /* entries of an item in flight = the entry block aligned items start on */
 __host__ __device__ constexpr int pass_block_entries(int KV) { return (KV >= 4) ? 1 : (KV == 2) ? 2 : 4; }
 
@@ -541,6 +549,18 @@ __global__ void __launch_bounds__(PLSA_PASS_THREADS, (KV == 1) ? 4 : (KV == 2) ?
     for (int base = 0; base < maxlen; base += U) {
         int2 en[U];
         load_entries<U, VEC>(ent + base + U, en);
+        /* the entry stream (8 bytes per entry, from HBM) is pulled into L2 ahead of its use:
+         * with only the next block in registers, every block waited a memory latency for its
+         * entries and then another one for the rows they point at */
+        if constexpr (PLSA_ENT_PREFETCH > 0) {
+            if (j == 0 && base + PLSA_ENT_PREFETCH < maxlen + U) {
+#if PLSA_ENT_PREFETCH_L1
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(ent + base + PLSA_ENT_PREFETCH));
+#else
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ent + base + PLSA_ENT_PREFETCH));
+#endif
+            }
+        }
         pass_block<G, KV, U, MODE, TEX, true>(a, e, base, len, gat_base, lane_off, stride_bytes,
                                               own, acc, ll_acc, min_norm, rw, thresh, j, gbase,
                                               lane_on);
@@ -722,8 +742,17 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float *__rest
     if (kp <= 256) { /* 256 / kp rows at a time, kp consecutive threads along a row */
         const int nsub = 256 / kp, sub = (int)threadIdx.x / kp, z = (int)threadIdx.x - sub * kp;
         double t = 0.0;
-        if (sub < nsub)
-            for (int64_t r = r0 + sub; r < r1; r += nsub) t += (double)mat[r * stride + z];
+        if (sub < nsub) { /* four independent loads in flight; the order of the sum stays fixed */
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+            int64_t r = r0 + sub;
+            for (; r + 3 * nsub < r1; r += 4 * nsub) {
+                const float a0 = mat[r * stride + z], a1 = mat[(r + nsub) * stride + z],
+                            a2 = mat[(r + 2 * nsub) * stride + z], a3 = mat[(r + 3 * nsub) * stride + z];
+                t0 += (double)a0; t1 += (double)a1; t2 += (double)a2; t3 += (double)a3;
+            }
+            for (; r < r1; r += nsub) t0 += (double)mat[r * stride + z];
+            t = (t0 + t1) + (t2 + t3);
+        }
         sm[threadIdx.x] = t;
         __syncthreads();
         if ((int)threadIdx.x < kp) {
@@ -744,11 +773,17 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const double *__restr
                                                            int kp, float *__restrict__ scale_out,
                                                            double *__restrict__ colnorm_out)
 {
-    for (int z = threadIdx.x; z < kp; z += blockDim.x) {
+    /* one warp per topic: lanes stride over the partials, fixed-order butterfly */
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int z = warp; z < kp; z += nw) {
         double t = 0.0;
-        for (int i = 0; i < n_part; ++i) t += part[(int64_t)i * kp + z];
-        colnorm_out[z] = t;
-        scale_out[z] = t > 0.0 ? (float)(1.0 / t) : 1.f;
+        for (int i = lane; i < n_part; i += 32) t += part[(int64_t)i * kp + z];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        if (lane == 0) {
+            colnorm_out[z] = t;
+            scale_out[z] = t > 0.0 ? (float)(1.0 / t) : 1.f;
+        }
     }
 }
 
@@ -905,22 +940,27 @@ __global__ void topic_prep_kernel(const float *__restrict__ P, const double *__r
     }
 }
 
+/* blockIdx.z cuts the terms into gridDim.z slices (a 320 x 320 problem has only 100 pair tiles:
+ * without the cut two thirds of the SMs idle); every slice writes raw float64 sums into its own
+ * [n, n] plane of `part`, topic_pairs_finish_kernel adds the planes in order. */
 template <int KIND>
 __global__ void __launch_bounds__(256) topic_pairs_kernel(const float *__restrict__ A,
-                                                          const float *__restrict__ B,
-                                                          const double *__restrict__ l1, int n,
-                                                          int64_t m, double *__restrict__ out)
+                                                          const float *__restrict__ B, int n,
+                                                          int64_t m, double *__restrict__ part)
 {
     constexpr int T = 32, WC = 32;
     __shared__ float ai[T][WC + 1], aj[T][WC + 1], bi[KIND ? T : 1][WC + 1], bj[KIND ? T : 1][WC + 1];
     const int i0 = blockIdx.y * T, j0 = blockIdx.x * T;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4; /* pairs (i0+ty+16a, j0+tx+16b) */
     double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-    for (int64_t w0 = 0; w0 < m; w0 += WC) {
+    const int64_t per = ((m + gridDim.z - 1) / gridDim.z + WC - 1) / WC * WC;
+    const int64_t w_lo = (int64_t)blockIdx.z * per, w_hi = min(m, w_lo + per);
+    double *out = part + (int64_t)blockIdx.z * n * n;
+    for (int64_t w0 = w_lo; w0 < w_hi; w0 += WC) {
         for (int e = threadIdx.x; e < T * WC; e += 256) {
             const int r = e / WC, c = e % WC;
             const int64_t w = w0 + c;
-            const bool okw = w < m;
+            const bool okw = w < w_hi;
             const int gi = i0 + r, gj = j0 + r;
             ai[r][c] = (okw && gi < n) ? A[(int64_t)gi * m + w] : 0.f;
             aj[r][c] = (okw && gj < n) ? A[(int64_t)gj * m + w] : 0.f;
@@ -959,13 +999,25 @@ __global__ void __launch_bounds__(256) topic_pairs_kernel(const float *__restric
         for (int b = 0; b < 2; ++b) {
             const int gi = i0 + ty + 16 * a, gj = j0 + tx + 16 * b;
             if (gi >= n || gj >= n) continue;
-            double v = acc[a][b];
-            if constexpr (KIND == 0) {
-                const bool zi = !(l1[gi] > 0.0), zj = !(l1[gj] > 0.0);
-                v = (gi == gj || (zi && zj)) ? 0.0 : (zi || zj) ? 1.0 : sqrt(0.5 * v);
-            }
-            out[(int64_t)gi * n + gj] = v;
+            out[(int64_t)gi * n + gj] = acc[a][b];
         }
+}
+
+/* sum of the term slices (fixed order) and, for Hellinger, the final form of the distance */
+__global__ void topic_pairs_finish_kernel(const double *__restrict__ part, int n_slices,
+                                          const double *__restrict__ l1, int n, int kind,
+                                          double *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n * n) return;
+    double v = 0.0;
+    for (int s = 0; s < n_slices; ++s) v += part[(int64_t)s * n * n + i];
+    if (kind == 0) {
+        const int gi = (int)(i / n), gj = (int)(i - (int64_t)gi * n);
+        const bool zi = !(l1[gi] > 0.0), zj = !(l1[gj] > 0.0);
+        v = (gi == gj || (zi && zj)) ? 0.0 : (zi || zj) ? 1.0 : sqrt(0.5 * v);
+    }
+    out[i] = v;
 }
 
 /* ---- layout conversion between the reference's arrays and the device layout ---------- */

@@ -31,18 +31,27 @@
 
 namespace plsa {
 
-constexpr int TILE_THREADS = 512;                 /* 16 warps, one CTA per SM */
+#ifndef PLSA_TILE_ABLATE
+#define PLSA_TILE_ABLATE 0                        /* 1-3: timing experiments, results are wrong */
+#endif
+#ifndef PLSA_TILE_PF_L1
+#define PLSA_TILE_PF_L1 0
+#endif
+#ifndef PLSA_TILE_THREADS
+#define PLSA_TILE_THREADS 512
+#endif
+constexpr int TILE_THREADS = PLSA_TILE_THREADS;   /* 16 warps, one CTA per SM */
 constexpr int TILE_MIN_ROWS = 8;                  /* padding entries address slots 0..7 */
+constexpr int TILE_MAX_SMEM = 221 * 1024;         /* dynamic shared memory a tile may ask for (option "tile_kb" <= 220) */
 
 __host__ __device__ constexpr int tile_pitch_chunks(int kc) { return kc | 1; } /* odd */
 
 struct TileArgs {
-    const int32_t *order;     /* [n_items] work items (rows of the tiled CSR) in launch order:
-                                 doc side by padded length, longest first; term side by tile
-                                 block, then by length                                       */
-    const int32_t *indptr;    /* [n_items + 1] tiled CSR; every row length is a multiple of 8 */
+    const int4 *items;        /* [n_items] work items in launch order {first entry, entries (a
+                                 multiple of 8), factor row the item owns, its partial-sum
+                                 slot}: doc side by padded length, longest first; term side by
+                                 tile block, then by length (tile_headers_kernel)            */
     const int2 *ent;          /* entries {slot inside the tile, value bits}                  */
-    const int32_t *own_row;   /* [n_items] factor row an item owns; nullptr: the item's number */
     const float *own_old;     /* [rows, stride_own]                                          */
     const float *tile_src;    /* compact image of the gathered factor, [*, pitch]; block b of
                                  the tile starts at row b * block_rows                        */
@@ -59,7 +68,9 @@ struct TileArgs {
     int64_t src_rows;         /* rows of the gathered factor (last block may be short)       */
     int32_t block_rows, n_blocks, stride_own, kp;
     float ftz_scale;          /* S = FLT_MIN / thresh                                        */
-    double log2_ftz_scale;    /* LL: log2(S), subtracted once per item in double             */
+    float inv_ftz_scale;      /* LL: float(1 / S): the log is taken of the unscaled normaliser */
+    double log2_ftz_corr;     /* LL: log2(S * float(1 / S)), the systematic part of that
+                                 un-scaling, taken off once per item in double                */
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -126,20 +137,32 @@ __device__ __forceinline__ int octet_fold(float (&a)[K], int li, int &first)
 /* four items (one per octet of the warp) starting at item `first`, items at or past `limit`
  * are idle */
 template <int KC, bool LL>
-__device__ __forceinline__ void tile_batch(const TileArgs &a, const float4 *tile, int64_t first,
-                                           int64_t limit, int li, int oct, double &ll_acc,
-                                           float &min_norm)
+__device__ __forceinline__ void tile_batch(const TileArgs &a, const float4 *tile, const int4 hdr,
+                                           bool has, const int4 next, bool has_next, int li,
+                                           double &ll_acc, float &min_norm)
 {
     constexpr int PC = tile_pitch_chunks(KC);
     constexpr int K = 4 * KC;
-    const int64_t i = first + oct;
-    const bool has = i < limit;
-    int item = 0, row = 0, start = 0, len = 0;
-    if (has) {
-        item = a.order[i];
-        row = a.own_row ? a.own_row[item] : item;
-        start = a.indptr[item];
-        len = a.indptr[item + 1] - start;
+    const int start = hdr.x, len = has ? hdr.y : 0, row = hdr.z, item = hdr.w;
+    /* Items are short (a dozen steps): what a batch reads first — its owned row and its first
+     * entry blocks — is pulled into L2 while the batch before it runs; inside an item the
+     * stream is prefetched four blocks ahead (below). */
+    if (has_next) {
+        const int2 *ne = a.ent + next.x + li * 4;
+        const int nmem = (next.y + 31) & ~31;
+#if PLSA_TILE_PF_L1   /* experiment: the first two blocks and the owned row into L1 (needs a smaller tile) */
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (q < 2 && q * 32 < nmem) asm volatile("prefetch.global.L1 [%0];" ::"l"(ne + q * 32));
+            else if (q * 32 < nmem) asm volatile("prefetch.global.L2 [%0];" ::"l"(ne + q * 32));
+        }
+        if (li == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.own_old + (int64_t)next.z * a.stride_own));
+#else
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (q * 32 < nmem) asm volatile("prefetch.global.L2 [%0];" ::"l"(ne + q * 32));
+        if (li == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.own_old + (int64_t)next.z * a.stride_own));
+#endif
     }
     int maxlen = len;
     maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, 8));
@@ -159,50 +182,102 @@ __device__ __forceinline__ void tile_batch(const TileArgs &a, const float4 *tile
         acc2[2 * c] = 0ull;
         acc2[2 * c + 1] = 0ull;
     }
-    float ll_row = 0.f, x_sum = 0.f; /* LL: sum of x * log2(scaled normaliser), sum of x */
-    const int2 *ent = a.ent + start + li;
-    int2 e = (len > 0) ? __ldg(ent) : make_int2(li, 0);
-    for (int t = 0; t < maxlen; t += 8) {
-        /* one step ahead; past the item's end: own residue class, value 0 */
-        const int2 en = (t + 8 < len) ? __ldg(ent + t + 8) : make_int2(li, 0);
-        float4 g[KC];
+    double ll_row = 0.0, x_sum = 0.0; /* LL: sum of x * log2(normaliser), sum of x */
+    /* Entries come in blocks of 4 steps, lane-major (tile_place_kernel): lane li reads its four
+     * entries of a block with ONE 32-byte load.  The block after the current one is already in
+     * registers and the lines three blocks further are on their way into L2, so that the entry
+     * stream (8 bytes per lane and step, from HBM) never stalls a step — with a look-ahead of a
+     * single step every step waited a full memory latency (profiles/r2_kernel_experiments.md). */
+    const int2 *ent = a.ent + start + li * 4;
+    const int len_mem = (len + 31) & ~31;
+    int2 e[4], en[4];
+#if PLSA_TILE_ABLATE == 3   /* timing experiment: no entry stream */
 #pragma unroll
-        for (int c = 0; c < KC; ++c) g[c] = tile[e.x * PC + c];
-        const float x = __int_as_float(e.y);
-        f32x2 v[2 * KC];
+    for (int q = 0; q < 4; ++q) e[q] = make_int2(li + 8 * q, 0x3f800000);
+#else
+    load_entries<4, true>(ent, e); /* readable for every item: the array is padded by a block */
+#endif
+    if (len == 0) {
 #pragma unroll
-        for (int c = 0; c < KC; ++c) {
-            v[2 * c] = mul2_ftz(pk2(g[c].x, g[c].y), own2[2 * c]);
-            v[2 * c + 1] = mul2_ftz(pk2(g[c].z, g[c].w), own2[2 * c + 1]);
+        for (int q = 0; q < 4; ++q) e[q] = make_int2(li, 0);
+    }
+    for (int t = 0; t < maxlen; t += 32) {
+        if (t + 32 < len_mem) {
+#if PLSA_TILE_ABLATE == 3
+#pragma unroll
+            for (int q = 0; q < 4; ++q) en[q] = make_int2(li + 8 * q + (t & 1023), 0x3f800000);
+#else
+            load_entries<4, true>(ent + t + 32, en);
+#endif
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) en[q] = make_int2(li, 0);
         }
-        f32x2 s = add2(v[0], v[1]);
+        if (t + 128 < len_mem) asm volatile("prefetch.global.L2 [%0];" ::"l"(ent + t + 128));
 #pragma unroll
-        for (int c = 1; c < KC; ++c) s = add2(s, add2(v[2 * c], v[2 * c + 1]));
-        float s_lo, s_hi;
-        upk2(s, s_lo, s_hi);
-        const float norm = s_lo + s_hi;
-        if constexpr (LL) {
-            /* plsa.py:383-384; x == 0 marks padding.  The sum carries S: log2(S) * sum of x is
-             * taken off per item in double (a float correction per entry would be biased) */
-            ll_row += (x != 0.f) ? x * log2_ftz(norm) : 0.f;
-            x_sum += x;
-            min_norm = fminf(min_norm, (x != 0.f) ? norm : 3.0e38f);
+        for (int q = 0; q < 4; ++q) {
+            /* past the item's end (the block is padded, or another octet's item is longer): own
+             * residue class, value 0 */
+            const bool on = t + 8 * q < len;
+            const int slot = on ? e[q].x : li;
+            const float x = on ? __int_as_float(e[q].y) : 0.f;
+            float4 g[KC];
+#if PLSA_TILE_ABLATE == 1   /* timing experiment: no shared-memory reads */
+#pragma unroll
+            for (int c = 0; c < KC; ++c) g[c] = make_float4(__int_as_float(slot + c), 1.f, 2.f, 3.f);
+#else
+#pragma unroll
+            for (int c = 0; c < KC; ++c) g[c] = tile[slot * PC + c];
+#endif
+            f32x2 v[2 * KC];
+#pragma unroll
+            for (int c = 0; c < KC; ++c) {
+                v[2 * c] = mul2_ftz(pk2(g[c].x, g[c].y), own2[2 * c]);
+                v[2 * c + 1] = mul2_ftz(pk2(g[c].z, g[c].w), own2[2 * c + 1]);
+            }
+            f32x2 s = add2(v[0], v[1]);
+#pragma unroll
+            for (int c = 1; c < KC; ++c) s = add2(s, add2(v[2 * c], v[2 * c + 1]));
+            float s_lo, s_hi;
+            upk2(s, s_lo, s_hi);
+            const float norm = s_lo + s_hi;
+            if constexpr (LL) {
+                /* plsa.py:383-384; x == 0 marks padding.  The log is taken of the same number the
+                 * group-per-row pass sees (MUFU.LG2's error depends on the magnitude): the sum
+                 * carries S, float(1/S) takes it off, and what S * float(1/S) differs from 1 by is
+                 * corrected per item in double */
+                ll_row += (double)((x != 0.f) ? x * log2_ftz(norm * a.inv_ftz_scale) : 0.f);
+                x_sum += (double)x;
+                min_norm = fminf(min_norm, (x != 0.f) ? norm : 3.0e38f);
+            }
+#if PLSA_TILE_ABLATE == 2   /* timing experiment: no reciprocal, no accumulation */
+            acc2[0] = add2(acc2[0], pk2(norm, x));
+#else
+            /* x / norm (see pass_block).  The scaled normaliser can be as small as FLT_MIN, so
+             * the quotient is formed 2^-24 too small (no overflow for counts below 6e7; larger
+             * ones are clamped) and the item's sums are multiplied by 2^24 at the end: exact */
+            const float cf = fminf((x * 5.9604645e-8f) * rcp_fast(norm), 3.0e38f);
+            const f32x2 c2 = pk2(cf, cf);
+#pragma unroll
+            for (int c = 0; c < 2 * KC; ++c) acc2[c] = fma2(c2, v[c], acc2[c]);
+#endif
         }
-        const float cf = fminf(x * rcp_fast(norm), 3.0e38f); /* see pass_block */
-        const f32x2 c2 = pk2(cf, cf);
 #pragma unroll
-        for (int q = 0; q < 2 * KC; ++q) acc2[q] = fma2(c2, v[q], acc2[q]);
-        e = en;
+        for (int q = 0; q < 4; ++q) e[q] = en[q];
     }
     if constexpr (LL) {
         /* same float ln 2 as __logf / the group-per-row pass, so that the paths agree */
         if (has)
-            ll_acc += ((double)ll_row - a.log2_ftz_scale * (double)x_sum) * (double)0.69314718f *
+            ll_acc += (ll_row - a.log2_ftz_corr * x_sum) * (double)0.69314718f *
                       (double)a.row_weight[row];
     }
     float acc[K];
 #pragma unroll
-    for (int q = 0; q < 2 * KC; ++q) upk2(acc2[q], acc[2 * q], acc[2 * q + 1]);
+    for (int q = 0; q < 2 * KC; ++q) {
+        upk2(acc2[q], acc[2 * q], acc[2 * q + 1]);
+        acc[2 * q] *= 16777216.f;
+        acc[2 * q + 1] *= 16777216.f;
+    }
     int first_topic;
     const int nv = octet_fold<K>(acc, li, first_topic);
     if (has) {
@@ -255,9 +330,22 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) tile_pass_kernel(const TileAr
         /* one block for everybody; batches dealt round-robin over all warps of the grid: with
          * the items sorted by length every warp gets the same work to within its last batch */
         load_tile(0);
-        const int64_t gw = (int64_t)blockIdx.x * NW + warp, GW = (int64_t)gridDim.x * NW;
-        for (int64_t b = gw * 4; b < a.n_items; b += GW * 4)
-            tile_batch<KC, LL>(a, tile, b, a.n_items, li, oct, ll_acc, min_norm);
+        /* consecutive batches (equally long: the items are sorted) go to DIFFERENT CTAs — warp w
+         * of CTA c takes batches w * grid + c, + grid * NW, ...: every SM gets the same mix */
+        const int64_t gw = (int64_t)warp * gridDim.x + blockIdx.x, GW = (int64_t)gridDim.x * NW;
+        /* item headers are fetched two batches ahead, so that a batch can prefetch what the
+         * batch after it reads first */
+        auto header = [&](int64_t i) {
+            return i < a.n_items ? __ldg(a.items + i) : make_int4(0, 0, 0, 0);
+        };
+        int4 hdr = header(gw * 4 + oct), next = header(gw * 4 + GW * 4 + oct);
+        for (int64_t b = gw * 4; b < a.n_items; b += GW * 4) {
+            const int4 after = header(b + 2 * GW * 4 + oct);
+            tile_batch<KC, LL>(a, tile, hdr, b + oct < a.n_items, next, b + GW * 4 + oct < a.n_items, li,
+                               ll_acc, min_norm);
+            hdr = next;
+            next = after;
+        }
     } else {
         /* this CTA's range of items, cut at tile-block boundaries; a new block = a new tile */
         const int lo = a.cta_begin[blockIdx.x], hi = a.cta_begin[blockIdx.x + 1];
@@ -271,8 +359,17 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) tile_pass_kernel(const TileAr
                 if (!first_tile) __syncthreads(); /* everybody is done with the previous tile */
                 first_tile = false;
                 load_tile(blk);
-                for (int64_t b = cur + warp * 4; b < seg_end; b += NW * 4)
-                    tile_batch<KC, LL>(a, tile, b, seg_end, li, oct, ll_acc, min_norm);
+                auto header = [&](int64_t i) {
+                    return i < seg_end ? __ldg(a.items + i) : make_int4(0, 0, 0, 0);
+                };
+                int4 hdr = header(cur + warp * 4 + oct), next = header(cur + warp * 4 + NW * 4 + oct);
+                for (int64_t b = cur + warp * 4; b < seg_end; b += NW * 4) {
+                    const int4 after = header(b + 2 * NW * 4 + oct);
+                    tile_batch<KC, LL>(a, tile, hdr, b + oct < seg_end, next, b + NW * 4 + oct < seg_end, li,
+                                       ll_acc, min_norm);
+                    hdr = next;
+                    next = after;
+                }
                 cur = seg_end;
             }
             ++blk;
@@ -338,7 +435,8 @@ struct SlotMap {
  * length; one warp per item; item r covers entries [beg[r], end[r]) */
 __global__ void tile_count_kernel(const int32_t *__restrict__ beg, const int32_t *__restrict__ end,
                                   int64_t n_items, const int2 *__restrict__ ent, const SlotMap map,
-                                  int32_t *__restrict__ head_len, int32_t *__restrict__ tail_len)
+                                  int32_t *__restrict__ head_len, int32_t *__restrict__ head_mem,
+                                  int32_t *__restrict__ tail_len)
 {
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= n_items) return;
@@ -357,7 +455,8 @@ __global__ void tile_count_kernel(const int32_t *__restrict__ beg, const int32_t
 #pragma unroll
     for (int q = 0; q < 8; ++q) mx = max(mx, cnt[q]);
     if (lane == 0) {
-        head_len[r] = 8 * mx;
+        head_len[r] = 8 * mx;                 /* slots the kernel walks */
+        head_mem[r] = (8 * mx + 31) & ~31;    /* slots in memory: whole blocks of 4 steps */
         if (tail_len) tail_len[r] = (p1 - p0) - head;
     }
 }
@@ -376,7 +475,9 @@ __global__ void tile_place_kernel(const int32_t *__restrict__ beg, const int32_t
     const int lane = threadIdx.x & 31;
     const int32_t p0 = beg[r], p1 = end[r];
     const int32_t h0 = head_indptr[r], h1 = head_indptr[r + 1], t0 = tail_indptr ? tail_indptr[r] : 0;
-    for (int32_t h = h0 + lane; h < h1; h += 32) head_ent[h] = make_int2((h - h0) & 7, 0);
+    /* memory order inside a block of 4 steps (32 slots): lane-major, [lane p][step q] at
+     * 4 p + q — a lane's four entries are one 32-byte load */
+    for (int32_t h = h0 + lane; h < h1; h += 32) head_ent[h] = make_int2(((h - h0) & 31) >> 2, 0);
     __syncwarp();
     int base[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int tbase = 0;
@@ -399,7 +500,7 @@ __global__ void tile_place_kernel(const int32_t *__restrict__ beg, const int32_t
         }
         const unsigned mt = __ballot_sync(0xffffffffu, ok && s < 0);
         if (ok) {
-            if (s >= 0) head_ent[h0 + rank * 8 + (s & 7)] = make_int2(s, e.y);
+            if (s >= 0) head_ent[h0 + (rank >> 2) * 32 + (s & 7) * 4 + (rank & 3)] = make_int2(s, e.y);
             else if (tail_ent) tail_ent[t0 + tbase + __popc(mt & lt)] = e;
         }
         tbase += __popc(mt);
@@ -456,6 +557,18 @@ __global__ void term_item_keys_kernel(const int32_t *__restrict__ head_len, int6
     if (v >= n_items) return;
     const int per = block_rows / 8 + 1;
     keys[v] = (int32_t)(v % n_blocks) * per + (block_rows / 8 - head_len[v] / 8);
+}
+
+/* the items in launch order as self-contained headers {first entry, entries, owned row, slot} */
+__global__ void tile_headers_kernel(const int32_t *__restrict__ order, const int32_t *__restrict__ indptr,
+                                    const int32_t *__restrict__ head_len,
+                                    const int32_t *__restrict__ own_row, int64_t n_items,
+                                    int4 *__restrict__ items)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    const int32_t v = order[i];
+    items[i] = make_int4(indptr[v], head_len[v], own_row ? own_row[v] : v, v);
 }
 
 /* work of the items in launch order (padded entries + a per-item constant), input of the scan

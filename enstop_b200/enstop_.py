@@ -119,6 +119,15 @@ def stack_in_member_order(stacked, shards, k):
     return out
 
 
+def distances_in_member_order(dist, shards, k):
+    """The same re-ordering for an all-pairs matrix computed on the shard-major stack."""
+    order = [r for members in shards for r in members]
+    perm = np.empty(len(order) * k, dtype=np.int64)       # perm[new row] = old row
+    for pos, r in enumerate(order):
+        perm[r * k:(r + 1) * k] = np.arange(pos * k, (pos + 1) * k)
+    return dist[np.ix_(perm, perm)]
+
+
 def resolve_devices(devices=None, n_jobs=None):
     count = _lib.device_count()
     if count < 1:
@@ -184,10 +193,12 @@ def release_member_contexts(contexts, failed=False):
 
 
 def ensemble_of_topics(X, k, model="plsa", n_jobs=4, n_runs=16, parallelism="threads",
-                       devices=None, return_seeds=False, **kwargs):
+                       devices=None, return_seeds=False, return_distances=None, **kwargs):
     """Topics of ``n_runs`` bootstrapped pLSA fits stacked as [n_runs * k, n_words]
     (enstop_.py:164-231).  Members are sharded over ``devices`` (default: all visible GPUs,
-    at most ``n_jobs`` of them), member r on device r mod G."""
+    at most ``n_jobs`` of them), member r on device r mod G.  ``return_distances``
+    ("hellinger" / "kl"): also the all-pairs matrix of enstop_.py:234-263, computed on the
+    gathered stack while it is still on the root GPU; the result is then a tuple."""
     if model != "plsa":
         raise ValueError('Model must be "plsa" (the sklearn NMF alternative is not offered)')
     if parallelism not in ("dask", "joblib", "threads", "none"):
@@ -221,14 +232,21 @@ def ensemble_of_topics(X, k, model="plsa", n_jobs=4, n_runs=16, parallelism="thr
             raise errors[0]
         stacked = _lib.gather_topics([results[d][0] for d in used],
                                      [len(assign[d]) for d in used])
+        dist = None
+        if return_distances is not None:
+            dist = _lib.gathered_distances(results[used[0]][0], return_distances)
     except BaseException:
         release_member_contexts(all_contexts, failed=True)
         raise
     release_member_contexts(all_contexts)
-    out = stack_in_member_order(stacked, [results[d][1] for d in used], k)
+    orders = [results[d][1] for d in used]
+    out = stack_in_member_order(stacked, orders, k)
+    extra = []
     if return_seeds:
-        return out, seeds
-    return out
+        extra.append(seeds)
+    if return_distances is not None:
+        extra.append(distances_in_member_order(dist, orders, k))
+    return (out, *extra) if extra else out
 
 
 # ---- distances between topics (enstop_.py:234-263) ------------------------------------------
@@ -330,11 +348,31 @@ def ensemble_fit(X, estimated_n_topics=10, model="plsa", init="random", min_samp
     X = check_array(X, accept_sparse="csr", dtype=np.float32)
     if not issparse(X):
         X = csr_matrix(X, dtype=np.float32)
-    all_topics = ensemble_of_topics(
+    # the combiner's distance matrix comes from the stack while it is resident on the root GPU
+    have_umap = True
+    if topic_combination == "hellinger_umap":
+        try:
+            import umap  # noqa: F401
+        except ImportError:
+            have_umap = False
+    kind = {"kl_divergence": "kl", "hellinger": "hellinger",
+            "hellinger_umap": None if have_umap else "hellinger"}[topic_combination]
+    res = ensemble_of_topics(
         X, estimated_n_topics, model, n_jobs, n_starts, parallelism, devices=devices,
         init=init, n_iter=n_iter, n_iter_per_test=n_iter_per_test, tolerance=tolerance,
-        e_step_thresh=e_step_thresh, bootstrap=bootstrap, random_state=random_state)
-    stable_topics = _topic_combiner[topic_combination](all_topics, min_samples, min_cluster_size)
+        e_step_thresh=e_step_thresh, bootstrap=bootstrap, random_state=random_state,
+        return_distances=kind)
+    all_topics, dist = res if kind is not None else (res, None)
+    if topic_combination == "hellinger_umap" and have_umap:
+        stable_topics = generate_combined_topics_hellinger_umap(all_topics, min_samples, min_cluster_size)
+    elif topic_combination == "hellinger_umap":
+        warn("umap is not installed: topic_combination='hellinger_umap' falls back to "
+             "'hellinger' (HDBSCAN on the exact Hellinger distance matrix)")
+        stable_topics = generate_combined_topics_hellinger(all_topics, min_samples, min_cluster_size,
+                                                           distances=dist)
+    else:
+        stable_topics = _topic_combiner[topic_combination](all_topics, min_samples, min_cluster_size,
+                                                           distances=dist)
     if stable_topics.shape[0] == 0:
         raise ValueError("no stable topic cluster was found; lower min_cluster_size or "
                          "min_samples, or raise n_starts")

@@ -228,6 +228,11 @@ int plsa_comm_gather_topics(plsa_comm *comm, plsa_ctx *ctx, const int32_t *n_per
 #define PLSA_DIST_KL 1
 int plsa_topic_distances(int32_t device, const float *topics, int64_t n_topics, int64_t n_terms,
                          int32_t kind, double *out);
+/* The same on the stack of topic matrices the last plsa_gather_topics / plsa_comm_gather_topics
+ * left on this (root) context's device: the clustering stage of the ensemble
+ * (enstop_.py:266-351) gets its distance matrix without uploading the stack again.
+ * out == NULL: only *n_topics is returned. */
+int plsa_gathered_distances(plsa_ctx *ctx, int32_t kind, double *out, int64_t *n_topics);
 
 /* ---- one fit over several GPUs: documents sharded by rows -------------------------------------
  * Generalises the row blocking of enstop/block_parallel_plsa.py:156-185 and

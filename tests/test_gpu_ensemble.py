@@ -54,6 +54,21 @@ def test_nccl_gather_across_devices(corpus):
     assert np.array_equal(stacked, np.vstack(topics))
 
 
+def test_distances_of_the_gathered_stack(corpus):
+    """The all-pairs matrix computed on the stack the gather left on the root GPU equals the one
+    computed from the host copy (and the float64 oracle), re-ordered to member order."""
+    X = corpus
+    k, n_runs = 5, 5
+    kw = dict(n_iter=8, n_iter_per_test=5, tolerance=0.0, e_step_thresh=1e-32, random_state=3)
+    for kind, ref in (("hellinger", oracle.all_pairs_hellinger_distance),
+                      ("kl", oracle.all_pairs_kl_divergence)):
+        stacked, dist = enstop_.ensemble_of_topics(X, k, n_runs=n_runs, n_jobs=8,
+                                                   return_distances=kind, **kw)
+        assert dist.shape == (n_runs * k, n_runs * k)
+        assert np.array_equal(dist, _lib.topic_distances(stacked, kind, 0))
+        assert np.allclose(dist, ref(stacked), rtol=1e-5, atol=2e-6)
+
+
 def test_ensemble_topics_estimator(corpus):
     X = corpus
     model = EnsembleTopics(n_components=6, n_starts=6, n_iter=30, topic_combination="hellinger",

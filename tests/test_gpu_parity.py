@@ -10,6 +10,7 @@ fixtures.  Tolerances (relative L2 over the whole array unless noted):
   (c1_planted) and reported otherwise.
 """
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -385,3 +386,51 @@ def test_device_plan_is_the_host_plan(chunk, golden_c1_planted):
                 assert np.array_equal(d[key], h[key]), (which, key)
         tail = ctx.debug_items(2)
         assert 0 < tail["indptr"][-1] < X.nnz
+
+
+def test_properties_at_config3_size():
+    """BASELINE config 3 in full (the config-2 matrix at k = 128, the wide-row kernels
+    row_pass_kernel<32, 4, ...>): size-independent properties and the exact log-likelihood of the
+    returned model (float64 oracle pass over all ~10 M entries x 128 topics)."""
+    X = synth.make_config("C3")
+    k = synth.CONFIGS["C3"]["k"]
+    sw = np.ones(X.shape[0], dtype=np.float32)
+    pzd, pwz, info = plsa.plsa_fit(X, k, sw, n_iter=11, n_iter_per_test=5, tolerance=0.0,
+                                   random_state=42, device=0, return_info=True)
+    assert info["n_iter"] == 11 and len(info["ll_trace"]) == 4
+    assert pzd.shape == (X.shape[0], k) and pwz.shape == (k, X.shape[1])
+    assert np.allclose(pzd.sum(axis=1), 1.0, atol=5e-6)
+    assert np.allclose(pwz.sum(axis=1), 1.0, atol=5e-6)
+    assert pzd.min() >= 0 and pwz.min() >= 0 and np.isfinite(pzd).all() and np.isfinite(pwz).all()
+    ll = info["ll_trace"]
+    assert np.all(np.diff(ll) > 0)
+    assert abs(oracle.log_likelihood(X, pwz, pzd) - ll[-1]) / abs(ll[-1]) < 1e-6
+    pzd2, pwz2 = plsa.plsa_fit(X, k, sw, n_iter=11, n_iter_per_test=5, tolerance=0.0,
+                               random_state=42, device=0)
+    assert np.array_equal(pzd, pzd2) and np.array_equal(pwz, pwz2)   # run-to-run bit equality
+
+
+@pytest.mark.skipif(not os.environ.get("ENSTOP_B200_SLOW"), reason="config-5 size: set ENSTOP_B200_SLOW=1 "
+                    "(minutes of host time to generate 200 M entries)")
+def test_properties_at_config5_size():
+    """BASELINE config 5 in full (1M x 200k, ~200 M stored entries, k = 20): int32 row pointers
+    near 2^28, the 2^27-entry radix sort, factors beyond the 1-D texture limit — size-independent
+    properties plus the exact log-likelihood on a 1 % row sample."""
+    X = synth.make_config("C5")
+    assert abs(X.nnz - 200_000_000) < 6_000_000
+    k = 20
+    sw = np.ones(X.shape[0], dtype=np.float32)
+    pzd, pwz, info = plsa.plsa_fit(X, k, sw, n_iter=6, n_iter_per_test=5, tolerance=0.0,
+                                   random_state=42, device=0, return_info=True)
+    assert info["n_iter"] == 6 and len(info["ll_trace"]) == 3
+    assert np.allclose(pzd.sum(axis=1), 1.0, atol=5e-6)
+    assert np.allclose(pwz.sum(axis=1), 1.0, atol=5e-6)
+    assert pzd.min() >= 0 and pwz.min() >= 0 and np.isfinite(pzd).all() and np.isfinite(pwz).all()
+    assert np.all(np.diff(info["ll_trace"]) > 0)
+    rows = np.random.RandomState(0).choice(X.shape[0], X.shape[0] // 100, replace=False)
+    rows.sort()
+    with _lib.Context(0) as ctx:        # engine's own LL of the sample against the float64 oracle
+        ctx.upload_csr(X[rows])
+        ctx.set_factors(pzd[rows], pwz)
+        ll_sample = ctx.log_likelihood()
+    assert abs(oracle.log_likelihood(X[rows], pwz, pzd[rows]) - ll_sample) / abs(ll_sample) < 1e-6
