@@ -27,6 +27,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
               "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden,-mavx2", "-diag-suppress", "550"]
 
 PLSA_OK, PLSA_EINVAL, PLSA_ECUDA, PLSA_ENOMEM, PLSA_ENCCL = 0, 1, 2, 3, 4
+ABI_VERSION = 200   # plsa_version() of the library this binding was written against
 PROF_SLOTS = ("doc_pass", "word_pass", "fixup", "normalize", "loglik", "doc_head", "term_head")
 
 _i32p = ctypes.POINTER(ctypes.c_int32)
@@ -67,6 +68,7 @@ SIGNATURES = {
     "plsa_set_option": (ctypes.c_int, [_ctx, ctypes.c_char_p, _i64]),
     "plsa_plan_items": (ctypes.c_int, [_i32p, _i64, _i64, _i32, _i64, _i64p, _i32p, _i32p,
                                        _i32p, _i32p, _i64p, _i32p, _i32p]),
+    "plsa_last_distances_ms": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)]),
     "plsa_gathered_distances": (ctypes.c_int, [_ctx, _i32, _f64p, _i64p]),
     "plsa_debug_items": (ctypes.c_int, [_ctx, _i32, _i64, _i64p, _i32p, _i32p, _i32p, _i32p, _i64p,
                                         _i32p, _i32p, _i64p, _i32p, _i32p, _i64]),
@@ -151,10 +153,21 @@ def lib():
             L = ctypes.CDLL(SO_PATH)
         except OSError as exc:
             raise PlsaError("cannot load %s: %s" % (SO_PATH, exc)) from exc
-        for name, (res, args) in SIGNATURES.items():
-            fn = getattr(L, name)
-            fn.restype = res
-            fn.argtypes = args
+        try:
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(L, name)
+                fn.restype = res
+                fn.argtypes = args
+        except AttributeError as exc:
+            raise PlsaError("%s is older than this binding (%s): rebuild it with "
+                            "enstop_b200._lib.build(force=True)" % (SO_PATH, exc)) from exc
+        if L.plsa_version() != ABI_VERSION:
+            raise PlsaError("%s has ABI version %d, this binding expects %d: rebuild it with "
+                            "enstop_b200._lib.build(force=True)" % (SO_PATH, L.plsa_version(), ABI_VERSION))
+        if not os.environ.get("ENSTOP_B200_LIB") and needs_build():
+            import warnings
+            warnings.warn("libplsa_b200.so is older than its sources (csrc/, include/): the loaded "
+                          "library may not match them; run enstop_b200._lib.build()", RuntimeWarning)
         _lib = L
     return _lib
 
@@ -461,6 +474,11 @@ class Context:
 _pool = {}
 _pool_lock = threading.Lock()
 _POOL_MAX_PER_DEVICE = 2
+# A pooled context keeps its device buffers (two copies of the corpus, factors, sort scratch:
+# roughly 40 bytes per stored entry).  Contexts of corpora above this many stored entries are
+# destroyed instead of pooled, so that a long-lived process does not sit on gigabytes of HBM;
+# ENSTOP_B200_POOL_MAX_NNZ overrides (0 disables the pool).
+_POOL_MAX_NNZ = int(os.environ.get("ENSTOP_B200_POOL_MAX_NNZ", 64_000_000))
 
 
 def acquire_context(device=0):
@@ -473,11 +491,16 @@ def acquire_context(device=0):
 
 
 def release_context(ctx):
-    with _pool_lock:
-        free = _pool.setdefault(ctx.device, [])
-        if len(free) < _POOL_MAX_PER_DEVICE and ctx._h:
-            free.append(ctx)
-            return
+    try:
+        small = ctx._h and ctx.shape[2] <= _POOL_MAX_NNZ
+    except PlsaError:
+        small = False
+    if small:
+        with _pool_lock:
+            free = _pool.setdefault(ctx.device, [])
+            if len(free) < _POOL_MAX_PER_DEVICE:
+                free.append(ctx)
+                return
     ctx.close()
 
 
@@ -528,6 +551,13 @@ def topic_distances(topics, kind, device=0):
     check(lib().plsa_topic_distances(int(device), _ptr(topics, _f32p), n, m, code,
                                      _ptr(out, _f64p)))
     return out
+
+
+def last_distances_ms():
+    """Device time of the kernels of this thread's last topic_distances / gathered_distances."""
+    ms = _f32(0.0)
+    check(lib().plsa_last_distances_ms(ctypes.byref(ms)))
+    return ms.value
 
 
 def gathered_distances(ctx, kind):

@@ -14,9 +14,14 @@
  * tests/test_host_cpu.py checks bit-equality with numpy for many seeds, positions and
  * shapes, and with the reference's own initial factors stored in tests/golden.
  */
+#include <sched.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+
+#include <algorithm>
+#include <thread>
+#include <vector>
 
 #if defined(__AVX2__)
 #include <immintrin.h>
@@ -140,22 +145,17 @@ struct Stream {
 
 } // namespace
 
-/* Draw rows*cols doubles (row-major, the order rng.rand(rows, cols) produces them),
- * L1-normalise every row with a float64 marginal accumulated left to right
- * (enstop/utils.py:22-41; rows whose marginal is not > 0 are left as drawn) and store
- * float32 (plsa.py:709-710).  key[624] / *pos are the RandomState's MT19937 state, updated
- * in place.  out_f64 (optional) receives the normalised float64 values. */
-API int plsa_host_random_rows(uint32_t *key, int32_t *pos, int64_t rows, int64_t cols, float *out,
-                              double *out_f64)
+/* rows [r0, r1) of the draw from a generator state positioned at the first word of row r0 */
+static int draw_rows(uint32_t *key, int32_t *pos, int64_t r0, int64_t r1, int64_t cols, float *out,
+                     double *out_f64)
 {
-    if (!key || !pos || !out || rows < 0 || cols < 0 || *pos < 0 || *pos > MT_N) return PLSA_EINVAL;
     Stream s;
     s.key = key;
     s.pos = *pos;
     s.temper_from(s.pos < MT_N ? s.pos : MT_N);
     double *buf = (double *)malloc(sizeof(double) * (size_t)(cols > 0 ? cols : 1));
     if (!buf) return PLSA_ENOMEM;
-    for (int64_t r = 0; r < rows; ++r) {
+    for (int64_t r = r0; r < r1; ++r) {
         s.fill(buf, cols);
         double marginal = 0.0;
         for (int64_t c = 0; c < cols; ++c) marginal += buf[c]; /* left to right, as utils.py:25-29 */
@@ -176,5 +176,83 @@ API int plsa_host_random_rows(uint32_t *key, int32_t *pos, int64_t rows, int64_t
     }
     free(buf);
     *pos = s.pos;
+    return PLSA_OK;
+}
+
+/* advance the state by `words` outputs without producing them (twist only: the tempering, the
+ * conversion to doubles and the normalisation are four fifths of a draw's cost) */
+static void skip_words(uint32_t *key, int32_t *pos, int64_t words)
+{
+    int p = *pos;
+    while (words > 0) {
+        if (p == MT_N) {
+            mt_refill(key);
+            p = 0;
+        }
+        const int64_t take = words < (int64_t)(MT_N - p) ? words : (int64_t)(MT_N - p);
+        p += (int)take;
+        words -= take;
+    }
+    *pos = p;
+}
+
+/* worker threads of one draw: the cores this process may use, shared with the other ranks of
+ * the box (LOCAL_WORLD_SIZE) and with the upload threads running beside the draw */
+static int init_threads()
+{
+    static const int n = [] {
+        if (const char *e = getenv("ENSTOP_B200_INIT_THREADS")) return std::max(1, std::min(8, atoi(e)));
+        cpu_set_t set;
+        int cores = 0;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set);
+        if (cores <= 0) cores = (int)std::thread::hardware_concurrency();
+        int ranks = 1;
+        if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+        return std::max(1, std::min(4, cores / ranks / 2));
+    }();
+    return n;
+}
+
+/* Draw rows*cols doubles (row-major, the order rng.rand(rows, cols) produces them),
+ * L1-normalise every row with a float64 marginal accumulated left to right
+ * (enstop/utils.py:22-41; rows whose marginal is not > 0 are left as drawn) and store
+ * float32 (plsa.py:709-710).  key[624] / *pos are the RandomState's MT19937 state, updated
+ * in place.  out_f64 (optional) receives the normalised float64 values.
+ *
+ * The MT19937 stream is sequential, but advancing it is cheap next to consuming it: the rows
+ * are cut into one slice per worker thread, this thread skips the state ahead to the start of
+ * each slice (a snapshot per slice) and the workers produce their slices in parallel — the
+ * same words land in the same places as in a serial draw. */
+API int plsa_host_random_rows(uint32_t *key, int32_t *pos, int64_t rows, int64_t cols, float *out,
+                              double *out_f64)
+{
+    if (!key || !pos || !out || rows < 0 || cols < 0 || *pos < 0 || *pos > MT_N) return PLSA_EINVAL;
+    const int64_t total = rows * cols;
+    int T = init_threads();
+    if (total < (int64_t)1 << 18 || rows < 2 * T) T = 1;
+    if (T == 1) return draw_rows(key, pos, 0, rows, cols, out, out_f64);
+    struct Slice { uint32_t key[MT_N]; int32_t pos; int64_t r0, r1; int rc; };
+    std::vector<Slice> slices((size_t)T);
+    std::vector<std::thread> workers;
+    try {
+        for (int t = 0; t < T; ++t) {
+            Slice &sl = slices[(size_t)t];
+            sl.r0 = rows * t / T;
+            sl.r1 = rows * (t + 1) / T;
+            sl.rc = PLSA_OK;
+            memcpy(sl.key, key, sizeof(sl.key));
+            sl.pos = *pos;
+            workers.emplace_back([&sl, cols, out, out_f64]() {
+                sl.rc = draw_rows(sl.key, &sl.pos, sl.r0, sl.r1, cols, out, out_f64);
+            });
+            skip_words(key, pos, 2 * (sl.r1 - sl.r0) * cols); /* the caller's state: behind this slice */
+        }
+    } catch (...) { /* thread creation failed: finish what was started, report */
+        for (auto &w : workers) w.join();
+        return PLSA_ENOMEM;
+    }
+    for (auto &w : workers) w.join();
+    for (const Slice &sl : slices)
+        if (sl.rc != PLSA_OK) return sl.rc;
     return PLSA_OK;
 }

@@ -171,11 +171,10 @@ struct plsa_ctx {
     ItemSet doc_items, term_items;
     TileSet tiles;
     TermTiles tterm;
-    int term_tiled_opt = 0;             /* option "term_tiled": tile the term pass too (with "tiled") */
+    int term_tiled_opt = 1;             /* option "term_tiled": tile the term pass too (with "tiled") */
     int64_t term_tile_min = 12;         /* option "term_tile_min": entries per (term, block) item, on average, for a term to be tiled */
     bool a_comp[2] = {false, false};    /* tterm.acomp[i] is the compact image of A[i] */
-    int tiled_opt = 0;                  /* option "tiled": -1 by corpus size, 0 off (default: measured no faster
-                                           at C2, profiles/r2_kernel_experiments.md), 1 on where possible */
+    int tiled_opt = -1;                 /* option "tiled": -1 by corpus size (tiled_wanted), 0 off, 1 on where possible */
     int64_t tile_bytes = 200 * 1024;    /* option "tile_kb": shared memory of the tile        */
     bool b_norm[2] = {false, false};    /* B[i] is column-normalised in place, tiles.img[i] holds its tile rows */
     int n_sms = 0;
@@ -200,6 +199,7 @@ struct plsa_ctx {
     char *pin_factors = nullptr;
     size_t pin_factors_cap = 0;
     cudaTextureObject_t texA[2] = {0, 0}, texB[2] = {0, 0};
+    std::map<cudaTextureObject_t *, std::pair<void *, size_t>> tex_bound; /* what each is bound to */
     size_t tex_max_texels = 0;
 
     /* model */
@@ -797,11 +797,15 @@ static bool tiled_possible(const plsa_ctx *ctx, int kp)
            c.nnz > 0 && c.nnz < ((int64_t)1 << 28); /* padded head slots (< 8 nnz) stay int32 */
 }
 
+/* Automatic choice (option "tiled" = -1, the default).  Measured on B200
+ * (profiles/r2_kernel_experiments.md): at C2 (10 M entries, both factors deep inside the L2) the
+ * tiled passes are no faster than the group-per-row passes, whose gathers mostly hit L1/L2; at
+ * C5 (200 M entries, P(z|d) = 128 MB > L2) they take 3.22 instead of 4.42 ms per iteration. */
 static bool tiled_wanted(const plsa_ctx *ctx, int kp)
 {
     if (!tiled_possible(ctx, kp)) return false;
     if (ctx->tiled_opt > 0) return true;
-    return ctx->cur().nnz >= 2'000'000; /* below this the tile load and two launches do not pay */
+    return ctx->cur().nnz >= 64'000'000;
 }
 
 typedef void (*tile_fn)(const TileArgs);
@@ -1147,7 +1151,7 @@ static void corpus_changed(plsa_ctx *ctx)
 /* ============================================================================================
  * C ABI
  * ============================================================================================ */
-API int plsa_version(void) { return 100; }
+API int plsa_version(void) { return 200; }
 
 API int plsa_device_count(int *count)
 {
@@ -1432,6 +1436,11 @@ API int plsa_corpus_shape(const plsa_ctx *ctx, int64_t *n_docs, int64_t *n_terms
  * which leaves the LSU/shared-memory pipe to the shuffles.  0 if the buffer is too large. */
 static int make_texture(plsa_ctx *ctx, cudaTextureObject_t *tex, void *ptr, size_t bytes)
 {
+    /* repeated fits reuse their factor buffers: keep the texture object of an unchanged
+     * (pointer, size) — creating four of them cost ~1 ms of every plsa_set_factors */
+    auto &bound = ctx->tex_bound[tex];
+    if (*tex && bound.first == ptr && bound.second == bytes) return PLSA_OK;
+    bound = std::make_pair(ptr, bytes);
     if (*tex) {
         cudaDestroyTextureObject(*tex);
         *tex = 0;
@@ -2356,6 +2365,15 @@ API int plsa_b200_refit_inner(const int32_t *X_rows, const int32_t *X_cols, cons
 }
 
 /* ---- all-pairs distances between topic vectors (ensemble clustering input) ------------------------ */
+static thread_local float g_distances_kernel_ms = 0.f; /* device time of the last call's kernels */
+
+API int plsa_last_distances_ms(float *kernel_ms)
+{
+    if (!kernel_ms) return PLSA_EINVAL;
+    *kernel_ms = g_distances_kernel_ms;
+    return PLSA_OK;
+}
+
 /* distances of a [n_topics, n_terms] matrix that already lives on `device` (host_src: uploaded
  * first); out is a host array [n_topics, n_topics] */
 static int topic_distances_impl(int32_t device, const float *dev_src, const float *host_src,
@@ -2399,6 +2417,10 @@ static int topic_distances_impl(int32_t device, const float *dev_src, const floa
             return done(PLSA_ECUDA, "upload");
         src = P.as<float>();
     }
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, st);
     topic_rowsum_kernel<<<(unsigned)n_topics, 256, 0, st>>>(src, n_terms, l1.as<double>());
     if (n_terms > 0)
         topic_prep_kernel<<<(unsigned)cdiv((int64_t)cells, 256), 256, 0, st>>>(
@@ -2412,10 +2434,14 @@ static int topic_distances_impl(int32_t device, const float *dev_src, const floa
                                                     part.as<double>());
     topic_pairs_finish_kernel<<<(unsigned)cdiv(n_topics * n_topics, 256), 256, 0, st>>>(
         part.as<double>(), slices, l1.as<double>(), (int)n_topics, kind, D.as<double>());
-    if ((e = cudaGetLastError()) != cudaSuccess) return done(PLSA_ECUDA, "launch");
-    if ((e = cudaMemcpyAsync(out, D.p, (size_t)n_topics * n_topics * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
-        (e = cudaStreamSynchronize(st)) != cudaSuccess)
-        return done(PLSA_ECUDA, "download");
+    cudaEventRecord(ev1, st);
+    if ((e = cudaGetLastError()) == cudaSuccess)
+        e = cudaMemcpyAsync(out, D.p, (size_t)n_topics * n_topics * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) cudaEventElapsedTime(&g_distances_kernel_ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    if (e != cudaSuccess) return done(PLSA_ECUDA, "kernels / download");
     return done(PLSA_OK, "");
 }
 
@@ -2729,6 +2755,10 @@ struct plsa_comm {
     ncclComm_t comm = nullptr;
     int device = 0, n_ranks = 1, rank = 0;
     cudaStream_t stream = nullptr;
+    /* plsa_comm_abort may come from another thread (a peer rank of a sharded fit failed): the
+     * handle is only read or dropped under this mutex; collectives are enqueued (not waited
+     * for) under it, so an abort is never held up by a rank that is blocked on the device */
+    std::mutex mu;
 };
 
 API int plsa_nccl_unique_id(char *id)
@@ -2798,8 +2828,12 @@ static int shard_allreduce(plsa_ctx *ctx, void *buf, size_t count, bool f64, cud
     if (!c || c->n_ranks < 2 || count == 0) return PLSA_OK;
     Nccl *nc = load_nccl();
     if (!nc) return ctx->fail(PLSA_ENCCL, "sharded fit: libnccl.so.2 could not be loaded");
-    const int r = nc->AllReduce(buf, buf, count, f64 ? kNcclDouble : kNcclFloat, kNcclSum, c->comm,
-                                stream);
+    int r;
+    {
+        std::lock_guard<std::mutex> lock(c->mu);
+        if (!c->comm) return ctx->fail(PLSA_ENCCL, "sharded fit: the communicator was aborted (a peer rank failed)");
+        r = nc->AllReduce(buf, buf, count, f64 ? kNcclDouble : kNcclFloat, kNcclSum, c->comm, stream);
+    }
     ctx->launches++;
     if (r != 0) {
         const int rc = nccl_fail(nc, "sharded fit: ncclAllReduce", r);
@@ -2923,6 +2957,7 @@ API int plsa_comm_abort(plsa_comm *c)
 {
     if (!c) return PLSA_OK;
     cudaSetDevice(c->device);
+    std::lock_guard<std::mutex> lock(c->mu);
     if (c->comm) {
         Nccl *nc = load_nccl();
         if (nc && nc->CommAbort) nc->CommAbort(c->comm);

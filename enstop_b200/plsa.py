@@ -285,11 +285,32 @@ def _plsa_fit_sharded(X, k, sample_weight, init, n_iter, n_iter_per_test, tolera
     comms = comms or [None] * G
     results, errors = [None] * G, [None] * G
     exchange = ThreadPeerExchange(devices) if p2p else None
+    # Every rank's communicator exists before any rank touches its shard: a rank that fails later
+    # (upload, allocation) can then abort the others instead of leaving them in ncclCommInitRank.
+    n_dev = _lib.device_count()
+    bad = [d for d in devices if not 0 <= d < n_dev]
+    if bad or len(set(devices)) != G:
+        raise ValueError("devices must be distinct CUDA ordinals below {}: {}".format(n_dev, devices))
+    if any(c is None for c in comms):
+        def make_comm(r):
+            try:
+                comms[r] = _lib.Comm(devices[r], G, r, uid)
+            except BaseException as exc:
+                errors[r] = exc
+        makers = [threading.Thread(target=make_comm, args=(r,)) for r in range(G)]
+        for t in makers:
+            t.start()
+        for t in makers:
+            t.join()
+        if any(e is not None for e in errors):
+            for c in comms:
+                if c is not None:
+                    c.abort()
+                    c.close()
+            raise next(e for e in errors if e is not None)
 
     def worker(r):
         try:
-            if comms[r] is None:
-                comms[r] = _lib.Comm(devices[r], G, r, uid)
             comm = comms[r]
             lo, hi = bounds[r], bounds[r + 1]
             results[r] = plsa_fit_shard(X[lo:hi], k, p_z_given_d[lo:hi], p_w_given_z,

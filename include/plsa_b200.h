@@ -233,6 +233,8 @@ int plsa_topic_distances(int32_t device, const float *topics, int64_t n_topics, 
  * (enstop_.py:266-351) gets its distance matrix without uploading the stack again.
  * out == NULL: only *n_topics is returned. */
 int plsa_gathered_distances(plsa_ctx *ctx, int32_t kind, double *out, int64_t *n_topics);
+/* Device time (CUDA events) of the kernels of this thread's last distance call. */
+int plsa_last_distances_ms(float *kernel_ms);
 
 /* ---- one fit over several GPUs: documents sharded by rows -------------------------------------
  * Generalises the row blocking of enstop/block_parallel_plsa.py:156-185 and

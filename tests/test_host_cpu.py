@@ -28,7 +28,7 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(L, name), name
     # and the binding table covers exactly the header
     assert sorted(_lib.SIGNATURES) == names
-    assert L.plsa_version() >= 100
+    assert L.plsa_version() >= 200
 
 
 def test_binary_is_sm100a_only():
