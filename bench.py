@@ -219,8 +219,8 @@ TOL_VS_REFERENCE = 3e-4         # tests/test_gpu_parity.py TOL_REF_50 (the refer
 
 def sharded_fit_checks(plumb, rank, world, device):
     """N > 1, before anything is timed: ONE fit of the committed C1 golden corpus with its
-    documents sharded over all N ranks — through the peer-memory reduce kernel and through
-    ncclAllReduce — against the same fit on one GPU and against the reference's own output
+    documents sharded over all N ranks — through the peer-memory kernels (one-shot and two-shot exchange) and
+    through ncclAllReduce — against the same fit on one GPU and against the reference's own output
     (tests/golden/c1_planted.npz, made by tests/golden/make_golden.py from enstop/plsa.py).
     Returns the list of check records (rank 0; every rank learns the verdict)."""
     import scipy.sparse as sp
@@ -239,18 +239,26 @@ def sharded_fit_checks(plumb, rank, world, device):
     uid = plumb.bcast_bytes(_lib.Comm.unique_id() if rank == 0 else None)
     comm = _lib.Comm(device, world, rank, uid)
     checks = []
-    for path in ("peer-memory kernel", "ncclAllReduce"):
+    forced = os.environ.get("ENSTOP_B200_TWO_SHOT")
+    for path in ("peer-memory kernel, one-shot", "peer-memory kernel, two-shot", "ncclAllReduce"):
         ex = IpcExchange(plumb, no_p2p=(path == "ncclAllReduce"))
-        pzd_rows, pwz, info = plsa.plsa_fit_shard(X[lo:hi], k, g["pzd0"][lo:hi], g["pwz0"], sw[lo:hi],
-                                                  comm, device, n_iter=n_iter, tolerance=0.0,
-                                                  exchange=ex)
+        os.environ["ENSTOP_B200_TWO_SHOT"] = "1" if path.endswith("two-shot") else "0"
+        try:
+            pzd_rows, pwz, info = plsa.plsa_fit_shard(X[lo:hi], k, g["pzd0"][lo:hi], g["pwz0"],
+                                                      sw[lo:hi], comm, device, n_iter=n_iter,
+                                                      tolerance=0.0, exchange=ex)
+        finally:
+            if forced is None:
+                del os.environ["ENSTOP_B200_TWO_SHOT"]
+            else:
+                os.environ["ENSTOP_B200_TWO_SHOT"] = forced
         parts = plumb.allgather(pzd_rows)
         pwzs = plumb.allgather(pwz if rank in (0, world - 1) else None)
         used = plumb.allgather(bool(info["p2p"]))
         if rank == 0:
             pzd = np.concatenate(parts)
             rec = {"check": "doc-sharded fit of C1 golden over %d ranks, %s" % (world, path),
-                   "exchange_used": "peer-memory kernel" if all(used) else "ncclAllReduce",
+                   "exchange_used": path if all(used) else "ncclAllReduce",
                    "iters": int(info["n_iter"]),
                    "components_vs_single_gpu": _rel_l2(pwz, single[1]),
                    "embedding_vs_single_gpu": _rel_l2(pzd, single[0]),
@@ -648,6 +656,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-p2p", action="store_true", help="--mode shard: ncclAllReduce instead of "
                                                           "the peer-memory all-reduce kernel")
+    ap.add_argument("--pageable", action="store_true", help="e2e: keep the CSR arrays in pageable memory")
     ap.add_argument("--no-checks", action="store_true", help="N > 1: skip the sharded-fit parity checks")
     ap.add_argument("--no-c4", action="store_true", help="skip the 16-member ensemble (config 4) leg")
     ap.add_argument("--cpu-iters", type=int, default=10)
@@ -747,15 +756,19 @@ def main():
 
     # ---- end to end through the public API, HOST buffers ---------------------------------
     sw = np.ones(n_fit, dtype=np.float32)
+    # the step's inputs (the three CSR arrays) start in page-locked HOST memory, as the bench
+    # contract has it: the upload inside the timed call is then one DMA transfer per array
+    # (pageable arrays work the same way through a staged copy; --pageable times that)
+    to_host = (lambda M: M) if args.pageable else _lib.pinned_csr
     if world == 1:
         def e2e_call(n_iter):
             model = plsa.PLSA(n_components=k, n_iter=n_iter, tolerance=0.0, random_state=42,
                               device=device)
-            model.fit(X)
+            model.fit(Xe)
             return model
-        Xe = X
+        Xe = to_host(X)
     else:
-        Xe = X[np.random.RandomState(member_seed).randint(0, n, size=n)]
+        Xe = to_host(X[np.random.RandomState(member_seed).randint(0, n, size=n)])
 
         def e2e_call(n_iter):
             return plsa.plsa_fit(Xe, k, sw, n_iter=n_iter, tolerance=0.0,
@@ -841,7 +854,10 @@ def main():
                                        "it creates the pooled context (pinned staging, device buffers, "
                                        "sort scratch); `seconds` are the calls after it",
                     "call": "PLSA(n_components=%d, n_iter=%d, tolerance=0).fit(X)" % (k, args.steps)
-                    if world == 1 else "plsa_fit(bootstrap member) per rank"},
+                    if world == 1 else "plsa_fit(bootstrap member) per rank",
+                    "host_buffers": "pageable numpy arrays (staged upload)" if args.pageable else
+                    "CSR arrays in page-locked host memory (enstop_b200._lib.pinned_csr); factors are "
+                    "drawn on the host inside the call"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if gather_ms is not None:

@@ -54,6 +54,8 @@ SIGNATURES = {
     "plsa_set_sample_weight": (ctypes.c_int, [_ctx, _f32p]),
     "plsa_pinned_factors": (ctypes.c_int, [_ctx, _i64, _i64, _i32, ctypes.POINTER(_f32p),
                                            ctypes.POINTER(_f32p)]),
+    "plsa_host_alloc": (ctypes.c_int, [_i64, ctypes.POINTER(ctypes.c_void_p)]),
+    "plsa_host_free": (ctypes.c_int, [ctypes.c_void_p]),
     "plsa_get_factors": (ctypes.c_int, [_ctx, _f32p, _f32p]),
     "plsa_stash_topics": (ctypes.c_int, [_ctx, _i32, _i32]),
     "plsa_topics_device": (ctypes.c_int, [_ctx, ctypes.POINTER(ctypes.c_void_p), _i64p]),
@@ -229,6 +231,34 @@ def plan_items(indptr, chunk, align=4):
                             _ptr(out["skip"], _i32p), ctypes.byref(n), ctypes.byref(ns),
                             ctypes.byref(nl)))
     out["n_split"], out["n_slots"] = ns.value, nl.value
+    return out
+
+
+def pinned_empty(shape, dtype):
+    """An uninitialised numpy array in page-locked host memory (freed with the array): uploads
+    from it are plain DMA transfers."""
+    import weakref
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape))
+    ptr = ctypes.c_void_p()
+    check(lib().plsa_host_alloc(count * dtype.itemsize, ctypes.byref(ptr)))
+    buf = (ctypes.c_char * max(1, count * dtype.itemsize)).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+    weakref.finalize(buf, lib().plsa_host_free, ptr)
+    return arr
+
+
+def pinned_csr(X):
+    """A copy of a scipy CSR matrix whose three arrays live in page-locked memory."""
+    import scipy.sparse as sp
+    X = X.tocsr()
+    parts = []
+    for a in (X.data, X.indices, X.indptr):
+        p = pinned_empty(a.shape, a.dtype)
+        p[...] = a
+        parts.append(p)
+    out = sp.csr_matrix(tuple(parts), shape=X.shape, copy=False)
+    out.has_sorted_indices = X.has_sorted_indices
     return out
 
 

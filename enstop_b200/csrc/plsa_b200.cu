@@ -225,6 +225,8 @@ struct plsa_ctx {
         bool peer_ipc[SHARD_MAX_RANKS] = {};
         int n_attached = 0;
         unsigned int seq = 0;
+        size_t red_bytes = 0;       /* one finished-slice buffer of the two-shot exchange */
+        int two_shot = -1;          /* option "p2p_two_shot": -1 from 4 ranks up, 0 never, 1 always */
         bool enabled = true; /* option "p2p" */
         int64_t timeout_ms = 30000; /* option "p2p_timeout_ms": wait for a peer's signal */
     } p2p;
@@ -298,6 +300,13 @@ static cudaError_t h2d_fast(plsa_ctx *ctx, void *dst, const void *src, size_t by
     constexpr size_t CH = plsa_ctx::H2D_CHUNK;
     if (bytes < 8 * CH) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
     cudaError_t e;
+    {   /* a source that is already page-locked (plsa_host_alloc, cudaHostRegister) goes by DMA as
+         * it is: no staging copy, no host threads */
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost)
+            return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        cudaGetLastError(); /* an ordinary pointer is not an error */
+    }
     for (int t = 0; t < T; ++t) {
         if (!ctx->pin[t]) {
             if ((e = cudaHostAlloc((void **)&ctx->pin[t], 2 * CH, cudaHostAllocDefault)) != cudaSuccess ||
@@ -1209,6 +1218,7 @@ API int plsa_ctx_create(int device, plsa_ctx **out)
     if (const char *e = getenv("ENSTOP_B200_TERM_TILE_MIN"))
         ctx->term_tile_min = std::max(1, std::min(100000, atoi(e)));
     if (const char *e = getenv("ENSTOP_B200_DEVICE_PLAN")) ctx->device_plan = atoi(e) != 0;
+    if (const char *e = getenv("ENSTOP_B200_TWO_SHOT")) ctx->p2p.two_shot = atoi(e) < 0 ? -1 : (atoi(e) != 0);
     if (const char *e = getenv("ENSTOP_B200_TILE_KB"))
         ctx->tile_bytes = (int64_t)std::max(1, std::min(220, atoi(e))) * 1024;
     *out = ctx;
@@ -1564,6 +1574,26 @@ API int plsa_pinned_factors(plsa_ctx *ctx, int64_t n_docs, int64_t n_terms, int3
     }
     *p_z_given_d = reinterpret_cast<float *>(ctx->pin_factors);
     *p_w_given_z = reinterpret_cast<float *>(ctx->pin_factors + a);
+    return PLSA_OK;
+}
+
+/* Page-locked host memory for the caller's own buffers (e.g. the CSR arrays of a corpus that
+ * is fitted repeatedly): uploads from it skip the staging copy. */
+API int plsa_host_alloc(int64_t bytes, void **ptr)
+{
+    if (!ptr || bytes < 0) return PLSA_EINVAL;
+    *ptr = nullptr;
+    const cudaError_t e = cudaHostAlloc(ptr, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        g_err = std::string("host_alloc: ") + cudaGetErrorString(e);
+        return e == cudaErrorMemoryAllocation ? PLSA_ENOMEM : PLSA_ECUDA;
+    }
+    return PLSA_OK;
+}
+
+API int plsa_host_free(void *ptr)
+{
+    if (ptr) cudaFreeHost(ptr);
     return PLSA_OK;
 }
 
@@ -2025,14 +2055,47 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                 ProfScope ps(ctx, PLSA_PROF_NORMALIZE, s2);
                 ctx->p2p.seq += 1;
                 p2p_used = true;
-                ShardReduceArgs ra{};
                 const int me = shard_rank(ctx);
+                const size_t sig_off = 2 * ctx->p2p.part_bytes + 2 * ctx->p2p.red_bytes;
+                const bool two_shot = ctx->p2p.two_shot > 0 || (ctx->p2p.two_shot < 0 && n_ranks >= 4);
+                if (two_shot) { /* each rank adds its slice of the rows, the finished slices are exchanged */
+                    ShardTwoShotArgs ta{};
+                    for (int p = 0; p < n_ranks; ++p) {
+                        char *base = (p == me) ? ctx->p2p.block.as<char>() : (char *)ctx->p2p.peer_base[p];
+                        ta.part[p] = reinterpret_cast<const float *>(base + (ctx->p2p.seq & 1u) * ctx->p2p.part_bytes);
+                        ta.red[p] = reinterpret_cast<float *>(base + 2 * ctx->p2p.part_bytes +
+                                                              (ctx->p2p.seq & 1u) * ctx->p2p.red_bytes);
+                        ta.peer_sig[p] = reinterpret_cast<unsigned int *>(base + sig_off);
+                        ta.peer_sig2[p] = reinterpret_cast<unsigned int *>(base + sig_off + 64);
+                    }
+                    ta.my_sig = reinterpret_cast<volatile unsigned int *>(ctx->p2p.block.as<char>() + sig_off);
+                    ta.my_sig2 = reinterpret_cast<volatile unsigned int *>(ctx->p2p.block.as<char>() + sig_off + 64);
+                    ta.out = ctx->B[nB].as<float>();
+                    ta.colpart = ctx->colpart2.as<double>();
+                    ta.err = ctx->p2p.err.as<int>();
+                    ta.rows = c.m;
+                    ta.slice_rows = cdiv(std::max<int64_t>(c.m, 1), n_ranks);
+                    ta.stride = ctx->strideB;
+                    ta.kp = kp;
+                    ta.n_ranks = n_ranks;
+                    ta.rank = me;
+                    ta.seq = ctx->p2p.seq;
+                    ta.timeout_clocks = (long long)ctx->p2p.timeout_ms * 2000000LL;
+                    shard_slice_reduce_kernel<<<colsum_grid, 256, 0, s2>>>(ta);
+                    shard_slice_gather_kernel<<<colsum_grid, 256, 0, s2>>>(ta);
+                    colsum_final_kernel<<<1, 256, 0, s2>>>(
+                        ctx->colpart2.as<double>(), colsum_grid, kp,
+                        reinterpret_cast<float *>(ctx->scale.p) + (size_t)nB * kp, ctx->colnorm.as<double>());
+                    ctx->launches += 3;
+                    CK(cudaGetLastError());
+                } else {
+                ShardReduceArgs ra{};
                 char *sig0 = nullptr;
                 for (int p = 0; p < n_ranks; ++p) {
                     char *base = (p == me) ? ctx->p2p.block.as<char>() : (char *)ctx->p2p.peer_base[p];
                     ra.part[p] = reinterpret_cast<const float *>(base + (ctx->p2p.seq & 1u) * ctx->p2p.part_bytes);
-                    ra.peer_sig[p] = reinterpret_cast<unsigned int *>(base + 2 * ctx->p2p.part_bytes);
-                    if (p == me) sig0 = base + 2 * ctx->p2p.part_bytes;
+                    ra.peer_sig[p] = reinterpret_cast<unsigned int *>(base + sig_off);
+                    if (p == me) sig0 = base + sig_off;
                 }
                 ra.my_sig = reinterpret_cast<volatile unsigned int *>(sig0);
                 ra.out = ctx->B[nB].as<float>();
@@ -2051,6 +2114,7 @@ API int plsa_em(plsa_ctx *ctx, int32_t n_iter, int32_t n_iter_per_test, double t
                     reinterpret_cast<float *>(ctx->scale.p) + (size_t)nB * kp, ctx->colnorm.as<double>());
                 ctx->launches += 2;
                 CK(cudaGetLastError());
+                }
             } else if (sharded) {
                 ProfScope ps(ctx, PLSA_PROF_NORMALIZE, s2);
                 if ((rc = shard_allreduce(ctx, ctx->B[nB].p, (size_t)c.m * ctx->strideB, false, s2)))
@@ -2199,6 +2263,10 @@ API int plsa_set_option(plsa_ctx *ctx, const char *name, int64_t value)
     }
     if (!strcmp(name, "p2p")) { /* sharded fit: 0 = NCCL all-reduce even when peers are attached */
         ctx->p2p.enabled = value != 0;
+        return PLSA_OK;
+    }
+    if (!strcmp(name, "p2p_two_shot")) { /* -1: from 4 ranks up, 0: one-shot exchange, 1: two-shot */
+        ctx->p2p.two_shot = value < 0 ? -1 : (value != 0);
         return PLSA_OK;
     }
     if (!strcmp(name, "p2p_timeout_ms")) { /* sharded fit: how long a rank waits for a peer's partial sums */
@@ -2884,8 +2952,11 @@ API int plsa_shard_p2p_prepare(plsa_ctx *ctx, uint64_t *base, int64_t *bytes)
     if (ctx->shard->n_ranks > SHARD_MAX_RANKS)
         return ctx->fail(PLSA_EINVAL, "shard_p2p_prepare: too many ranks for the peer-memory path");
     p2p_release(ctx);
+    /* [partial 0 | partial 1 | finished slice 0 | finished slice 1 | signal words (2 x 64 B)] */
     const size_t part = (size_t)std::max<int64_t>(ctx->cur().m, 1) * ctx->strideB * 4;
-    const size_t total = 2 * part + 256;
+    const size_t red = (size_t)cdiv(std::max<int64_t>(ctx->cur().m, 1), ctx->shard->n_ranks) * ctx->strideB * 4;
+    const size_t total = 2 * part + 2 * red + 256;
+    ctx->p2p.red_bytes = red;
     CK(ctx->p2p.block.ensure(total));
     CK(ctx->p2p.err.ensure(4));
     CK(cudaMemsetAsync(ctx->p2p.block.p, 0, total, ctx->stream));

@@ -825,40 +825,50 @@ __device__ __forceinline__ float4 ld_peer_f4(const float *p)
     return v;
 }
 
-__global__ void __launch_bounds__(256) shard_reduce_kernel(const ShardReduceArgs a)
+/* Signal the peers (CTA 0 only, so a peer sees `seq` once per round) and wait for theirs.
+ * false: a wait timed out, now or earlier in this fit (*err): do not wait or add stale sums. */
+__device__ __forceinline__ bool shard_handshake(unsigned int *const *peer_sig, volatile unsigned int *my_sig,
+                                                int n_ranks, int rank, unsigned int seq,
+                                                long long timeout_clocks, int *err, int *give_up)
 {
-    __shared__ double sm[256][4];
-    __shared__ int give_up;
-    /* a wait that timed out earlier in this fit: do not wait (or add stale sums) again */
-    if (*reinterpret_cast<volatile int *>(a.err)) return;
-    if (threadIdx.x == 0) give_up = 0;
-    /* (1) + (2): every CTA signals nothing but waits itself; CTA 0 does the signalling, so a
-     * peer sees `seq` exactly once per iteration */
-    if (blockIdx.x == 0 && (int)threadIdx.x < a.n_ranks && (int)threadIdx.x != a.rank) {
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_sig[threadIdx.x] + a.rank),
-                     "r"(a.seq) : "memory");
-    }
+    if (threadIdx.x == 0) *give_up = *reinterpret_cast<volatile int *>(err);
     __syncthreads();
-    if ((int)threadIdx.x < a.n_ranks && (int)threadIdx.x != a.rank) {
+    const bool dead = *give_up != 0; /* one read per CTA: the whole CTA takes the same branch */
+    __syncthreads();
+    if (dead) return false;
+    if (blockIdx.x == 0 && (int)threadIdx.x < n_ranks && (int)threadIdx.x != rank) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_sig[threadIdx.x] + rank), "r"(seq) : "memory");
+    }
+    if ((int)threadIdx.x < n_ranks && (int)threadIdx.x != rank) {
         const long long t0 = clock64();
         unsigned int v;
         for (;;) {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v)
-                         : "l"(const_cast<unsigned int *>(a.my_sig) + threadIdx.x) : "memory");
-            if ((int)(v - a.seq) >= 0) break;
-            if (clock64() - t0 > a.timeout_clocks) {
-                give_up = 1;
+                         : "l"(const_cast<unsigned int *>(my_sig) + threadIdx.x) : "memory");
+            if ((int)(v - seq) >= 0) break;
+            if (clock64() - t0 > timeout_clocks) {
+                *give_up = 1;
                 break;
             }
             __nanosleep(200);
         }
     }
     __syncthreads();
-    if (give_up) {
-        if (threadIdx.x == 0) *a.err = 1;
-        return;
+    if (*give_up) {
+        if (threadIdx.x == 0) *err = 1;
+        return false;
     }
+    return true;
+}
+
+__global__ void __launch_bounds__(256) shard_reduce_kernel(const ShardReduceArgs a)
+{
+    __shared__ double sm[256][4];
+    __shared__ int give_up;
+    /* (1) + (2) */
+    if (!shard_handshake(a.peer_sig, a.my_sig, a.n_ranks, a.rank, a.seq, a.timeout_clocks, a.err, &give_up))
+        return;
     /* (3) + (4): kp/4 consecutive threads along a row, 256/(kp/4) rows at a time */
     const int nv = a.kp >> 2;
     const int64_t per = (a.rows + gridDim.x - 1) / gridDim.x;
@@ -888,6 +898,91 @@ __global__ void __launch_bounds__(256) shard_reduce_kernel(const ShardReduceArgs
             for (int s2 = 0; s2 < nsub; ++s2) acc += sm[s2 * nv + (z >> 2)][z & 3];
             a.colpart[(int64_t)blockIdx.x * a.kp + z] = acc;
         }
+    }
+}
+
+/* ---- two-shot variant (4 ranks and up) ----------------------------------------------------------
+ * The one-shot kernel above reads (G-1) x the whole matrix per rank over NVLink.  Here rank r
+ * first adds only ITS slice of the rows (m / G of them) from all ranks, in rank order, and
+ * publishes the finished slice in a second exchange buffer; a second kernel then fetches the
+ * other ranks' finished slices and takes the column sums of the complete matrix.  2 (G-1)/G of
+ * the matrix per rank instead of (G-1): a quarter of the wire traffic at G = 8, the same sums
+ * (every element is still the sum of the ranks' partials in rank order), bit-identical on all
+ * ranks.  Two signal rounds per iteration: "my partial #seq is complete" (sig) and "my slice
+ * #seq is complete" (sig2). */
+struct ShardTwoShotArgs {
+    const float *part[SHARD_MAX_RANKS];       /* every rank's partial, [rows, stride] */
+    float *red[SHARD_MAX_RANKS];              /* every rank's finished slice, [slice_rows, stride]; [rank] is local */
+    unsigned int *peer_sig[SHARD_MAX_RANKS];  /* first round: word [rank] of rank p's array is ours */
+    unsigned int *peer_sig2[SHARD_MAX_RANKS]; /* second round */
+    volatile unsigned int *my_sig, *my_sig2;
+    float *out;                               /* local complete P(w|z)^T [rows, stride] */
+    double *colpart;                          /* [grid, kp] (second kernel) */
+    int *err;
+    int64_t rows, slice_rows;                 /* rank p owns rows [p * slice_rows, min(rows, (p+1) * slice_rows)) */
+    int32_t stride, kp, n_ranks, rank;
+    unsigned int seq;
+    long long timeout_clocks;
+};
+
+/* shot 1: this rank's slice = sum of all ranks' partials, into `out` and into the exchange buffer */
+__global__ void __launch_bounds__(256) shard_slice_reduce_kernel(const ShardTwoShotArgs a)
+{
+    __shared__ int give_up;
+    if (!shard_handshake(a.peer_sig, a.my_sig, a.n_ranks, a.rank, a.seq, a.timeout_clocks, a.err, &give_up))
+        return;
+    const int nv = a.kp >> 2;
+    const int64_t s0 = (int64_t)a.rank * a.slice_rows, s1 = min(a.rows, s0 + a.slice_rows);
+    const int64_t per = (max((int64_t)0, s1 - s0) + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = s0 + (int64_t)blockIdx.x * per, r1 = min(s1, r0 + per);
+    const int nsub = 256 / nv, sub = (int)threadIdx.x / nv, q = (int)threadIdx.x - sub * nv;
+    if (sub >= nsub) return;
+    for (int64_t r = r0 + sub; r < r1; r += nsub) {
+        const int64_t off = r * a.stride + 4 * q;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = 0; p < a.n_ranks; ++p) {
+            const float4 v = (p == a.rank) ? *reinterpret_cast<const float4 *>(a.part[p] + off)
+                                           : ld_peer_f4(a.part[p] + off);
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        *reinterpret_cast<float4 *>(a.out + off) = t;
+        *reinterpret_cast<float4 *>(a.red[a.rank] + (r - s0) * a.stride + 4 * q) = t;
+    }
+}
+
+/* shot 2: fetch the other ranks' finished slices, column sums of the whole matrix */
+__global__ void __launch_bounds__(256) shard_slice_gather_kernel(const ShardTwoShotArgs a)
+{
+    __shared__ double sm[256][4];
+    __shared__ int give_up;
+    if (!shard_handshake(a.peer_sig2, a.my_sig2, a.n_ranks, a.rank, a.seq, a.timeout_clocks, a.err, &give_up))
+        return;
+    const int nv = a.kp >> 2;
+    const int64_t per = (a.rows + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(a.rows, r0 + per);
+    const int nsub = 256 / nv, sub = (int)threadIdx.x / nv, q = (int)threadIdx.x - sub * nv;
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+    if (sub < nsub) {
+        for (int64_t r = r0 + sub; r < r1; r += nsub) {
+            const int64_t off = r * a.stride + 4 * q;
+            const int owner = (int)(r / a.slice_rows);
+            float4 t;
+            if (owner == a.rank) {
+                t = *reinterpret_cast<const float4 *>(a.out + off);
+            } else {
+                t = ld_peer_f4(a.red[owner] + (r - (int64_t)owner * a.slice_rows) * a.stride + 4 * q);
+                *reinterpret_cast<float4 *>(a.out + off) = t;
+            }
+            c0 += (double)t.x; c1 += (double)t.y; c2 += (double)t.z; c3 += (double)t.w;
+        }
+    }
+    sm[threadIdx.x][0] = c0; sm[threadIdx.x][1] = c1;
+    sm[threadIdx.x][2] = c2; sm[threadIdx.x][3] = c3;
+    __syncthreads();
+    for (int z = threadIdx.x; z < a.kp; z += 256) {
+        double acc = 0.0;
+        for (int s2 = 0; s2 < nsub; ++s2) acc += sm[s2 * nv + (z >> 2)][z & 3];
+        a.colpart[(int64_t)blockIdx.x * a.kp + z] = acc;
     }
 }
 

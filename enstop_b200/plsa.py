@@ -231,6 +231,8 @@ def plsa_fit_shard(X_rows, k, p_z_given_d_rows, p_w_given_z, sample_weight_rows,
     ok = False
     try:
         ctx.set_option("p2p", 1)
+        # exchange shape: -1 = two-shot (reduce a slice, gather the slices) from 4 ranks up
+        ctx.set_option("p2p_two_shot", int(os.environ.get("ENSTOP_B200_TWO_SHOT", "-1")))
         ctx.upload_csr(_as_csr(X_rows))
         ctx.set_shard(comm)
         ctx.set_factors(np.ascontiguousarray(p_z_given_d_rows, dtype=np.float32),

@@ -89,6 +89,10 @@ int plsa_set_factors(plsa_ctx *ctx, const float *p_z_given_d, const float *p_w_g
  * inside plsa_upload_csr* / plsa_prepare on the same context. */
 int plsa_pinned_factors(plsa_ctx *ctx, int64_t n_docs, int64_t n_terms, int32_t k,
                         float **p_z_given_d, float **p_w_given_z);
+/* Page-locked host memory for the caller's own buffers (cudaHostAlloc, portable): an upload
+ * whose source lies in it is one DMA transfer, without the staging copy pageable memory needs. */
+int plsa_host_alloc(int64_t bytes, void **ptr);
+int plsa_host_free(void *ptr);
 /* sample_weight [n_docs] or NULL for all ones (plsa.py:1144). */
 int plsa_set_sample_weight(plsa_ctx *ctx, const float *sample_weight);
 /* Either output may be NULL. */

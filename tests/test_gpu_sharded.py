@@ -89,6 +89,24 @@ def test_two_gpu_sharded_fit_matches_oracle(corpus, k, weighted, p2p, monkeypatc
 
 
 @pytest.mark.skipif(_lib.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("k", [10, 20, 128])
+def test_two_shot_exchange_is_the_one_shot_exchange(corpus, k, monkeypatch):
+    """Both exchanges add the ranks' partial sums in rank order (shard_reduce_kernel /
+    shard_slice_reduce_kernel + shard_slice_gather_kernel): same bits, same trace."""
+    X = corpus
+    sw = np.ones(X.shape[0], dtype=np.float32)
+    kw = dict(n_iter=25, n_iter_per_test=5, tolerance=0.0, random_state=5)
+    out = []
+    for two_shot in ("0", "1"):
+        monkeypatch.setenv("ENSTOP_B200_TWO_SHOT", two_shot)
+        out.append(plsa.plsa_fit(X, k, sw, devices=[0, 1], return_info=True, **kw))
+    (pzd0, pwz0, i0), (pzd1, pwz1, i1) = out
+    assert i0["p2p"] and i1["p2p"]
+    assert np.array_equal(pzd0, pzd1) and np.array_equal(pwz0, pwz1)
+    assert np.array_equal(np.asarray(i0["ll_trace"]), np.asarray(i1["ll_trace"]))
+
+
+@pytest.mark.skipif(_lib.device_count() < 2, reason="needs 2 GPUs")
 def test_two_gpu_estimator(corpus):
     X = corpus
     m2 = PLSA(n_components=8, n_iter=20, tolerance=0.0, random_state=1, devices=[0, 1]).fit(X)
