@@ -20,6 +20,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
+#include <stdio.h>
 #include <thread>
 #include <vector>
 
@@ -145,6 +147,34 @@ struct Stream {
 
 } // namespace
 
+/* The factors go to the GPU next (plsa_set_factors, a DMA read of page-locked memory): written
+ * with ordinary stores by several cores they sit dirty in those cores' caches and the DMA engine
+ * snoops them out line by line (measured: 8 MB at 6 GB/s instead of 45).  Streaming stores put
+ * them in memory. */
+static inline void store_streaming(float *dst, const float *src, int64_t n)
+{
+#if defined(__AVX2__)
+    auto one = [&](int64_t c) {
+        int bits;
+        memcpy(&bits, src + c, 4);
+        _mm_stream_si32(reinterpret_cast<int *>(dst + c), bits);
+    };
+    int64_t c = 0;
+    for (; c < n && ((uintptr_t)(dst + c) & 15u); ++c) one(c);
+    for (; c + 4 <= n; c += 4) _mm_stream_ps(dst + c, _mm_loadu_ps(src + c));
+    for (; c < n; ++c) one(c);
+#else
+    memcpy(dst, src, sizeof(float) * (size_t)n);
+#endif
+}
+
+static inline void store_fence()
+{
+#if defined(__AVX2__)
+    _mm_sfence();
+#endif
+}
+
 /* rows [r0, r1) of the draw from a generator state positioned at the first word of row r0 */
 static int draw_rows(uint32_t *key, int32_t *pos, int64_t r0, int64_t r1, int64_t cols, float *out,
                      double *out_f64)
@@ -153,8 +183,10 @@ static int draw_rows(uint32_t *key, int32_t *pos, int64_t r0, int64_t r1, int64_
     s.key = key;
     s.pos = *pos;
     s.temper_from(s.pos < MT_N ? s.pos : MT_N);
-    double *buf = (double *)malloc(sizeof(double) * (size_t)(cols > 0 ? cols : 1));
+    /* one row of doubles, then the same row as floats */
+    double *buf = (double *)malloc((sizeof(double) + sizeof(float)) * (size_t)(cols > 0 ? cols : 1));
     if (!buf) return PLSA_ENOMEM;
+    float *row32 = reinterpret_cast<float *>(buf + (cols > 0 ? cols : 1));
     for (int64_t r = r0; r < r1; ++r) {
         s.fill(buf, cols);
         double marginal = 0.0;
@@ -164,16 +196,18 @@ static int draw_rows(uint32_t *key, int32_t *pos, int64_t r0, int64_t r1, int64_
         if (marginal > 0.0) {
             for (int64_t c = 0; c < cols; ++c) {
                 const double v = buf[c] / marginal;
-                o[c] = (float)v;
+                row32[c] = (float)v;
                 if (o64) o64[c] = v;
             }
         } else {
             for (int64_t c = 0; c < cols; ++c) {
-                o[c] = (float)buf[c];
+                row32[c] = (float)buf[c];
                 if (o64) o64[c] = buf[c];
             }
         }
+        store_streaming(o, row32, cols);
     }
+    store_fence();
     free(buf);
     *pos = s.pos;
     return PLSA_OK;
@@ -208,7 +242,7 @@ static int init_threads()
         if (cores <= 0) cores = (int)std::thread::hardware_concurrency();
         int ranks = 1;
         if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
-        return std::max(1, std::min(4, cores / ranks / 2));
+        return std::max(1, std::min(8, cores / ranks / 2));
     }();
     return n;
 }
@@ -229,30 +263,66 @@ API int plsa_host_random_rows(uint32_t *key, int32_t *pos, int64_t rows, int64_t
     if (!key || !pos || !out || rows < 0 || cols < 0 || *pos < 0 || *pos > MT_N) return PLSA_EINVAL;
     const int64_t total = rows * cols;
     int T = init_threads();
-    if (total < (int64_t)1 << 18 || rows < 2 * T) T = 1;
+    if (total < (int64_t)1 << 18) T = 1;
+    if (rows < 2 * T) T = (int)std::max<int64_t>(1, rows / 2); /* few, long rows (P(w|z)): fewer slices */
     if (T == 1) return draw_rows(key, pos, 0, rows, cols, out, out_f64);
-    struct Slice { uint32_t key[MT_N]; int32_t pos; int64_t r0, r1; int rc; };
-    std::vector<Slice> slices((size_t)T);
+    /* Worker t can start once this thread has skipped the slices before it, so equal slices
+     * would finish one after the other.  A slice costs ~7.5x more to draw than to skip (2.25 against
+     * 0.3 ns per word, scripts/time_init.py): slices shrinking by 1/8 per worker finish together.  The last slice is drawn by this
+     * thread on the caller's state, which is then where a serial draw would have left it. */
+    struct Slice { uint32_t key[MT_N]; int32_t pos; int64_t r0, r1; int rc; double t0, t1; };
+    std::vector<Slice> slices((size_t)(T - 1));
+    static const bool profile = getenv("ENSTOP_B200_INIT_PROFILE") != nullptr; /* slice time line on stderr */
+    const double ratio = 7.0 / 8.0;
+    const auto clk0 = std::chrono::steady_clock::now();
+    auto now_ms = [clk0]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - clk0).count(); };
+    std::vector<double> skip_done((size_t)T, 0.0);
+    std::vector<int64_t> cut((size_t)T + 1, 0);
+    {
+        double w = 1.0, sum = 0.0;
+        std::vector<double> share((size_t)T);
+        for (int t = 0; t < T; ++t, w *= ratio) sum += (share[(size_t)t] = w);
+        double acc = 0.0;
+        for (int t = 0; t < T; ++t) {
+            acc += share[(size_t)t];
+            cut[(size_t)t + 1] = std::min<int64_t>(rows, (int64_t)((double)rows * acc / sum + 0.5));
+        }
+        cut[(size_t)T] = rows;
+    }
     std::vector<std::thread> workers;
     try {
-        for (int t = 0; t < T; ++t) {
+        for (int t = 0; t + 1 < T; ++t) {
             Slice &sl = slices[(size_t)t];
-            sl.r0 = rows * t / T;
-            sl.r1 = rows * (t + 1) / T;
+            sl.r0 = cut[(size_t)t];
+            sl.r1 = cut[(size_t)t + 1];
             sl.rc = PLSA_OK;
             memcpy(sl.key, key, sizeof(sl.key));
             sl.pos = *pos;
-            workers.emplace_back([&sl, cols, out, out_f64]() {
+            workers.emplace_back([&sl, cols, out, out_f64, now_ms]() {
+                sl.t0 = now_ms();
                 sl.rc = draw_rows(sl.key, &sl.pos, sl.r0, sl.r1, cols, out, out_f64);
+                sl.t1 = now_ms();
             });
             skip_words(key, pos, 2 * (sl.r1 - sl.r0) * cols); /* the caller's state: behind this slice */
+            skip_done[(size_t)t] = now_ms();
         }
     } catch (...) { /* thread creation failed: finish what was started, report */
         for (auto &w : workers) w.join();
         return PLSA_ENOMEM;
     }
+    const double t_last0 = now_ms();
+    const int rc_last = draw_rows(key, pos, cut[(size_t)T - 1], rows, cols, out, out_f64);
+    const double t_last1 = now_ms();
     for (auto &w : workers) w.join();
+    if (profile) {
+        for (int t = 0; t + 1 < T; ++t)
+            fprintf(stderr, "[init] slice %d rows %lld: thread %.3f..%.3f ms, skipped by %.3f\n", t,
+                    (long long)(slices[(size_t)t].r1 - slices[(size_t)t].r0), slices[(size_t)t].t0,
+                    slices[(size_t)t].t1, skip_done[(size_t)t]);
+        fprintf(stderr, "[init] last slice rows %lld: %.3f..%.3f ms, joined %.3f\n",
+                (long long)(rows - cut[(size_t)T - 1]), t_last0, t_last1, now_ms());
+    }
     for (const Slice &sl : slices)
         if (sl.rc != PLSA_OK) return sl.rc;
-    return PLSA_OK;
+    return rc_last;
 }

@@ -188,6 +188,9 @@ struct plsa_ctx {
     cudaEvent_t ev_ll = nullptr;
     bool overlap = true;     /* doc pass and term pass of an iteration on two streams */
     cudaStream_t stream2 = nullptr;
+    bool presort_opt = false;      /* option "presort": sort by term while the values upload */
+    bool presorted = false;        /* the base corpus' term sort is queued on stream2 */
+    cudaEvent_t ev_presort = nullptr, ev_cols = nullptr, ev_d2h = nullptr;
     /* pinned staging for host->device copies of pageable memory (see h2d_fast) */
     static constexpr int H2D_THREADS = 4; /* at most; h2d_threads() of them are used */
     static constexpr size_t H2D_CHUNK = (size_t)4 << 20;
@@ -711,71 +714,102 @@ static int build_items_device(plsa_ctx *ctx, const int32_t *d_indptr, int64_t ro
 /* ---- term-major copy ---------------------------------------------------------------------- */
 /* Stable radix sort of the entry numbers by column: within a term the documents stay in
  * ascending order, so the summation order — and the result — is reproducible. */
-static int build_term_major(plsa_ctx *ctx)
+/* First half of the term-major build: the stable sort of the stored entries by term — keys and
+ * permutation only, no values — and the term row pointers.  `cols` (the uploaded column
+ * indices, still in their staging buffer) lets plsa_upload_csr start it on `s` = the second
+ * stream as soon as the indices have arrived, while the values are still crossing PCIe
+ * (option "presort"); otherwise the keys are read from the interleaved entries. */
+static int term_major_sort(plsa_ctx *ctx, const Corpus &c, const int32_t *cols, cudaStream_t s)
 {
-    Corpus &c = ctx->cur();
     const int64_t nnz = c.nnz, n = c.n, m = c.m;
-    cudaStream_t s = ctx->stream;
     /* scratch (20 B per entry) is kept with the context for the next corpus unless it is
      * large: repeated fits then skip seven cudaMalloc/cudaFree pairs */
     DevBuf &rows_exp = ctx->scratch[0], &keys_in = ctx->scratch[1], &perm_in = ctx->scratch[2],
            &perm_out = ctx->scratch[3], &keys_out = ctx->scratch[4], &tindptr = ctx->t_indptr,
            &tmp = ctx->scratch[6];
-    auto cleanup = [&]() {
-        if (nnz > ((int64_t)32 << 20))
-            for (DevBuf &b : ctx->scratch) b.release();
-    };
-#define CKT(expr)                                                                             \
-    do {                                                                                      \
-        cudaError_t e_ = (expr);                                                              \
-        if (e_ != cudaSuccess) {                                                              \
-            cleanup();                                                                        \
-            return ctx->fail(e_ == cudaErrorMemoryAllocation ? PLSA_ENOMEM : PLSA_ECUDA,      \
-                             std::string(#expr) + ": " + cudaGetErrorString(e_));            \
-        }                                                                                     \
-    } while (0)
     const size_t nz = (size_t)std::max<int64_t>(nnz, 1);
-    CKT(ctx->t_ent.ensure(ent_bytes(nnz)));
-    CKT(cudaMemsetAsync(ctx->t_ent.as<int2>() + nnz, 0, ENT_PAD * sizeof(int2), s));
-    ctx->h_tindptr.assign((size_t)m + 1, 0);
-    CKT(tindptr.ensure((size_t)(m + 1) * 4));
-    if (nnz == 0) CKT(cudaMemsetAsync(tindptr.p, 0, (size_t)(m + 1) * 4, s));
-    if (nnz > 0) {
-        CKT(rows_exp.ensure(nz * 4));
-        CKT(keys_in.ensure(nz * 4));
-        CKT(perm_in.ensure(nz * 4));
-        CKT(perm_out.ensure(nz * 4));
-        CKT(keys_out.ensure(nz * 4));
-        CKT(tindptr.ensure((size_t)(m + 1) * 4));
-        const int T = 256;
-        expand_rows_kernel<<<(unsigned)cdiv(n * 32, T), T, 0, s>>>(
-            c.indptr.as<int32_t>(), n, c.ent.as<int2>(), rows_exp.as<int32_t>(),
-            keys_in.as<int32_t>());
-        iota_kernel<<<(unsigned)cdiv(nnz, T), T, 0, s>>>(perm_in.as<int32_t>(), nnz);
-        ctx->launches += 2;
-        int end_bit = 1;
-        while (((int64_t)1 << end_bit) < m) ++end_bit;
-        size_t tmp_bytes = 0;
-        CKT(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in.as<int32_t>(),
-                                            keys_out.as<int32_t>(), perm_in.as<int32_t>(),
-                                            perm_out.as<int32_t>(), (int)nnz, 0, end_bit, s));
-        CKT(tmp.ensure(tmp_bytes));
-        CKT(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_in.as<int32_t>(),
-                                            keys_out.as<int32_t>(), perm_in.as<int32_t>(),
-                                            perm_out.as<int32_t>(), (int)nnz, 0, end_bit, s));
-        permute_kernel<<<(unsigned)cdiv(nnz, T), T, 0, s>>>(perm_out.as<int32_t>(), nnz,
-                                                           rows_exp.as<int32_t>(),
-                                                           c.ent.as<int2>(), ctx->t_ent.as<int2>());
-        lower_bound_kernel<<<(unsigned)cdiv(m + 1, T), T, 0, s>>>(keys_out.as<int32_t>(), nnz, m,
-                                                                 tindptr.as<int32_t>());
-        ctx->launches += 2;
-        CKT(cudaGetLastError());
-        CKT(cudaMemcpyAsync(ctx->h_tindptr.data(), tindptr.p, (size_t)(m + 1) * 4,
-                            cudaMemcpyDeviceToHost, s));
-        CKT(cudaStreamSynchronize(s));
+    CK(tindptr.ensure((size_t)(m + 1) * 4));
+    if (nnz == 0) {
+        CK(cudaMemsetAsync(tindptr.p, 0, (size_t)(m + 1) * 4, s));
+        return PLSA_OK;
     }
-    cleanup();
-#undef CKT
+    CK(rows_exp.ensure(nz * 4));
+    CK(keys_in.ensure(nz * 4));
+    CK(perm_in.ensure(nz * 4));
+    CK(perm_out.ensure(nz * 4));
+    CK(keys_out.ensure(nz * 4));
+    const int T = 256;
+    expand_rows_kernel<<<(unsigned)cdiv(n * 32, T), T, 0, s>>>(
+        c.indptr.as<int32_t>(), n, cols ? nullptr : c.ent.as<int2>(), cols, rows_exp.as<int32_t>(),
+        keys_in.as<int32_t>());
+    iota_kernel<<<(unsigned)cdiv(nnz, T), T, 0, s>>>(perm_in.as<int32_t>(), nnz);
+    ctx->launches += 2;
+    int end_bit = 1;
+    while (((int64_t)1 << end_bit) < m) ++end_bit;
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in.as<int32_t>(),
+                                       keys_out.as<int32_t>(), perm_in.as<int32_t>(),
+                                       perm_out.as<int32_t>(), (int)nnz, 0, end_bit, s));
+    CK(tmp.ensure(tmp_bytes));
+    CK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_in.as<int32_t>(),
+                                       keys_out.as<int32_t>(), perm_in.as<int32_t>(),
+                                       perm_out.as<int32_t>(), (int)nnz, 0, end_bit, s));
+    lower_bound_kernel<<<(unsigned)cdiv(m + 1, T), T, 0, s>>>(keys_out.as<int32_t>(), nnz, m,
+                                                             tindptr.as<int32_t>());
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return PLSA_OK;
+}
+
+static void release_sort_scratch(plsa_ctx *ctx, int64_t nnz)
+{
+    if (nnz > ((int64_t)32 << 20))
+        for (DevBuf &b : ctx->scratch) b.release();
+}
+
+static int build_term_major(plsa_ctx *ctx)
+{
+    Corpus &c = ctx->cur();
+    const int64_t nnz = c.nnz, m = c.m;
+    cudaStream_t s = ctx->stream;
+    /* the sort may already be under way (or done) on the second stream: plsa_upload_csr */
+    const bool presorted = ctx->presorted && !ctx->use_boot;
+    ctx->presorted = false;
+    int rc = PLSA_OK;
+    if (presorted) {
+        cudaError_t e = cudaStreamWaitEvent(s, ctx->ev_presort, 0);
+        if (e != cudaSuccess) rc = ctx->fail(PLSA_ECUDA, std::string("presort wait: ") + cudaGetErrorString(e));
+    } else {
+        if (ctx->ev_presort) cudaStreamWaitEvent(s, ctx->ev_presort, 0); /* same scratch buffers */
+        rc = term_major_sort(ctx, c, nullptr, s);
+    }
+    auto failed = [&](cudaError_t e, const char *what) {
+        release_sort_scratch(ctx, nnz);
+        return ctx->fail(e == cudaErrorMemoryAllocation ? PLSA_ENOMEM : PLSA_ECUDA,
+                         std::string(what) + ": " + cudaGetErrorString(e));
+    };
+    if (rc != PLSA_OK) {
+        release_sort_scratch(ctx, nnz);
+        return rc;
+    }
+    cudaError_t e;
+    if ((e = ctx->t_ent.ensure(ent_bytes(nnz))) != cudaSuccess) return failed(e, "term-major entries");
+    if ((e = cudaMemsetAsync(ctx->t_ent.as<int2>() + nnz, 0, ENT_PAD * sizeof(int2), s)) != cudaSuccess)
+        return failed(e, "term-major padding");
+    ctx->h_tindptr.assign((size_t)m + 1, 0);
+    if (nnz > 0) {
+        const int T = 256;
+        permute_kernel<<<(unsigned)cdiv(nnz, T), T, 0, s>>>(ctx->scratch[3].as<int32_t>(), nnz,
+                                                           ctx->scratch[0].as<int32_t>(),
+                                                           c.ent.as<int2>(), ctx->t_ent.as<int2>());
+        ctx->launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess) return failed(e, "permute_kernel");
+        if ((e = cudaMemcpyAsync(ctx->h_tindptr.data(), ctx->t_indptr.p, (size_t)(m + 1) * 4,
+                                 cudaMemcpyDeviceToHost, s)) != cudaSuccess)
+            return failed(e, "term row pointers");
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return failed(e, "term-major build");
+    }
+    release_sort_scratch(ctx, nnz);
     ctx->term_items.ready = false;
     ctx->t_ready = true;
     ctx->t_weighted_ready = false;
@@ -1145,6 +1179,7 @@ static int compact_a(plsa_ctx *ctx, int which, cudaStream_t stream)
 
 static void corpus_changed(plsa_ctx *ctx)
 {
+    ctx->presorted = false; /* set again by an upload that started the sort */
     ctx->tiles.ready = false;
     ctx->tiles.tail_items.ready = false;
     ctx->tterm.ready = false;
@@ -1230,8 +1265,12 @@ API int plsa_ctx_destroy(plsa_ctx *ctx)
     if (!ctx) return PLSA_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2); /* a term sort nobody waited for */
     prof_collect(ctx);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->ev_presort) cudaEventDestroy(ctx->ev_presort);
+    if (ctx->ev_cols) cudaEventDestroy(ctx->ev_cols);
+    if (ctx->ev_d2h) cudaEventDestroy(ctx->ev_d2h);
     for (Corpus *c : {&ctx->base, &ctx->boot}) {
         c->indptr.release(); c->ent.release();
     }
@@ -1313,10 +1352,25 @@ static int upload_csr_impl(plsa_ctx *ctx, const int32_t *indptr, const int32_t *
     CK(cudaMemsetAsync(c.ent.as<int2>() + nnz, 0, ENT_PAD * sizeof(int2), ctx->stream));
     CK(cudaMemcpyAsync(c.indptr.p, indptr, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
     int bad = 0;
+    bool presort_started = false;
     if (nnz > 0) {
         CK(ctx->up_cols.ensure((size_t)nnz * 4));
         CK(ctx->up_vals.ensure((size_t)nnz * vsz));
+        if (ctx->ev_presort) /* an earlier sort that nobody waited for still reads up_cols */
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_presort, 0));
         CK(h2d_fast(ctx, ctx->up_cols.p, indices, (size_t)nnz * 4));
+        if (ctx->presort_opt && ctx->stream2) {
+            /* the indices are enough to sort the entries by term: do that on the second stream
+             * while the values follow over PCIe (build_term_major picks the result up) */
+            if (!ctx->ev_cols) CK(cudaEventCreateWithFlags(&ctx->ev_cols, cudaEventDisableTiming));
+            if (!ctx->ev_presort) CK(cudaEventCreateWithFlags(&ctx->ev_presort, cudaEventDisableTiming));
+            CK(cudaEventRecord(ctx->ev_cols, ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_cols, 0));
+            const int src = term_major_sort(ctx, c, ctx->up_cols.as<int32_t>(), ctx->stream2);
+            if (src != PLSA_OK) return src;
+            CK(cudaEventRecord(ctx->ev_presort, ctx->stream2));
+            presort_started = true;
+        }
         CK(h2d_fast(ctx, ctx->up_vals.p, data, (size_t)nnz * vsz));
         const unsigned grid = (unsigned)cdiv(nnz, 256);
         int2 *ent = c.ent.as<int2>();
@@ -1335,6 +1389,7 @@ static int upload_csr_impl(plsa_ctx *ctx, const int32_t *indptr, const int32_t *
     CK(cudaStreamSynchronize(ctx->stream));
     if (bad) return ctx->fail(PLSA_EINVAL, "upload: column index out of range");
     c.h_indptr.swap(h_indptr);
+    ctx->presorted = presort_started;
     return PLSA_OK;
 }
 
@@ -1618,6 +1673,34 @@ API int plsa_set_sample_weight(plsa_ctx *ctx, const float *sample_weight)
     return PLSA_OK;
 }
 
+/* pageable destination: the copy of a large result out of the page-locked bounce buffer is cut
+ * into slices, one per thread — most of its cost is the first touch of the destination's fresh
+ * pages, which parallelises */
+static void host_copy_mt(void *dst, const void *src, size_t bytes)
+{
+    const int T = bytes >= ((size_t)2 << 20) ? h2d_threads() : 1;
+    if (T <= 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t slice = (bytes / T + 4095) / 4096 * 4096;
+    std::thread th[plsa_ctx::H2D_THREADS];
+    for (int t = 1; t < T; ++t) {
+        const size_t lo = std::min(bytes, slice * (size_t)t), hi = std::min(bytes, lo + slice);
+        th[t] = std::thread([=]() { memcpy((char *)dst + lo, (const char *)src + lo, hi - lo); });
+    }
+    memcpy(dst, src, std::min(bytes, slice));
+    for (int t = 1; t < T; ++t) th[t].join();
+}
+
+static bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes attr;
+    const bool yes = cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError(); /* an ordinary pointer is not an error */
+    return yes;
+}
+
 API int plsa_get_factors(plsa_ctx *ctx, float *p_z_given_d, float *p_w_given_z)
 {
     CHECK_CTX(ctx);
@@ -1626,25 +1709,48 @@ API int plsa_get_factors(plsa_ctx *ctx, float *p_z_given_d, float *p_w_given_z)
     const int64_t n = c.n, m = c.m;
     const int k = ctx->k;
     CK(ctx->stage.ensure((size_t)std::max<int64_t>(std::max(n, m), 1) * k * 4));
-    if (p_z_given_d && n > 0) {
+    const size_t bytes_a = (p_z_given_d && n > 0) ? (size_t)n * k * 4 : 0;
+    const size_t bytes_b = (p_w_given_z && m > 0) ? (size_t)m * k * 4 : 0;
+    /* A device-to-host copy into pageable memory goes through the driver's own staging at a
+     * fraction of the PCIe rate.  Large results land in the context's page-locked factor buffer
+     * by DMA instead and are copied out by a few threads; P(z|d) is copied out while P(w|z) is
+     * still on its way.  A page-locked destination (plsa_host_alloc) takes the DMA directly. */
+    const bool bounce_a = bytes_a >= ((size_t)1 << 20) && !is_pinned_host(p_z_given_d);
+    const bool bounce_b = bytes_b >= ((size_t)1 << 20) && !is_pinned_host(p_w_given_z);
+    char *pin_a = nullptr, *pin_b = nullptr;
+    if (bounce_a || bounce_b) {
+        float *fa = nullptr, *fb = nullptr;
+        int rc = plsa_pinned_factors(ctx, n, m, k, &fa, &fb);
+        if (rc != PLSA_OK) return rc;
+        pin_a = reinterpret_cast<char *>(fa);
+        pin_b = reinterpret_cast<char *>(fb);
+        if (!ctx->ev_d2h) CK(cudaEventCreateWithFlags(&ctx->ev_d2h, cudaEventDisableTiming));
+    }
+    if (bytes_a) {
         unpack_rows_kernel<<<(unsigned)cdiv(n * k, 256), 256, 0, ctx->stream>>>(
             ctx->A[ctx->curA].as<float>(), nullptr, ctx->stage.as<float>(), n, k, ctx->strideA, 0);
         ctx->launches++;
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(p_z_given_d, ctx->stage.p, (size_t)n * k * 4, cudaMemcpyDeviceToHost,
-                           ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaMemcpyAsync(bounce_a ? (void *)pin_a : (void *)p_z_given_d, ctx->stage.p, bytes_a,
+                           cudaMemcpyDeviceToHost, ctx->stream));
+        if (bounce_a) CK(cudaEventRecord(ctx->ev_d2h, ctx->stream));
+        else CK(cudaStreamSynchronize(ctx->stream));
     }
-    if (p_w_given_z && m > 0) {
+    if (bytes_b) {
         unpack_rows_kernel<<<(unsigned)cdiv(m * k, 256), 256, 0, ctx->stream>>>(
             ctx->B[ctx->curB].as<float>(), cur_scale(ctx), ctx->stage.as<float>(), m, k,
             ctx->strideB, 1);
         ctx->launches++;
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(p_w_given_z, ctx->stage.p, (size_t)m * k * 4, cudaMemcpyDeviceToHost,
-                           ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaMemcpyAsync(bounce_b ? (void *)pin_b : (void *)p_w_given_z, ctx->stage.p, bytes_b,
+                           cudaMemcpyDeviceToHost, ctx->stream));
     }
+    if (bounce_a) {
+        CK(cudaEventSynchronize(ctx->ev_d2h));
+        host_copy_mt(p_z_given_d, pin_a, bytes_a);
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (bounce_b) host_copy_mt(p_w_given_z, pin_b, bytes_b);
     return PLSA_OK;
 }
 
@@ -2263,6 +2369,10 @@ API int plsa_set_option(plsa_ctx *ctx, const char *name, int64_t value)
     }
     if (!strcmp(name, "p2p")) { /* sharded fit: 0 = NCCL all-reduce even when peers are attached */
         ctx->p2p.enabled = value != 0;
+        return PLSA_OK;
+    }
+    if (!strcmp(name, "presort")) { /* 1: plsa_upload_csr sorts the entries by term while the values upload */
+        ctx->presort_opt = value != 0;
         return PLSA_OK;
     }
     if (!strcmp(name, "p2p_two_shot")) { /* -1: from 4 ranks up, 0: one-shot exchange, 1: two-shot */

@@ -1167,15 +1167,15 @@ __global__ void interleave_kernel(const int32_t *__restrict__ cols, const T *__r
 
 /* per entry: its row (expanded indptr) and its column as a sort key; one warp per row */
 __global__ void expand_rows_kernel(const int32_t *__restrict__ indptr, int64_t n_rows,
-                                   const int2 *__restrict__ ent, int32_t *__restrict__ rows_out,
-                                   int32_t *__restrict__ keys_out)
+                                   const int2 *__restrict__ ent, const int32_t *__restrict__ cols,
+                                   int32_t *__restrict__ rows_out, int32_t *__restrict__ keys_out)
 {
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= n_rows) return;
     const int lane = threadIdx.x & 31;
     for (int32_t p = indptr[r] + lane; p < indptr[r + 1]; p += 32) {
         rows_out[p] = (int32_t)r;
-        keys_out[p] = ent[p].x;
+        keys_out[p] = cols ? cols[p] : ent[p].x; /* cols: the upload's staging copy of the indices */
     }
 }
 

@@ -157,7 +157,9 @@ def fit_members_on_device(X, k, device, members, seeds, **kwargs):
         try:
             ctx = _lib.acquire_context(device)   # pooled: creating and destroying a context
             contexts[lane] = ctx                 # (pinned staging, ~20 device buffers) costs more
-            ctx.upload_csr(X)                    # than several members
+                                                 # than several members
+            ctx.set_option("presort", 0)         # the members sort their bootstrap samples,
+            ctx.upload_csr(X)                    # not this base corpus
             for slot, r in enumerate(lanes[lane]):
                 kw = dict(kwargs)
                 kw["random_state"] = seeds[r]

@@ -125,6 +125,8 @@ class _Staging:
 
     def _run(self, X, k, refit):
         try:
+            # a full fit needs the term-major copy: its sort starts while the values upload
+            self.ctx.set_option("presort", 0 if refit else 1)
             self.ctx.upload_csr(X)
             self.ctx.prepare(k, refit)
         except BaseException as exc:  # re-raised by wait()
@@ -233,6 +235,7 @@ def plsa_fit_shard(X_rows, k, p_z_given_d_rows, p_w_given_z, sample_weight_rows,
         ctx.set_option("p2p", 1)
         # exchange shape: -1 = two-shot (reduce a slice, gather the slices) from 4 ranks up
         ctx.set_option("p2p_two_shot", int(os.environ.get("ENSTOP_B200_TWO_SHOT", "-1")))
+        ctx.set_option("presort", 1)
         ctx.upload_csr(_as_csr(X_rows))
         ctx.set_shard(comm)
         ctx.set_factors(np.ascontiguousarray(p_z_given_d_rows, dtype=np.float32),

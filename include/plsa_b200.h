@@ -141,7 +141,13 @@ int plsa_launch_count(const plsa_ctx *ctx, int64_t *launches);
  * "tiled" (-1: automatic by corpus size, 0: never, 1: wherever possible — the doc pass reads
  * the rows of the most frequent terms from a TMA-staged shared-memory tile, csrc/plsa_tile.cuh),
  * "tile_kb" (shared memory of that tile per CTA, 1..220),
- * "p2p_timeout_ms" (sharded fit: bound of a rank's wait for a peer's partial sums). */
+ * "presort" (1: plsa_upload_csr starts the sort of the entries by term — needed by a full fit,
+ * not by a refit — on a second stream as soon as the column indices have arrived, while the
+ * values are still being copied; default 0),
+ * "p2p_timeout_ms" (sharded fit: bound of a rank's wait for a peer's partial sums),
+ * "p2p_two_shot" (sharded fit over peer memory: -1 = from 4 ranks up every rank adds only its
+ * slice of the terms and the finished slices are exchanged, 0 = every rank adds everything,
+ * 1 = always slices; same bits either way). */
 int plsa_set_option(plsa_ctx *ctx, const char *name, int64_t value);
 /* Host-only (no device): the work items a pass over a CSR with these row pointers would launch,
  * in launch order.  A row longer than `chunk` entries is cut into equal chunks that write

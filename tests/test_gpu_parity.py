@@ -388,6 +388,46 @@ def test_device_plan_is_the_host_plan(chunk, golden_c1_planted):
         assert 0 < tail["indptr"][-1] < X.nnz
 
 
+@pytest.fixture(scope="module")
+def corpus_9m():
+    return synth.make_corpus(60000, 30000, 9_000_000, seed=11)   # 36 MB per array: chunked copies
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_presort_during_upload_changes_nothing(pinned, corpus_9m):
+    """Option "presort": the sort of the entries by term runs on the second stream from the
+    uploaded column indices while the values are still being copied.  Same term-major copy,
+    so the same factors bit for bit — from pageable and from page-locked inputs, through the
+    estimator (which switches it on) and through a bare context, twice in a row, followed by
+    a corpus of another shape through the same pooled context."""
+    X = corpus_9m
+    Xin = _lib.pinned_csr(X) if pinned else X
+    k = 12
+    rng = np.random.RandomState(4)
+    pzd0 = rng.rand(X.shape[0], k).astype(np.float32)
+    pwz0 = rng.rand(k, X.shape[1]).astype(np.float32)
+    sw = np.ones(X.shape[0], dtype=np.float32)
+    out = []
+    for presort in (0, 1, 1):
+        with _lib.Context(0) as ctx:
+            ctx.set_option("presort", presort)
+            ctx.upload_csr(Xin)
+            out.append(plsa.plsa_fit(Xin, k, sw, init=(pzd0, pwz0), n_iter=7, tolerance=0.0,
+                                     context=ctx))
+    for a, b in out[1:]:
+        assert np.array_equal(a, out[0][0]) and np.array_equal(b, out[0][1])
+    est = plsa.plsa_fit(Xin, k, sw, init=(pzd0, pwz0), n_iter=7, tolerance=0.0)
+    assert np.array_equal(est[0], out[0][0]) and np.array_equal(est[1], out[0][1])
+    # another corpus through the pooled context the estimator path just used, then this one again
+    Y = synth.make_corpus(2500, 4000, 60000, seed=12)
+    plsa.plsa_fit(Y, 5, np.ones(Y.shape[0], dtype=np.float32), n_iter=3, tolerance=0.0, random_state=1)
+    again = plsa.plsa_fit(Xin, k, sw, init=(pzd0, pwz0), n_iter=7, tolerance=0.0)
+    assert np.array_equal(again[0], out[0][0]) and np.array_equal(again[1], out[0][1])
+    # a refit (no term-major copy wanted) after a presorted upload
+    emb = plsa.plsa_refit(Xin, est[1], sw, n_iter=5, random_state=3)
+    assert emb.shape == (X.shape[0], k) and np.allclose(emb.sum(axis=1), 1.0, atol=1e-4)
+
+
 def test_properties_at_config3_size():
     """BASELINE config 3 in full (the config-2 matrix at k = 128, the wide-row kernels
     row_pass_kernel<32, 4, ...>): size-independent properties and the exact log-likelihood of the

@@ -90,6 +90,24 @@ def test_host_random_rows_is_numpy_bit_for_bit(seed, burn, rows, cols):
     assert a.get_state()[2] == b.get_state()[2]
 
 
+@pytest.mark.parametrize("seed,burn,rows,cols", [(42, 13, 40000, 10), (3, 5, 7, 60001),
+                                                 (11, 622, 30011, 13), (8, 0, 17, 20000)])
+def test_host_random_rows_parallel_slices(seed, burn, rows, cols):
+    """From 2^18 values the draw is cut into slices of unequal length, one per thread, each
+    started from the state skipped ahead to its first word; the last slice runs on the
+    caller's state: same bits, same final state as numpy's serial draw."""
+    a, b = np.random.RandomState(seed), np.random.RandomState(seed)
+    if burn:
+        a.randint(0, 10, size=burn)
+        b.randint(0, 10, size=burn)
+    x = a.rand(rows, cols)
+    x /= np.cumsum(x, axis=1)[:, -1:]          # left-to-right float64 marginal (utils.py:25-29)
+    y32 = _lib.random_rows(b, rows, cols)
+    assert np.array_equal(x.astype(np.float32), y32)
+    assert np.array_equal(a.rand(7), b.rand(7))
+    assert a.get_state()[2] == b.get_state()[2]
+
+
 def test_fast_random_init_equals_plsa_init(golden_c1_zipf):
     g, X = golden_c1_zipf
     fast = plsa._random_init_f32(X.shape[0], X.shape[1], 10, np.random.RandomState(42))
