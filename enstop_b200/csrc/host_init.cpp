@@ -175,42 +175,75 @@ static inline void store_fence()
 #endif
 }
 
-/* rows [r0, r1) of the draw from a generator state positioned at the first word of row r0 */
-static int draw_rows(uint32_t *key, int32_t *pos, int64_t r0, int64_t r1, int64_t cols, float *out,
-                     double *out_f64)
+/* R rows at a time.  The left-to-right marginal of a row is one chain of dependent additions
+ * (4 cycles each: more than everything else done per value).  Long rows (P(w|z)) are drawn four
+ * at a time and their four chains advance together; every row's sum is still taken in the
+ * reference's order.  Short rows (R = 1) overlap by themselves in the out-of-order window. */
+template <int R>
+static int draw_rows_by(uint32_t *key, int32_t *pos, int64_t r0, int64_t r1, int64_t cols, float *out,
+                        double *out_f64)
 {
     Stream s;
     s.key = key;
     s.pos = *pos;
     s.temper_from(s.pos < MT_N ? s.pos : MT_N);
-    /* one row of doubles, then the same row as floats */
-    double *buf = (double *)malloc((sizeof(double) + sizeof(float)) * (size_t)(cols > 0 ? cols : 1));
+    const size_t w = (size_t)(cols > 0 ? cols : 1);
+    double *buf = (double *)malloc(sizeof(double) * R * w + sizeof(float) * w);
     if (!buf) return PLSA_ENOMEM;
-    float *row32 = reinterpret_cast<float *>(buf + (cols > 0 ? cols : 1));
-    for (int64_t r = r0; r < r1; ++r) {
-        s.fill(buf, cols);
-        double marginal = 0.0;
-        for (int64_t c = 0; c < cols; ++c) marginal += buf[c]; /* left to right, as utils.py:25-29 */
-        float *o = out + r * cols;
-        double *o64 = out_f64 ? out_f64 + r * cols : nullptr;
-        if (marginal > 0.0) {
-            for (int64_t c = 0; c < cols; ++c) {
-                const double v = buf[c] / marginal;
-                row32[c] = (float)v;
-                if (o64) o64[c] = v;
+    float *row32 = reinterpret_cast<float *>(buf + R * w);
+    for (int64_t r = r0; r < r1; r += R) {
+        const int nr = (int)std::min<int64_t>(R, r1 - r);
+        s.fill(buf, (int64_t)nr * cols); /* rng.rand(rows, cols) is row-major: nr whole rows */
+        double marginal[R];
+        if (R == 4 && nr == 4) {
+            const double *b0 = buf, *b1 = buf + cols, *b2 = buf + 2 * cols, *b3 = buf + 3 * cols;
+            double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
+            for (int64_t c = 0; c < cols; ++c) { /* left to right, as utils.py:25-29 */
+                m0 += b0[c];
+                m1 += b1[c];
+                m2 += b2[c];
+                m3 += b3[c];
             }
+            marginal[0] = m0; marginal[1 % R] = m1; marginal[2 % R] = m2; marginal[3 % R] = m3;
         } else {
-            for (int64_t c = 0; c < cols; ++c) {
-                row32[c] = (float)buf[c];
-                if (o64) o64[c] = buf[c];
+            for (int j = 0; j < nr; ++j) {
+                double m = 0.0;
+                for (int64_t c = 0; c < cols; ++c) m += buf[j * cols + c];
+                marginal[j] = m;
             }
         }
-        store_streaming(o, row32, cols);
+        for (int j = 0; j < nr; ++j) {
+            const double *src = buf + j * cols;
+            float *o = out + (r + j) * cols;
+            double *o64 = out_f64 ? out_f64 + (r + j) * cols : nullptr;
+            const double m = marginal[j];
+            if (m > 0.0) {
+                for (int64_t c = 0; c < cols; ++c) {
+                    const double v = src[c] / m;
+                    row32[c] = (float)v;
+                    if (o64) o64[c] = v;
+                }
+            } else {
+                for (int64_t c = 0; c < cols; ++c) {
+                    row32[c] = (float)src[c];
+                    if (o64) o64[c] = src[c];
+                }
+            }
+            store_streaming(o, row32, cols);
+        }
     }
     store_fence();
     free(buf);
     *pos = s.pos;
     return PLSA_OK;
+}
+
+/* rows [r0, r1) of the draw from a generator state positioned at the first word of row r0 */
+static int draw_rows(uint32_t *key, int32_t *pos, int64_t r0, int64_t r1, int64_t cols, float *out,
+                     double *out_f64)
+{
+    return cols >= 256 ? draw_rows_by<4>(key, pos, r0, r1, cols, out, out_f64)
+                       : draw_rows_by<1>(key, pos, r0, r1, cols, out, out_f64);
 }
 
 /* advance the state by `words` outputs without producing them (twist only: the tempering, the
@@ -231,7 +264,7 @@ static void skip_words(uint32_t *key, int32_t *pos, int64_t words)
 }
 
 /* worker threads of one draw: the cores this process may use, shared with the other ranks of
- * the box (LOCAL_WORLD_SIZE) and with the upload threads running beside the draw */
+ * the box (LOCAL_WORLD_SIZE); the upload thread beside the draw mostly waits for DMA */
 static int init_threads()
 {
     static const int n = [] {
@@ -242,7 +275,7 @@ static int init_threads()
         if (cores <= 0) cores = (int)std::thread::hardware_concurrency();
         int ranks = 1;
         if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
-        return std::max(1, std::min(8, cores / ranks / 2));
+        return std::max(1, std::min(8, cores / ranks));
     }();
     return n;
 }
