@@ -1678,7 +1678,16 @@ API int plsa_set_sample_weight(plsa_ctx *ctx, const float *sample_weight)
  * pages, which parallelises */
 static void host_copy_mt(void *dst, const void *src, size_t bytes)
 {
-    const int T = bytes >= ((size_t)2 << 20) ? h2d_threads() : 1;
+    static const int threads = [] { /* the rank's share of the cores, at most H2D_THREADS */
+        cpu_set_t set;
+        int cores = 0;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set);
+        if (cores <= 0) cores = (int)std::thread::hardware_concurrency();
+        int ranks = 1;
+        if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+        return std::max(1, std::min(plsa_ctx::H2D_THREADS, cores / ranks));
+    }();
+    const int T = bytes >= ((size_t)2 << 20) ? threads : 1;
     if (T <= 1) {
         memcpy(dst, src, bytes);
         return;
