@@ -19,6 +19,7 @@
 #include <sched.h>
 
 #include <algorithm>
+#include <set>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -3128,10 +3129,18 @@ API int plsa_shard_p2p_attach(plsa_ctx *ctx, int32_t peer_rank, int32_t peer_dev
         int can = 0;
         CK(cudaDeviceCanAccessPeer(&can, ctx->device, peer_device));
         if (!can) return ctx->fail(PLSA_ECUDA, "shard_p2p_attach: no peer access between the devices");
-        cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
-        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
-        else if (e != cudaSuccess)
-            return ctx->fail(PLSA_ECUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        /* once per (device, peer) and process: asking again is an error return, harmless but
+         * noisy under compute-sanitizer */
+        static std::mutex mu;
+        static std::set<std::pair<int, int>> enabled;
+        std::lock_guard<std::mutex> lock(mu);
+        if (!enabled.count({ctx->device, peer_device})) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError(); /* NCCL was first */
+            else if (e != cudaSuccess)
+                return ctx->fail(PLSA_ECUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+            enabled.insert({ctx->device, peer_device});
+        }
         ptr = (void *)(uintptr_t)base;
     }
     if (!ptr) return ctx->fail(PLSA_EINVAL, "shard_p2p_attach: null peer block");
