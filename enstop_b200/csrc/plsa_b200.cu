@@ -326,7 +326,9 @@ static cudaError_t h2d_fast(plsa_ctx *ctx, void *dst, const void *src, size_t by
     cudaError_t errs[plsa_ctx::H2D_THREADS];
     std::thread th[plsa_ctx::H2D_THREADS];
     const int device = ctx->device;
-    for (int t = 0; t < T; ++t) {
+    int started = 0;
+    try { /* no C++ exception crosses the C ABI */
+    for (int t = 0; t < T; ++t, ++started) {
         errs[t] = cudaSuccess;
         th[t] = std::thread([=, &errs]() {
             cudaSetDevice(device);
@@ -349,7 +351,10 @@ static cudaError_t h2d_fast(plsa_ctx *ctx, void *dst, const void *src, size_t by
             errs[t] = cudaStreamSynchronize(ctx->pin_stream[t]);
         });
     }
-    for (int t = 0; t < T; ++t) th[t].join();
+    } catch (...) {
+    }
+    for (int t = 0; t < started; ++t) th[t].join();
+    if (started < T) return cudaErrorOperatingSystem; /* could not start a copy thread */
     for (int t = 0; t < T; ++t)
         if (errs[t] != cudaSuccess) return errs[t];
     return cudaSuccess;
@@ -1695,12 +1700,20 @@ static void host_copy_mt(void *dst, const void *src, size_t bytes)
     }
     const size_t slice = (bytes / T + 4095) / 4096 * 4096;
     std::thread th[plsa_ctx::H2D_THREADS];
-    for (int t = 1; t < T; ++t) {
-        const size_t lo = std::min(bytes, slice * (size_t)t), hi = std::min(bytes, lo + slice);
-        th[t] = std::thread([=]() { memcpy((char *)dst + lo, (const char *)src + lo, hi - lo); });
+    int started = 1;
+    try { /* no C++ exception crosses the C ABI: what no thread took is copied here */
+        for (; started < T; ++started) {
+            const size_t lo = std::min(bytes, slice * (size_t)started), hi = std::min(bytes, lo + slice);
+            th[started] = std::thread([=]() { memcpy((char *)dst + lo, (const char *)src + lo, hi - lo); });
+        }
+    } catch (...) {
     }
     memcpy(dst, src, std::min(bytes, slice));
-    for (int t = 1; t < T; ++t) th[t].join();
+    if (started < T) {
+        const size_t lo = std::min(bytes, slice * (size_t)started);
+        memcpy((char *)dst + lo, (const char *)src + lo, bytes - lo);
+    }
+    for (int t = 1; t < started; ++t) th[t].join();
 }
 
 static bool is_pinned_host(const void *p)
