@@ -404,6 +404,14 @@ class EnsembleTopics(BaseEstimator, TransformerMixin):
 
     Attributes: ``components_`` (stable topics, [n_components_, n_words]), ``embedding_``
     (P(z|d) [n_docs, n_components_]), ``training_data_``, ``n_components_``.
+
+    Clustering stage: the reference clusters with ``hdbscan`` and, for the default
+    ``topic_combination="hellinger_umap"``, embeds the topics with ``umap`` first.  Here
+    HDBSCAN is ``sklearn.cluster.HDBSCAN`` and, when ``umap`` cannot be imported, the default
+    falls back — with a warning — to ``"hellinger"`` (HDBSCAN on the exact all-pairs Hellinger
+    matrix, computed on the GPU): ``n_components_`` and ``components_`` can then differ from
+    what the reference's UMAP route would select.  The members' topics and the
+    membership-weighted cluster representatives are the reference's.
     """
 
     def __init__(self, n_components=10, model="plsa", init="random", n_starts=16, min_samples=3,
