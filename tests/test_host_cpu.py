@@ -108,6 +108,22 @@ def test_host_random_rows_parallel_slices(seed, burn, rows, cols):
     assert a.get_state()[2] == b.get_state()[2]
 
 
+@pytest.mark.parametrize("offset", [1, 2, 3])
+def test_host_random_rows_into_a_misaligned_buffer(offset):
+    """The factors are written with streaming stores (16-byte where aligned, 4-byte at the
+    edges): any float32-aligned destination works, e.g. a view that starts 4 bytes in."""
+    rows, cols = 301, 21
+    a, b = np.random.RandomState(17), np.random.RandomState(17)
+    flat = np.full(rows * cols + 8, -1.0, dtype=np.float32)
+    out = flat[offset:offset + rows * cols].reshape(rows, cols)
+    got = _lib.random_rows(b, rows, cols, out=out)
+    assert got is out
+    x = a.rand(rows, cols)
+    x /= np.cumsum(x, axis=1)[:, -1:]
+    assert np.array_equal(out, x.astype(np.float32))
+    assert np.all(flat[:offset] == -1.0) and np.all(flat[offset + rows * cols:] == -1.0)
+
+
 def test_fast_random_init_equals_plsa_init(golden_c1_zipf):
     g, X = golden_c1_zipf
     fast = plsa._random_init_f32(X.shape[0], X.shape[1], 10, np.random.RandomState(42))
